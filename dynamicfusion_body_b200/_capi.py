@@ -1,0 +1,108 @@
+"""ctypes binding of include/dfb.h (libdfb_b200.so).
+
+There is deliberately no fallback: if the CUDA library has not been built, importing this module
+raises, and every product entry point fails with it.  Build with `python -m dynamicfusion_body_b200.build`
+(or `__graft_entry__.build()`).
+"""
+import ctypes as C
+import os
+
+DFB_MAX_K = 8
+DFB_MAX_VIEWS = 8
+DFB_NODE_REC_FLOATS = 12
+MODE_HYBRID = 0
+MODE_EXACT = 1
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libdfb_b200.so")
+
+c_f32p = C.POINTER(C.c_float)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+c_u16p = C.POINTER(C.c_uint16)
+c_u32p = C.POINTER(C.c_uint32)
+c_i32p = C.POINTER(C.c_int32)
+
+
+class Volume(C.Structure):
+    _fields_ = [("tsdf", C.c_void_p), ("weight", C.c_void_p),
+                ("rx", C.c_int), ("ry", C.c_int), ("rz", C.c_int),
+                ("x0", C.c_int), ("x1", C.c_int)]
+
+
+class WarpField(C.Structure):
+    _fields_ = [("node_rec", C.c_void_p), ("node_pos", C.c_void_p), ("node_dq", C.c_void_p),
+                ("node_w", C.c_void_p), ("n_nodes", C.c_int), ("k", C.c_int), ("knn", C.c_void_p),
+                ("has_lw", C.c_int), ("lw_is_f32", C.c_int), ("lw", C.c_double * 8)]
+
+
+class Views(C.Structure):
+    _fields_ = [("n_views", C.c_int), ("depth", C.c_void_p * DFB_MAX_VIEWS),
+                ("rows", C.c_int), ("cols", C.c_int),
+                ("K", C.c_double * 9), ("Kinv", C.c_double * 9),
+                ("has_extrinsics", C.c_int), ("E", (C.c_double * 12) * DFB_MAX_VIEWS)]
+
+
+class Workspace(C.Structure):
+    _fields_ = [("list", C.c_void_p), ("capacity", C.c_uint32), ("counters", C.c_void_p)]
+
+
+def _dp(n):
+    return C.c_double * n
+
+
+def declare(lib, prefix="dfb_", device=True):
+    """Attach argtypes/restype for every entry point of include/dfb.h present in `lib`."""
+    vp = C.c_void_p
+    sig = {
+        "version": ([], C.c_int),
+        "last_error": ([], C.c_char_p),
+        "nodes_pack": ([vp, vp, vp, C.c_int, vp] + ([vp] if device else []), None if not device else C.c_int),
+        "knn_build_volume": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
+        "knn_points": ([vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp], C.c_int),
+        "tsdf_update_projective": ([C.POINTER(Volume), C.POINTER(WarpField), C.POINTER(Views), C.c_double, C.c_double,
+                                    C.c_int, C.POINTER(Workspace), vp, vp, vp], C.c_int),
+        "fuse_depth_rigid": ([C.POINTER(Volume), C.c_int, vp, C.c_int, C.c_int, c_f64p, c_f64p, c_f64p, C.c_double,
+                              c_f64p, C.c_double, C.c_double, C.c_int, C.POINTER(Workspace), vp, vp, vp], C.c_int),
+        "tsdf_update_volume": ([C.POINTER(Volume), C.POINTER(WarpField), vp, C.c_int, C.c_int, C.c_int, C.c_double,
+                                C.c_double, C.c_int, C.POINTER(Workspace), vp, vp], C.c_int),
+        "warp_points": ([vp, vp, C.c_int64, vp, C.POINTER(WarpField), vp, vp] + ([vp] if device else []), C.c_int),
+    }
+    for name, (argtypes, restype) in sig.items():
+        fn = getattr(lib, prefix + name, None)
+        if fn is None:
+            continue
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+_lib = None
+
+
+def lib():
+    """The CUDA library; raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise ImportError(
+                "libdfb_b200.so is not built (%s). There is no CPU fallback: run "
+                "`python -m dynamicfusion_body_b200.build` (needs nvcc)." % LIB_PATH)
+        _lib = declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+class DfbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().dfb_last_error()
+        raise DfbError("libdfb_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+EXPORTS = [
+    "dfb_version", "dfb_last_error", "dfb_nodes_pack", "dfb_knn_build_volume", "dfb_knn_points",
+    "dfb_tsdf_update_projective", "dfb_tsdf_update_volume", "dfb_fuse_depth_rigid", "dfb_warp_points",
+]

@@ -1,0 +1,309 @@
+// dfb_voxel.h -- per-voxel update logic of the three TSDF passes (a1 volume-sampling, a2 rigid
+// projective, a3 warped projective), shared by the CUDA kernels (tsdf.cu) and the CPU logic tests
+// (tests/hostshim/).  See dfb_math.h for the two arithmetic tiers.
+#pragma once
+#include "dfb_math.h"
+
+namespace dfb {
+
+enum { CLS_SKIP = 0, CLS_CLAMP = 1, CLS_UNCERTAIN = 2 };
+
+struct ViewFast {
+    float P[12];  // K * E_v * A_lw   (rows: u*z, v*z, z_k)
+    float L[4];   // third row of E_v * A_lw  (lpos_z)
+};
+
+struct ProjParams {
+    // volume (slab)
+    float* tsdf;
+    float* weight;
+    int rx, ry, rz, x0, x1;
+    // warp field
+    const float4* node_rec;
+    const float* node_pos;
+    const float* node_dq;
+    const float* node_w;
+    const uint16_t* knn;
+    int k;
+    int has_lw, lw_is_f32;
+    double lw[8];
+    // a2 only: grid -> world (pos = scale*(idx - res/2) + center), rigid 3x4 lw
+    int rigid;
+    double g_scale, g_half, g_center[3];
+    double lw34[12];
+    float G[12];  // fp32 affine idx -> lpos (a2 fast tier)
+    // views
+    int n_views, rows, cols, has_E;
+    const float* depth[8];
+    double K[9], Kinv[9];
+    double E[8][12];
+    ViewFast vf[8];
+    float kin[3];    // Kinv row 2, fp32
+    float knorm;     // max abs row sum of K rows 0,1 (error propagation to pixels)
+    float kin_uv;    // |Kinv20| + |Kinv21|
+    float coord_mag; // bound on |coordinates| entering the fp32 chain (error scale)
+    // update
+    double tdist, wmax, scale;
+    float tdist_f, wmax_f;
+    // bookkeeping
+    uint32_t* list;
+    uint32_t capacity;
+    uint32_t* counters;
+    uint8_t* mask_out;
+    uint8_t* frustum_out;
+};
+
+struct VolParams {
+    float* tsdf;
+    float* weight;
+    int rx, ry, rz, x0, x1;
+    const float4* node_rec;
+    const float* node_pos;
+    const float* node_dq;
+    const float* node_w;
+    const uint16_t* knn;
+    int k;
+    int has_lw, lw_is_f32;
+    double lw[8];
+    float A[12];  // fp32 affine of lw (identity when !has_lw)
+    const float* curr;
+    int cx, cy, cz;
+    double tdist, wmax;
+    float tdist_f, wmax_f, coord_mag;
+    uint32_t* list;
+    uint32_t capacity;
+    uint32_t* counters;
+    uint8_t* mask_out;
+};
+
+// ---- fast tier: DQB of k nodes in fp32 --------------------------------------------------------
+// rec layout: [pos.xyz, coef][dq0..3][dq4..7], coef = -log2(e)/(4 w^2)  (exp(-(d/2w)^2) = exp2(coef*d^2))
+// Returns false when the fp32 chain cannot be trusted at all (all weights underflow in the reference's
+// float64 exp, or zero blend) -> caller treats the voxel as uncertain.
+// amin_out: most negative exp argument (natural-log units) among the k nodes: scales the error bound.
+template <int KMAX>
+DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k, float px, float py, float pz, float* out,
+                            float* amin_out) {
+    float a[KMAX];
+    float amax = -3.0e38f, amin = 0.f;
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+        if (i < k) {
+            const float4 r0 = rec[3 * (size_t)ids[i]];
+            const float dx = px - r0.x, dy = py - r0.y, dz = pz - r0.z;
+            a[i] = (dx * dx + dy * dy + dz * dz) * r0.w;
+            amax = fmaxf(amax, a[i]);
+            amin = fminf(amin, a[i]);
+        }
+    }
+    *amin_out = amin * 0.69314718f;
+    if (!(amax > -1000.f)) return false;  // reference exp() near/below its float64 underflow: exact tier
+    float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < KMAX; ++i) {
+        if (i < k) {
+            const float w = exp2f(a[i] - amax);
+            const float4 r1 = rec[3 * (size_t)ids[i] + 1];
+            const float4 r2 = rec[3 * (size_t)ids[i] + 2];
+            b[0] += w * r1.x; b[1] += w * r1.y; b[2] += w * r1.z; b[3] += w * r1.w;
+            b[4] += w * r2.x; b[5] += w * r2.y; b[6] += w * r2.z; b[7] += w * r2.w;
+        }
+    }
+    float n2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) n2 += b[c] * b[c];
+    if (!(n2 > 1e-30f)) return false;
+    float o[3];
+    dq_apply_unnormalised(b, px, py, pz, o);
+    const float inv = 1.0f / n2;
+    out[0] = o[0] * inv; out[1] = o[1] * inv; out[2] = o[2] * inv;
+    return true;
+}
+
+// error bound (voxel units) of the fp32 warp chain against the reference's value
+DFB_HD float pos_err_bound(float coord_mag, float amin_nat) {
+    return 1.1920929e-7f * coord_mag * (32.f - 4.f * amin_nat);
+}
+
+// ---- fast tier: classify one view (a2/a3) -----------------------------------------------------
+// in: (pu,pv,pz) = K*lpos, lz = lpos_z, e = error bound on lpos components.
+// frustum_bit: 1 if certainly inside the image, 0 if certainly outside (only valid if result != UNCERTAIN)
+DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const float* depth, int rows, int cols,
+                         const float* kin, float knorm, float kin_uv, float tdist, int* frustum_bit) {
+    *frustum_bit = 0;
+    const float apz = fabsf(pz);
+    const float ez = e * 4.f;  // |K row 2| is (0,0,1) for a pinhole; 4x head-room for general K
+    if (!(apz > 8.f * ez)) return CLS_UNCERTAIN;  // also catches NaN
+    const float inv = 1.0f / pz;
+    const float u = pu * inv, v = pv * inv;
+    const float eu = (knorm * e + fabsf(u) * ez) / apz + 4.8e-7f * fabsf(u) + 1e-6f;
+    const float ev = (knorm * e + fabsf(v) * ez) / apz + 4.8e-7f * fabsf(v) + 1e-6f;
+    const float umax = (float)(cols - 1), vmax = (float)(rows - 1);
+    // certainly outside?
+    if (u < -eu || u >= umax + eu || v < -ev || v >= vmax + ev) return CLS_SKIP;
+    // certainly inside?
+    if (!(u >= eu && u < umax - eu && v >= ev && v < vmax - ev)) return CLS_UNCERTAIN;
+    *frustum_bit = 1;
+    // candidate pixels (round-half-even both ends of the uncertainty interval)
+    const int u0 = (int)rintf(u - eu), u1 = (int)rintf(u + eu);
+    const int v0 = (int)rintf(v - ev), v1 = (int)rintf(v + ev);
+    const float kz = kin[0] * u + kin[1] * v + kin[2];
+    int cls = -1;
+    for (int vi = v0; vi <= v1; ++vi) {
+        for (int ui = u0; ui <= u1; ++ui) {
+            const float z = -depth[(size_t)vi * cols + ui];
+            int c;
+            if (!(z > 0.f)) {
+                c = CLS_SKIP;
+            } else {
+                const float tl = z * kz - lz;
+                const float et = fabsf(z) * (kin_uv * (eu + ev) + 4.8e-7f * fabsf(kz)) + e + 2.4e-7f * fabsf(lz);
+                if (tl > tdist + et) c = CLS_CLAMP;
+                else if (tl < -tdist - et) c = CLS_SKIP;
+                else return CLS_UNCERTAIN;
+            }
+            if (cls < 0) cls = c;
+            else if (cls != c) return CLS_UNCERTAIN;
+        }
+    }
+    return cls;
+}
+
+// fp32 clamped update of FusionDM.fuseDepths: v' = (scale*v*w + tdist)/(scale*(w+1)); w' = min(w+1, wmax)
+DFB_HD void clamp_update(float& v, float& w, float tdist, float wmax, float scale) {
+    v = (scale * v * w + tdist) / (scale * (1.0f + w));
+    w = fminf(1.0f + w, wmax);
+}
+
+// ---- exact tier: whole-voxel functions --------------------------------------------------------
+// a3 / a2 for one voxel; v,w in/out (float32 storage, float64 arithmetic).  Returns mask bits in
+// *mask, frustum bits in *frus.
+DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, const uint16_t* ids16, float* v_io,
+                                    float* w_io, int* mask, int* frus) {
+    double base[3];
+    if (P.rigid) {
+        // pos = scale * (pos - sdf_center) + center  (core/fusion_dm.py:183,191), float64
+        const double idx[3] = {(double)x, (double)y, (double)z};
+        for (int c = 0; c < 3; ++c) base[c] = dadd(dmul(P.g_scale, dsub(idx[c], P.g_half)), P.g_center[c]);
+    } else {
+        const float p[3] = {(float)x, (float)y, (float)z};
+        int ids[8];
+        for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
+        warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
+                 nullptr, nullptr);
+    }
+    double v = (double)*v_io, w = (double)*w_io;
+    int m = 0, f = 0;
+    for (int vi = 0; vi < P.n_views; ++vi) {
+        double lpos[3];
+        if (P.rigid) {
+            for (int r = 0; r < 3; ++r) lpos[r] = dot4_ref(P.lw34 + 4 * r, base[0], base[1], base[2], 1.0);
+        } else if (P.has_E) {
+            for (int r = 0; r < 3; ++r) lpos[r] = dot4_ref(P.E[vi] + 4 * r, base[0], base[1], base[2], 1.0);
+        } else {
+            lpos[0] = base[0]; lpos[1] = base[1]; lpos[2] = base[2];
+        }
+        const int r = project_fuse_ref(lpos, P.depth[vi], P.rows, P.cols, P.K, P.Kinv, P.tdist, P.scale, P.wmax, &v, &w);
+        if (r & 1) m |= 1 << vi;
+        if (r & 2) f |= 1 << vi;
+    }
+    *v_io = (float)v;
+    *w_io = (float)w;
+    *mask = m;
+    *frus = f;
+}
+
+// fast classification of a voxel for a2/a3.  Returns CLS_UNCERTAIN, or CLS_SKIP/CLS_CLAMP-style result:
+// *mask gets the per-view clamp bits (all certain), *frus the per-view frustum bits.
+template <int KMAX>
+DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus) {
+    float pw[3];
+    float e;
+    if (P.rigid) {
+        pw[0] = (float)x; pw[1] = (float)y; pw[2] = (float)z;
+        e = 1.1920929e-7f * P.coord_mag * 32.f;
+    } else {
+        float amin;
+        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin)) return CLS_UNCERTAIN;
+        e = pos_err_bound(P.coord_mag, amin);
+    }
+    int m = 0, f = 0;
+    for (int vi = 0; vi < P.n_views; ++vi) {
+        const ViewFast& V = P.vf[vi];
+        const float pu = V.P[0] * pw[0] + V.P[1] * pw[1] + V.P[2] * pw[2] + V.P[3];
+        const float pv = V.P[4] * pw[0] + V.P[5] * pw[1] + V.P[6] * pw[2] + V.P[7];
+        const float pz = V.P[8] * pw[0] + V.P[9] * pw[1] + V.P[10] * pw[2] + V.P[11];
+        const float lz = V.L[0] * pw[0] + V.L[1] * pw[1] + V.L[2] * pw[2] + V.L[3];
+        int fb;
+        const int c = classify_view(pu, pv, pz, lz, e, P.depth[vi], P.rows, P.cols, P.kin, P.knorm, P.kin_uv, P.tdist_f, &fb);
+        if (c == CLS_UNCERTAIN) return CLS_UNCERTAIN;
+        if (c == CLS_CLAMP) m |= 1 << vi;
+        if (fb) f |= 1 << vi;
+    }
+    *mask = m;
+    *frus = f;
+    return m ? CLS_CLAMP : CLS_SKIP;
+}
+
+// a1 for one voxel, exact tier.
+DFB_HDN bool voxel_volume_exact(const VolParams& P, int x, int y, int z, const uint16_t* ids16, float* v_io, float* w_io) {
+    const float p[3] = {(float)x, (float)y, (float)z};
+    int ids[8];
+    for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
+    double pw[3];
+    float wi = 0.f;
+    warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, pw, nullptr, &wi);
+    double tl = 0.0;
+    const bool valid = interpolate_tsdf_ref(pw, P.curr, P.cx, P.cy, P.cz, &tl);
+    double v = (double)*v_io, w = (double)*w_io;
+    const bool upd = volume_fuse_ref(valid, tl, wi, P.k, P.tdist, P.wmax, &v, &w);
+    if (upd) { *v_io = (float)v; *w_io = (float)w; }
+    return upd;
+}
+
+// a1 fast classification: CLS_SKIP (certainly outside the live volume), CLS_CLAMP (all 8 corners >= tdist:
+// the update uses min(tdist, tl) = tdist up to 1e-16), else CLS_UNCERTAIN.  wi_out: Q4 weight (fp32).
+template <int KMAX>
+DFB_HD int voxel_volume_classify(const VolParams& P, int x, int y, int z, const uint16_t* ids, float* wi_out) {
+    float pw[3];
+    float e;
+    const float px = (float)x, py = (float)y, pz = (float)z;
+    if (P.k > 0) {
+        float amin;
+        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, px, py, pz, pw, &amin)) return CLS_UNCERTAIN;
+        e = pos_err_bound(P.coord_mag, amin);
+    } else {
+        pw[0] = px; pw[1] = py; pw[2] = pz;
+        e = 1.1920929e-7f * P.coord_mag * 32.f;
+    }
+    const float qx = P.A[0] * pw[0] + P.A[1] * pw[1] + P.A[2] * pw[2] + P.A[3];
+    const float qy = P.A[4] * pw[0] + P.A[5] * pw[1] + P.A[6] * pw[2] + P.A[7];
+    const float qz = P.A[8] * pw[0] + P.A[9] * pw[1] + P.A[10] * pw[2] + P.A[11];
+    const float mx = (float)(P.cx - 1), my = (float)(P.cy - 1), mz = (float)(P.cz - 1);
+    if (qx < -e || qy < -e || qz < -e || qx > mx + e || qy > my + e || qz > mz + e) return CLS_SKIP;
+    if (!(qx >= e && qy >= e && qz >= e && qx <= mx - e && qy <= my - e && qz <= mz - e)) return CLS_UNCERTAIN;
+    // corners of every cell the true position may fall in
+    const int x0 = (int)floorf(qx - e), x1 = (int)ceilf(qx + e);
+    const int y0 = (int)floorf(qy - e), y1 = (int)ceilf(qy + e);
+    const int z0 = (int)floorf(qz - e), z1 = (int)ceilf(qz + e);
+    float mn = 3.0e38f;
+    for (int a = x0; a <= x1; ++a)
+        for (int b = y0; b <= y1; ++b)
+            for (int c = z0; c <= z1; ++c) mn = fminf(mn, P.curr[((size_t)a * P.cy + b) * P.cz + c]);
+    if (!(mn >= P.tdist_f * 1.000001f)) return CLS_UNCERTAIN;
+    if (P.k > 0) {
+        float wi = 0.f;
+        for (int i = 0; i < P.k; ++i) {
+            const float4 r0 = P.node_rec[3 * (size_t)ids[i]];
+            const float nr = norm3_f32_ref(r0.x, r0.y, r0.z, px, py, pz);
+            const float term = fdiv(nr, (float)P.k);
+            wi = (i == 0) ? term : fadd(wi, term);
+        }
+        *wi_out = wi;
+    } else {
+        *wi_out = 1.f;
+    }
+    return CLS_CLAMP;
+}
+
+}  // namespace dfb

@@ -1,0 +1,167 @@
+// knn.cu -- exact k-nearest deformation nodes (scipy KDTree.query semantics, core/fusion.py:175,122).
+//
+// The reference queries a KD-tree per voxel; the result is a pure function of the node positions, which
+// only change in update_graph (core/fusion.py:201-233), so the table is built once per graph revision
+// and reused by every frame / view (uint16 ids, 2k bytes per voxel).
+//
+// Exactness: distances are ranked in fp32 first (node tiles staged in shared memory, one broadcast
+// LDS.128 per node per warp); whenever two of the k+1 best squared distances are closer than the fp32
+// rounding bound the voxel is re-ranked in float64 with the oracle's operation order and the "lower id
+// wins" tie rule.
+#include "common.h"
+#include "dfb_math.h"
+
+using namespace dfb;
+
+namespace {
+
+constexpr int TILE = 1024;
+
+template <int KMAX>
+struct TopK {
+    float d[KMAX + 1];
+    int id[KMAX + 1];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j <= KMAX; ++j) { d[j] = 3.0e38f; id[j] = 0; }
+    }
+    // keep the kk+1 smallest (kk <= KMAX), ascending, stable in id order (strict <)
+    __device__ __forceinline__ void insert(float v, int i, int kk) {
+        if (!(v < d[kk])) return;
+        d[kk] = v; id[kk] = i;
+#pragma unroll
+        for (int j = KMAX; j > 0; --j) {
+            if (j <= kk && d[j] < d[j - 1]) {
+                const float td = d[j]; d[j] = d[j - 1]; d[j - 1] = td;
+                const int ti = id[j]; id[j] = id[j - 1]; id[j - 1] = ti;
+            }
+        }
+    }
+};
+
+// float64 re-rank of one query (rare path).  out: k ids ascending, ties -> lower id.
+template <int KMAX>
+__device__ __noinline__ void knn_exact_f64(float qx, float qy, float qz, const float* node_pos, int n, int k, int* out) {
+    double bd[KMAX];
+    int bi[KMAX];
+    for (int j = 0; j < KMAX; ++j) { bd[j] = 1.0e300; bi[j] = 0; }
+    for (int i = 0; i < n; ++i) {
+        const double dx = dfb::dsub((double)qx, (double)node_pos[3 * i]);
+        const double dy = dfb::dsub((double)qy, (double)node_pos[3 * i + 1]);
+        const double dz = dfb::dsub((double)qz, (double)node_pos[3 * i + 2]);
+        const double d2 = dfb::dadd(dfb::dadd(dfb::dmul(dx, dx), dfb::dmul(dy, dy)), dfb::dmul(dz, dz));
+        if (!(d2 < bd[k - 1])) continue;
+        int j = k - 1;
+        while (j > 0 && d2 < bd[j - 1]) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+        bd[j] = d2; bi[j] = i;
+    }
+    for (int j = 0; j < k; ++j) out[j] = bi[j];
+}
+
+template <int KMAX>
+__device__ __forceinline__ void knn_query(float qx, float qy, float qz, bool active, const float* node_pos, int n, int k,
+                                          float4* tile, int* out) {
+    TopK<KMAX> top;
+    top.init();
+    const int kk = (n > k) ? k : k - 1;  // index of the last tracked slot (k+1 entries when available)
+    for (int base = 0; base < n; base += TILE) {
+        const int cnt = min(TILE, n - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+            tile[j] = make_float4(node_pos[3 * (base + j)], node_pos[3 * (base + j) + 1], node_pos[3 * (base + j) + 2], 0.f);
+        __syncthreads();
+        if (active) {
+#pragma unroll 4
+            for (int j = 0; j < cnt; ++j) {
+                const float4 p = tile[j];
+                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                top.insert(d2, base + j, kk);
+            }
+        }
+    }
+    if (!active) return;
+    bool ambiguous = false;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < kk && top.d[j + 1] - top.d[j] <= 4.0e-6f * top.d[j + 1]) ambiguous = true;
+    if (ambiguous) {
+        knn_exact_f64<KMAX>(qx, qy, qz, node_pos, n, k, out);
+    } else {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) out[j] = top.id[j];
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) knn_volume_kernel(const float* node_pos, int n, int k, int ry, int rz, int x0,
+                                                         uint16_t* knn) {
+    __shared__ float4 tile[TILE];
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int xs = blockIdx.z;
+    const bool in = z < rz;
+    int out[KMAX];
+    knn_query<KMAX>((float)(xs + x0), (float)y, (float)z, in, node_pos, n, k, tile, out);
+    if (!in) return;
+    const size_t i = ((size_t)xs * ry + y) * rz + z;
+    if (KMAX == 4 && k == 4) {
+        uint2 r;
+        r.x = (uint32_t)out[0] | ((uint32_t)out[1] << 16);
+        r.y = (uint32_t)out[2] | ((uint32_t)out[3] << 16);
+        reinterpret_cast<uint2*>(knn)[i] = r;
+    } else {
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k) knn[i * (size_t)k + j] = (uint16_t)out[j];
+    }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(256) knn_points_kernel(const float* pts, int64_t m, const float* node_pos, int n, int k,
+                                                         int32_t* idx) {
+    __shared__ float4 tile[TILE];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = t < m;
+    const int64_t tt = in ? t : 0;
+    int out[KMAX];
+    knn_query<KMAX>(pts[3 * tt], pts[3 * tt + 1], pts[3 * tt + 2], in, node_pos, n, k, tile, out);
+    if (!in) return;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) idx[t * k + j] = out[j];
+}
+
+}  // namespace
+
+extern "C" int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
+                                    uint16_t* knn, dfb_stream_t stream) {
+    DFB_REQUIRE(node_pos && knn, "null pointer");
+    DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K, "k=%d out of range [1,%d]", k, DFB_MAX_K);
+    DFB_REQUIRE(n_nodes >= k && n_nodes <= 65535, "n_nodes=%d must be in [k,65535]", n_nodes);
+    DFB_REQUIRE(rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad grid / slab");
+    DFB_REQUIRE(ry <= 65535 && (x1 - x0) <= 65535, "ry and slab thickness must be <= 65535");
+    const int threads = rz >= 256 ? 256 : ((rz + 31) / 32) * 32;
+    const dim3 grid((rz + threads - 1) / threads, ry, x1 - x0);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k <= 4) knn_volume_kernel<4><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
+    else knn_volume_kernel<8><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
+    DFB_LAUNCH_CHECK("knn_volume_kernel");
+    return DFB_OK;
+}
+
+extern "C" int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
+                              dfb_stream_t stream) {
+    DFB_REQUIRE(pts && node_pos && idx, "null pointer");
+    DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K, "k=%d out of range [1,%d]", k, DFB_MAX_K);
+    DFB_REQUIRE(n_nodes >= k, "n_nodes=%d < k=%d", n_nodes, k);
+    DFB_REQUIRE(m >= 0, "negative point count");
+    if (m == 0) return DFB_OK;
+    const int64_t blocks = (m + 255) / 256;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k <= 4) knn_points_kernel<4><<<(unsigned)blocks, 256, 0, s>>>(pts, m, node_pos, n_nodes, k, idx);
+    else knn_points_kernel<8><<<(unsigned)blocks, 256, 0, s>>>(pts, m, node_pos, n_nodes, k, idx);
+    DFB_LAUNCH_CHECK("knn_points_kernel");
+    return DFB_OK;
+}

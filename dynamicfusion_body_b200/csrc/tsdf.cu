@@ -1,0 +1,310 @@
+// tsdf.cu -- the three TSDF update passes (a1 volume-sampling, a2 rigid projective, a3 warped
+// projective) as a fast HBM-streaming kernel plus a reference-exact clean-up kernel.
+//
+// Pass 1 (`*_fast_kernel`): one thread per voxel, z fastest (coalesced 128 B per warp for v, w and the
+//   kNN table).  The fp32 tier classifies the voxel: certainly not updated (no memory traffic at all
+//   beyond the kNN ids), certainly updated with the clamped value min(tdist, tl) = tdist (read v,w,
+//   fp32 running average, write v,w), or uncertain (inside the truncation band, near the image border,
+//   near a pixel-rounding boundary, ...) -> appended to a work list with one warp-aggregated atomic.
+// Pass 2 (`*_exact_kernel`): a grid-stride kernel over the work list that evaluates the reference's
+//   own arithmetic (dfb_math.h exact tier).  If the list overflowed it re-scans the volume instead.
+#include "common.h"
+#include "dfb_params.h"
+
+using namespace dfb;
+
+namespace {
+
+template <int KMAX>
+__device__ __forceinline__ void load_ids(const uint16_t* knn, size_t i, int k, uint16_t* ids) {
+    if (KMAX == 4) {
+        if (k == 4) {
+            const uint2 r = __ldg(reinterpret_cast<const uint2*>(knn) + i);
+            ids[0] = r.x & 0xffff; ids[1] = r.x >> 16; ids[2] = r.y & 0xffff; ids[3] = r.y >> 16;
+            return;
+        }
+    } else if (k == 8) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(knn) + i);
+        ids[0] = r.x & 0xffff; ids[1] = r.x >> 16; ids[2] = r.y & 0xffff; ids[3] = r.y >> 16;
+        ids[4] = r.z & 0xffff; ids[5] = r.z >> 16; ids[6] = r.w & 0xffff; ids[7] = r.w >> 16;
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+        if (j < k) ids[j] = knn[i * (size_t)k + j];
+}
+
+__device__ __forceinline__ void push_uncertain(bool unc, uint32_t i, uint32_t* list, uint32_t capacity, uint32_t* counters) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, unc);
+    if (ballot == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(ballot) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counters, (uint32_t)__popc(ballot));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (unc) {
+        const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
+        if (pos < capacity) list[pos] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2 / a3
+// ------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256) proj_fast_kernel(const __grid_constant__ ProjParams P) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int xs = blockIdx.z;
+    const bool in = z < P.rz;
+    const size_t i = ((size_t)xs * P.ry + y) * P.rz + (in ? z : 0);
+    int cls = CLS_SKIP, m = 0, f = 0;
+    if (in) {
+        uint16_t ids[KMAX];
+        if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
+        cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
+    }
+    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+    if (!in || cls == CLS_UNCERTAIN) return;
+    if (m) {
+        float v = P.tsdf[i], w = P.weight[i];
+        const float sc = (float)P.scale;
+        for (int vi = 0; vi < P.n_views; ++vi)
+            if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
+        P.tsdf[i] = v;
+        P.weight[i] = w;
+    }
+    if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+    if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+}
+
+// mode: 0 = work list (or re-scan on overflow), 1 = every voxel
+template <int KMAX>
+__global__ void __launch_bounds__(128) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
+    const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
+    const uint32_t count = P.counters[0];
+    const bool use_list = !all_mode && count <= P.capacity;
+    const size_t n = use_list ? (size_t)count : nvox;
+    const size_t plane = (size_t)P.ry * P.rz;
+    uint32_t done = 0;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = use_list ? (size_t)P.list[t] : t;
+        const int xs = (int)(i / plane);
+        const size_t rem = i - (size_t)xs * plane;
+        const int y = (int)(rem / P.rz);
+        const int z = (int)(rem - (size_t)y * P.rz);
+        uint16_t ids[KMAX];
+        if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
+        if (!use_list && !all_mode) {
+            int m0, f0;
+            if (voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m0, &f0) != CLS_UNCERTAIN) continue;
+        }
+        float v = P.tsdf[i], w = P.weight[i];
+        int m, f;
+        voxel_projective_exact(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
+        if (m) {
+            P.tsdf[i] = v;
+            P.weight[i] = w;
+        }
+        if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+        if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+        ++done;
+    }
+    for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+    if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a1
+// ------------------------------------------------------------------------------------------------
+template <int KMAX>
+__global__ void __launch_bounds__(256) vol_fast_kernel(const __grid_constant__ VolParams P) {
+    const int z = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int xs = blockIdx.z;
+    const bool in = z < P.rz;
+    const size_t i = ((size_t)xs * P.ry + y) * P.rz + (in ? z : 0);
+    int cls = CLS_SKIP;
+    float wi = 0.f;
+    if (in) {
+        uint16_t ids[KMAX];
+        if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
+        cls = voxel_volume_classify<KMAX>(P, xs + P.x0, y, z, ids, &wi);
+    }
+    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+    if (!in || cls == CLS_UNCERTAIN) return;
+    if (cls == CLS_CLAMP) {
+        float v = P.tsdf[i], w = P.weight[i];
+        if (P.k > 0) {
+            const float wt = (w == 0.f) ? wi : w;
+            v = (v * wt + fmul(P.tdist_f, wi)) / (wi + wt);
+            w = fminf(wi + wt, P.wmax_f);
+        } else {
+            v = (v * w + P.tdist_f) / (1.0f + w);
+            w = fminf(1.0f + w, P.wmax_f);
+        }
+        P.tsdf[i] = v;
+        P.weight[i] = w;
+    }
+    if (P.mask_out) P.mask_out[i] = (cls == CLS_CLAMP) ? 1 : 0;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) vol_exact_kernel(const __grid_constant__ VolParams P, int all_mode) {
+    const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
+    const uint32_t count = P.counters[0];
+    const bool use_list = !all_mode && count <= P.capacity;
+    const size_t n = use_list ? (size_t)count : nvox;
+    const size_t plane = (size_t)P.ry * P.rz;
+    uint32_t done = 0;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = use_list ? (size_t)P.list[t] : t;
+        const int xs = (int)(i / plane);
+        const size_t rem = i - (size_t)xs * plane;
+        const int y = (int)(rem / P.rz);
+        const int z = (int)(rem - (size_t)y * P.rz);
+        uint16_t ids[KMAX];
+        if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
+        if (!use_list && !all_mode) {
+            float wi;
+            if (voxel_volume_classify<KMAX>(P, xs + P.x0, y, z, ids, &wi) != CLS_UNCERTAIN) continue;
+        }
+        float v = P.tsdf[i], w = P.weight[i];
+        const bool upd = voxel_volume_exact(P, xs + P.x0, y, z, ids, &v, &w);
+        if (upd) {
+            P.tsdf[i] = v;
+            P.weight[i] = w;
+        }
+        if (P.mask_out) P.mask_out[i] = upd ? 1 : 0;
+        ++done;
+    }
+    for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+    if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4: warp arbitrary points (exact tier)
+// ------------------------------------------------------------------------------------------------
+__global__ void warp_points_kernel(const float* pts, const float* normals, int64_t m, const int32_t* idx, int k,
+                                   const float* node_pos, const float* node_dq, const float* node_w,
+                                   const __grid_constant__ dfb_warpfield wf, double* out_p, double* out_n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (int64_t)gridDim.x * blockDim.x) {
+        int ids[DFB_MAX_K];
+        for (int j = 0; j < k; ++j) ids[j] = idx[t * k + j];
+        double op[3], on[3];
+        warp_ref(pts + 3 * t, normals ? normals + 3 * t : nullptr, ids, k, node_pos, node_dq, node_w, wf.lw, wf.has_lw != 0,
+                 wf.lw_is_f32 != 0, op, on, nullptr);
+        for (int c = 0; c < 3; ++c) out_p[3 * t + c] = op[c];
+        if (normals && out_n)
+            for (int c = 0; c < 3; ++c) out_n[3 * t + c] = on[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// node packing
+// ------------------------------------------------------------------------------------------------
+__global__ void nodes_pack_kernel(const float* pos, const float* dq, const float* w, int n, float* rec) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* r = rec + (size_t)i * DFB_NODE_REC_FLOATS;
+    r[0] = pos[3 * i]; r[1] = pos[3 * i + 1]; r[2] = pos[3 * i + 2];
+    const double ww = (double)w[i];
+    r[3] = (float)(-1.4426950408889634 / (4.0 * ww * ww));
+    for (int c = 0; c < 8; ++c) r[4 + c] = dq[8 * i + c];
+}
+
+dim3 fast_grid(const dfb_volume* vol, int& threads) {
+    threads = vol->rz >= 256 ? 256 : ((vol->rz + 31) / 32) * 32;
+    return dim3((vol->rz + threads - 1) / threads, vol->ry, vol->x1 - vol->x0);
+}
+
+int exact_blocks(size_t nvox) {
+    const size_t want = (nvox + 127) / 128;
+    return (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
+}
+
+int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol) {
+    DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
+    const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
+    if (mode == DFB_MODE_HYBRID) {
+        int threads;
+        const dim3 grid = fast_grid(vol, threads);
+        if (P.k <= 4) proj_fast_kernel<4><<<grid, threads, 0, s>>>(P);
+        else proj_fast_kernel<8><<<grid, threads, 0, s>>>(P);
+        DFB_LAUNCH_CHECK("proj_fast_kernel");
+    }
+    const int all = mode == DFB_MODE_EXACT ? 1 : 0;
+    if (P.k <= 4) proj_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else proj_exact_kernel<8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    DFB_LAUNCH_CHECK("proj_exact_kernel");
+    return DFB_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" int dfb_nodes_pack(const float* node_pos, const float* node_dq, const float* node_w, int n_nodes,
+                              float* node_rec, dfb_stream_t stream) {
+    DFB_REQUIRE(node_pos && node_dq && node_w && node_rec, "null pointer");
+    DFB_REQUIRE(n_nodes > 0, "n_nodes must be positive");
+    nodes_pack_kernel<<<(n_nodes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(node_pos, node_dq, node_w, n_nodes, node_rec);
+    DFB_LAUNCH_CHECK("nodes_pack_kernel");
+    return DFB_OK;
+}
+
+extern "C" int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpfield* wf, const dfb_views* views,
+                                          double tdist, double wmax, int mode, const dfb_workspace* ws,
+                                          uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream) {
+    ProjParams P;
+    if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
+    return run_projective(P, mode, (cudaStream_t)stream, vol);
+}
+
+extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const float* depth, int rows, int cols,
+                                    const double lw34[12], const double K[9], const double Kinv[9], double scale,
+                                    const double center[3], double tdist, double wmax, int mode,
+                                    const dfb_workspace* ws, uint8_t* mask_out, uint8_t* frustum_out,
+                                    dfb_stream_t stream) {
+    ProjParams P;
+    if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
+                            mask_out, frustum_out))
+        return r;
+    return run_projective(P, mode, (cudaStream_t)stream, vol);
+}
+
+extern "C" int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield* wf, const float* curr, int cx,
+                                      int cy, int cz, double tdist, double wmax, int mode, const dfb_workspace* ws,
+                                      uint8_t* mask_out, dfb_stream_t stream) {
+    VolParams P;
+    if (int r = build_volume(P, vol, wf, curr, cx, cy, cz, tdist, wmax, mode, ws, mask_out)) return r;
+    cudaStream_t s = (cudaStream_t)stream;
+    DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
+    const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
+    if (mode == DFB_MODE_HYBRID) {
+        int threads;
+        const dim3 grid = fast_grid(vol, threads);
+        if (P.k <= 4) vol_fast_kernel<4><<<grid, threads, 0, s>>>(P);
+        else vol_fast_kernel<8><<<grid, threads, 0, s>>>(P);
+        DFB_LAUNCH_CHECK("vol_fast_kernel");
+    }
+    const int all = mode == DFB_MODE_EXACT ? 1 : 0;
+    if (P.k <= 4) vol_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else vol_exact_kernel<8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    DFB_LAUNCH_CHECK("vol_exact_kernel");
+    return DFB_OK;
+}
+
+extern "C" int dfb_warp_points(const float* pts, const float* normals, int64_t m, const int32_t* idx,
+                               const dfb_warpfield* wf, double* out_pts, double* out_normals, dfb_stream_t stream) {
+    if (int r = validate_warpfield(wf, false)) return r;
+    DFB_REQUIRE(pts && out_pts && m >= 0, "null pointer / negative count");
+    DFB_REQUIRE(wf->k == 0 || idx, "neighbour indices are null");
+    if (m == 0) return DFB_OK;
+    const int blocks = (int)((m + 127) / 128 < 148 * 8 ? (m + 127) / 128 : 148 * 8);
+    warp_points_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pts, normals, m, idx, wf->k, wf->node_pos, wf->node_dq,
+                                                                 wf->node_w, *wf, out_pts, out_normals);
+    DFB_LAUNCH_CHECK("warp_points_kernel");
+    return DFB_OK;
+}

@@ -1,0 +1,122 @@
+/*
+ * dfb.h -- C ABI of libdfb_b200.so: B200 (sm_100a) kernels for the two hot paths of
+ * nintendops/DynamicFusion_Body, called from the Python classes that mirror the reference's
+ * Fusion / FusionDM method surface (dynamicfusion_body_b200/fusion.py).
+ *
+ * The reference has no FFI: its replacement mechanism is "subclass and override the hot method"
+ * (FusionDM_GPU overrides FusionDM.fuseDepths, core/fusion_dm.py:563-600,737).  Each entry point
+ * below names the reference method body it replaces.
+ *
+ * Conventions
+ *   - every bulk pointer is a DEVICE pointer owned by the caller; small matrices inside the
+ *     parameter structs are HOST values copied into kernel arguments;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and makes no hidden allocation;
+ *   - return 0 on success, <0 on error (dfb_last_error() gives the text);  there is no CPU path;
+ *   - volumes are C-ordered [x][y][z] float32 (np.nditer order, core/fusion.py:171), optionally a
+ *     slab x in [x0,x1) of the full grid whose pointer addresses voxel (x0,0,0).
+ */
+#ifndef DFB_H_
+#define DFB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_MAX_K 8
+#define DFB_MAX_VIEWS 8
+#define DFB_NODE_REC_FLOATS 12 /* pos xyz, exp2 coefficient, dq[8] */
+
+#define DFB_OK 0
+#define DFB_ERR_INVALID (-1)
+#define DFB_ERR_CUDA (-2)
+
+#define DFB_MODE_HYBRID 0 /* fp32 classify + clamped update, reference-exact fp64 pass for the rest */
+#define DFB_MODE_EXACT 1  /* every voxel through the reference-exact pass (validation / debugging) */
+
+typedef void* dfb_stream_t; /* cudaStream_t */
+
+typedef struct dfb_volume {
+    float* tsdf;   /* Fusion._tsdf   (core/fusion.py:76),  slab-local */
+    float* weight; /* Fusion._tsdfw  (core/fusion.py:74),  slab-local */
+    int rx, ry, rz; /* full grid resolution */
+    int x0, x1;     /* this slab: x in [x0,x1) */
+} dfb_volume;
+
+typedef struct dfb_warpfield {
+    const float* node_rec; /* [n_nodes][12] from dfb_nodes_pack */
+    const float* node_pos; /* [n_nodes][3]  float32 node positions dg_v  (core/fusion.py:114) */
+    const float* node_dq;  /* [n_nodes][8]  float32 dual quaternions dg_se3 (core/fusion.py:115) */
+    const float* node_w;   /* [n_nodes]     dg_w = 2*radius (core/fusion.py:116) */
+    int n_nodes;
+    int k;               /* neighbours per voxel (Fusion._knn); 0 = rigid (FusionDM.updateTSDF) */
+    const uint16_t* knn; /* [(x1-x0)*ry*rz][k] from dfb_knn_build_volume, ascending distance */
+    int has_lw;          /* apply the global rigid dq `lw` (Fusion._lw, m_lw of Fusion.warp) */
+    int lw_is_f32;       /* lw is a float32 array in the reference (its initial state): the first
+                            dual-quaternion product of dqb_warp then runs in float32 (core/util.py:69-70) */
+    double lw[8];
+} dfb_warpfield;
+
+typedef struct dfb_views {
+    int n_views;                        /* applied sequentially in index order (core/fusion_dm.py:166-170) */
+    const float* depth[DFB_MAX_VIEWS];  /* [rows][cols] float32, depth stored NEGATIVE, 0 = no data */
+    int rows, cols;                     /* (dmx, dmy) = dm.shape (core/fusion_dm.py:181) */
+    double K[9];                        /* FusionDM._K    row-major 3x3 */
+    double Kinv[9];                     /* FusionDM._Kinv row-major 3x3 */
+    int has_extrinsics;                 /* lpos = E_v @ [p',1] */
+    double E[DFB_MAX_VIEWS][12];        /* row-major 3x4 */
+} dfb_views;
+
+typedef struct dfb_workspace {
+    uint32_t* list;     /* device [capacity]: voxels deferred to the exact pass */
+    uint32_t capacity;
+    uint32_t* counters; /* device [8]; counters[0] = deferred count of the last call,
+                           counters[1] = voxels the exact pass processed */
+} dfb_workspace;
+
+int dfb_version(void);
+const char* dfb_last_error(void);
+
+/* node table: (pos, dq, w) -> 48-byte records used by the update kernels. */
+int dfb_nodes_pack(const float* node_pos, const float* node_dq, const float* node_w, int n_nodes,
+                   float* node_rec, dfb_stream_t stream);
+
+/* scipy KDTree.query(pos, k+1)[:-1] for every voxel centre of a slab (core/fusion.py:175-176):
+ * k nearest node ids in ascending float64 distance (lower id first on exact ties). */
+int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
+                         uint16_t* knn, dfb_stream_t stream);
+/* KDTree.query(vert, k) for arbitrary float32 points (core/fusion.py:122,232). */
+int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
+                   dfb_stream_t stream);
+
+/* a3: Fusion.warp (core/fusion.py:502-520) + per-voxel body of FusionDM.fuseDepths
+ * (core/fusion_dm.py:193-210) with scale=1, center=0, all views fused in one pass.
+ * mask_out / frustum_out (optional, [slab voxels] uint8): bit v = view v updated the voxel /
+ * voxel projected inside view v's image (core/fusion_dm.py:195). */
+int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpfield* wf, const dfb_views* views,
+                               double tdist, double wmax, int mode, const dfb_workspace* ws,
+                               uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream);
+
+/* a1: Fusion.updateTSDF (core/fusion.py:171-190); with wf->k == 0: FusionDM.updateTSDF
+ * (core/fusion_dm.py:300-316).  curr = live TSDF volume [cx][cy][cz] float32. */
+int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield* wf, const float* curr, int cx, int cy,
+                           int cz, double tdist, double wmax, int mode, const dfb_workspace* ws,
+                           uint8_t* mask_out, dfb_stream_t stream);
+
+/* a2: FusionDM.fuseDepths (core/fusion_dm.py:180-217): rigid 3x4 `lw`, grid->world
+ * pos = scale*(idx - tsdf_res/2) + center. */
+int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const float* depth, int rows, int cols,
+                         const double lw34[12], const double K[9], const double Kinv[9], double scale,
+                         const double center[3], double tdist, double wmax, int mode, const dfb_workspace* ws,
+                         uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream);
+
+/* a4: Fusion.warp for arbitrary float32 points (+ optional normals) with explicit neighbours
+ * idx [m][k]; outputs float64 [m][3], computed with the reference's arithmetic. */
+int dfb_warp_points(const float* pts, const float* normals, int64_t m, const int32_t* idx, const dfb_warpfield* wf,
+                    double* out_pts, double* out_normals, dfb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFB_H_ */

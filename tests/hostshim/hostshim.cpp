@@ -1,0 +1,145 @@
+// hostshim.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the per-voxel logic of the CUDA kernels
+// (dynamicfusion_body_b200/csrc/dfb_voxel.h, dfb_params.h) for the host so that the CPU test-suite can
+// check the fast-tier classification and the reference-exact tier against the oracle on a box that has
+// no GPU.  It mirrors the composition the kernels in tsdf.cu perform (fast pass, then exact pass over
+// the uncertain voxels) with plain loops and HOST pointers.  The product never loads this library.
+#include <stdarg.h>
+#include <stdio.h>
+#include <vector>
+
+#include "../../dynamicfusion_body_b200/csrc/dfb_params.h"
+
+namespace dfb {
+static char g_err[512];
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" const char* hs_last_error() { return g_err; }
+
+extern "C" void hs_nodes_pack(const float* pos, const float* dq, const float* w, int n, float* rec) {
+    for (int i = 0; i < n; ++i) {
+        float* r = rec + (size_t)i * DFB_NODE_REC_FLOATS;
+        r[0] = pos[3 * i]; r[1] = pos[3 * i + 1]; r[2] = pos[3 * i + 2];
+        const double ww = (double)w[i];
+        r[3] = (float)(-1.4426950408889634 / (4.0 * ww * ww));
+        for (int c = 0; c < 8; ++c) r[4 + c] = dq[8 * i + c];
+    }
+}
+
+template <int KMAX>
+static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
+    const size_t plane = (size_t)P.ry * P.rz;
+    uint32_t n_unc = 0;
+    for (int xs = 0; xs < P.x1 - P.x0; ++xs)
+        for (int y = 0; y < P.ry; ++y)
+            for (int z = 0; z < P.rz; ++z) {
+                const size_t i = xs * plane + (size_t)y * P.rz + z;
+                uint16_t ids[KMAX] = {0};
+                for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
+                int m = 0, f = 0, cls = CLS_UNCERTAIN;
+                if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
+                if (cls_out) cls_out[i] = (uint8_t)cls;
+                float v = P.tsdf[i], w = P.weight[i];
+                if (cls == CLS_UNCERTAIN) {
+                    ++n_unc;
+                    voxel_projective_exact(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
+                } else if (m) {
+                    for (int vi = 0; vi < P.n_views; ++vi)
+                        if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, (float)P.scale);
+                }
+                if (m) { P.tsdf[i] = v; P.weight[i] = w; }
+                if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+                if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+            }
+    if (P.counters) P.counters[0] = n_unc;
+}
+
+extern "C" int hs_tsdf_update_projective(const dfb_volume* vol, const dfb_warpfield* wf, const dfb_views* views,
+                                         double tdist, double wmax, int mode, const dfb_workspace* ws,
+                                         uint8_t* mask_out, uint8_t* frustum_out, uint8_t* cls_out) {
+    ProjParams P;
+    if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
+    if (P.k <= 4) run_proj<4>(P, mode, cls_out);
+    else run_proj<8>(P, mode, cls_out);
+    return DFB_OK;
+}
+
+extern "C" int hs_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const float* depth, int rows, int cols,
+                                   const double* lw34, const double* K, const double* Kinv, double scale,
+                                   const double* center, double tdist, double wmax, int mode, const dfb_workspace* ws,
+                                   uint8_t* mask_out, uint8_t* frustum_out, uint8_t* cls_out) {
+    ProjParams P;
+    if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
+                            mask_out, frustum_out))
+        return r;
+    run_proj<4>(P, mode, cls_out);
+    return DFB_OK;
+}
+
+template <int KMAX>
+static void run_vol(VolParams& P, int mode, uint8_t* cls_out) {
+    const size_t plane = (size_t)P.ry * P.rz;
+    uint32_t n_unc = 0;
+    for (int xs = 0; xs < P.x1 - P.x0; ++xs)
+        for (int y = 0; y < P.ry; ++y)
+            for (int z = 0; z < P.rz; ++z) {
+                const size_t i = xs * plane + (size_t)y * P.rz + z;
+                uint16_t ids[KMAX] = {0};
+                for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
+                float wi = 0.f;
+                int cls = CLS_UNCERTAIN;
+                if (mode == DFB_MODE_HYBRID) cls = voxel_volume_classify<KMAX>(P, xs + P.x0, y, z, ids, &wi);
+                if (cls_out) cls_out[i] = (uint8_t)cls;
+                float v = P.tsdf[i], w = P.weight[i];
+                bool upd = false;
+                if (cls == CLS_UNCERTAIN) {
+                    ++n_unc;
+                    upd = voxel_volume_exact(P, xs + P.x0, y, z, ids, &v, &w);
+                } else if (cls == CLS_CLAMP) {
+                    upd = true;
+                    if (P.k > 0) {
+                        const float wt = (w == 0.f) ? wi : w;
+                        v = (v * wt + fmul(P.tdist_f, wi)) / (wi + wt);
+                        w = fminf(wi + wt, P.wmax_f);
+                    } else {
+                        v = (v * w + P.tdist_f) / (1.0f + w);
+                        w = fminf(1.0f + w, P.wmax_f);
+                    }
+                }
+                if (upd) { P.tsdf[i] = v; P.weight[i] = w; }
+                if (P.mask_out) P.mask_out[i] = upd ? 1 : 0;
+            }
+    if (P.counters) P.counters[0] = n_unc;
+}
+
+extern "C" int hs_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield* wf, const float* curr, int cx, int cy,
+                                     int cz, double tdist, double wmax, int mode, const dfb_workspace* ws,
+                                     uint8_t* mask_out, uint8_t* cls_out) {
+    VolParams P;
+    if (int r = build_volume(P, vol, wf, curr, cx, cy, cz, tdist, wmax, mode, ws, mask_out)) return r;
+    if (P.k <= 4) run_vol<4>(P, mode, cls_out);
+    else run_vol<8>(P, mode, cls_out);
+    return DFB_OK;
+}
+
+extern "C" int hs_warp_points(const float* pts, const float* normals, int64_t m, const int32_t* idx,
+                              const dfb_warpfield* wf, double* out_pts, double* out_normals) {
+    if (int r = validate_warpfield(wf, false)) return r;
+    for (int64_t t = 0; t < m; ++t) {
+        int ids[DFB_MAX_K];
+        for (int j = 0; j < wf->k; ++j) ids[j] = idx[t * wf->k + j];
+        double on[3];
+        warp_ref(pts + 3 * t, normals ? normals + 3 * t : nullptr, ids, wf->k, wf->node_pos, wf->node_dq, wf->node_w,
+                 wf->lw, wf->has_lw != 0, wf->lw_is_f32 != 0, out_pts + 3 * t, on, nullptr);
+        if (normals && out_normals)
+            for (int c = 0; c < 3; ++c) out_normals[3 * t + c] = on[c];
+    }
+    return DFB_OK;
+}
