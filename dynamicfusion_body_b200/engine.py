@@ -1,0 +1,264 @@
+"""Device-resident state and thin launch wrappers over the C ABI (include/dfb.h).
+
+torch is used for what it is good at here -- owning device memory, streams, and (in dist.py)
+torch.distributed -- never for the arithmetic of the hot path.  Every function below ends in a call
+into libdfb_b200.so on the current CUDA stream; there is no eager/torch/CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("dynamicfusion_body_b200 needs a CUDA device (B200); there is no CPU path")
+    return torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+
+
+def _to_dev(a, dtype, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype).contiguous()
+
+
+class Workspace:
+    """Deferred-voxel list for the exact pass.  capacity defaults to 1/4 of the slab."""
+
+    def __init__(self, n_voxels, device, fraction=0.25):
+        self.capacity = int(max(1024, n_voxels * fraction))
+        self.list = torch.empty(self.capacity, dtype=torch.int32, device=device)
+        self.counters = torch.zeros(8, dtype=torch.int32, device=device)
+
+    def struct(self):
+        s = _capi.Workspace()
+        s.list = self.list.data_ptr()
+        s.capacity = self.capacity
+        s.counters = self.counters.data_ptr()
+        return s
+
+    def stats(self):
+        c = self.counters.cpu().numpy().astype(np.int64) & 0xffffffff
+        return {"deferred": int(c[0]), "exact_processed": int(c[1])}
+
+
+class DeviceVolume:
+    """(tsdf, weight) slab x in [x0,x1) of an (rx,ry,rz) grid, float32, C order (x slowest)."""
+
+    def __init__(self, res, x0=0, x1=None, device=None, tsdf=None, weight=None, fill=None):
+        self.device = _require_cuda(device)
+        self.res = tuple(int(r) for r in res)
+        self.x0 = int(x0)
+        self.x1 = int(self.res[0] if x1 is None else x1)
+        shape = (self.x1 - self.x0, self.res[1], self.res[2])
+        if tsdf is not None:
+            self.tsdf = _to_dev(tsdf, torch.float32, self.device).reshape(shape)
+        else:
+            self.tsdf = torch.full(shape, float(fill if fill is not None else 0.0), dtype=torch.float32, device=self.device)
+        if weight is not None:
+            self.weight = _to_dev(weight, torch.float32, self.device).reshape(shape)
+        else:
+            self.weight = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self.workspace = Workspace(self.n_voxels, self.device)
+
+    @property
+    def n_voxels(self):
+        return (self.x1 - self.x0) * self.res[1] * self.res[2]
+
+    def struct(self):
+        s = _capi.Volume()
+        s.tsdf = self.tsdf.data_ptr()
+        s.weight = self.weight.data_ptr()
+        s.rx, s.ry, s.rz = self.res
+        s.x0, s.x1 = self.x0, self.x1
+        return s
+
+
+class DeviceWarpField:
+    """Deformation nodes (dg_v, dg_se3, dg_w of core/fusion.py:113-116) as device SoA + packed records,
+    and the cached voxel kNN table (valid until the node POSITIONS change, i.e. until update_graph)."""
+
+    def __init__(self, k, device=None):
+        self.device = _require_cuda(device)
+        self.k = int(k)
+        self.n_nodes = 0
+        self.node_pos = self.node_dq = self.node_w = self.node_rec = None
+        self._knn = {}
+
+    def set_nodes(self, node_pos, node_dq, node_w):
+        n = len(node_pos)
+        self.node_pos = _to_dev(node_pos, torch.float32, self.device).reshape(n, 3)
+        w = np.broadcast_to(np.asarray(node_w, dtype=np.float32), (n,)) if not isinstance(node_w, torch.Tensor) else node_w
+        self.node_w = _to_dev(w, torch.float32, self.device).reshape(n)
+        self.n_nodes = n
+        self._knn = {}
+        self.set_dq(node_dq)
+
+    def set_dq(self, node_dq):
+        """Only the transforms changed (e.g. after solve): repack records, keep the kNN tables."""
+        self.node_dq = _to_dev(node_dq, torch.float32, self.device).reshape(self.n_nodes, 8)
+        self.repack()
+
+    def repack(self):
+        self.node_rec = torch.empty((self.n_nodes, _capi.DFB_NODE_REC_FLOATS), dtype=torch.float32, device=self.device)
+        _capi.check(_capi.lib().dfb_nodes_pack(_ptr(self.node_pos), _ptr(self.node_dq), _ptr(self.node_w), self.n_nodes,
+                                               _ptr(self.node_rec), _stream()))
+
+    def knn_table(self, res, x0, x1):
+        """uint16 [(x1-x0)*ry*rz, k] (stored in an int16 tensor), built on first use."""
+        key = (tuple(res), x0, x1)
+        t = self._knn.get(key)
+        if t is None:
+            n = (x1 - x0) * res[1] * res[2]
+            t = torch.empty((n, self.k), dtype=torch.int16, device=self.device)
+            _capi.check(_capi.lib().dfb_knn_build_volume(_ptr(self.node_pos), self.n_nodes, self.k, res[0], res[1], res[2],
+                                                         x0, x1, _ptr(t), _stream()))
+            self._knn[key] = t
+        return t
+
+    def knn_points(self, pts, k=None):
+        k = self.k if k is None else k
+        p = _to_dev(pts, torch.float32, self.device).reshape(-1, 3)
+        out = torch.empty((p.shape[0], k), dtype=torch.int32, device=self.device)
+        _capi.check(_capi.lib().dfb_knn_points(_ptr(p), p.shape[0], _ptr(self.node_pos), self.n_nodes, k, _ptr(out), _stream()))
+        return out
+
+    def struct(self, lw=None, knn=None, k=None):
+        s = _capi.WarpField()
+        k = self.k if k is None else k
+        if k > 0:
+            s.node_rec = self.node_rec.data_ptr()
+            s.node_pos = self.node_pos.data_ptr()
+            s.node_dq = self.node_dq.data_ptr()
+            s.node_w = self.node_w.data_ptr()
+        s.n_nodes = self.n_nodes
+        s.k = k
+        s.knn = knn.data_ptr() if knn is not None else None
+        fill_lw(s, lw)
+        return s
+
+
+def fill_lw(s, lw):
+    """lw: None, or an 8-vector; a float32 numpy array keeps the reference's float32 dtype flow (Q3)."""
+    s.has_lw = 0 if lw is None else 1
+    s.lw_is_f32 = 0
+    if lw is not None:
+        if isinstance(lw, torch.Tensor):
+            lw = lw.detach().cpu().numpy()
+        lw = np.asarray(lw)
+        s.lw_is_f32 = 1 if lw.dtype == np.float32 else 0
+        for i in range(8):
+            s.lw[i] = float(lw[i])
+
+
+def make_views(depths, K, Kinv=None, extrinsics=None):
+    """depths: CUDA float32 tensor (V,rows,cols) (negative depth, 0 = no data)."""
+    if depths.dim() == 2:
+        depths = depths[None]
+    assert depths.is_cuda and depths.dtype == torch.float32 and depths.is_contiguous()
+    K = np.asarray(K, dtype=np.float64)
+    Kinv = np.linalg.inv(K) if Kinv is None else np.asarray(Kinv, dtype=np.float64)
+    v = _capi.Views()
+    v.n_views = depths.shape[0]
+    if v.n_views > _capi.DFB_MAX_VIEWS:
+        raise ValueError("at most %d views per pass" % _capi.DFB_MAX_VIEWS)
+    for i in range(v.n_views):
+        v.depth[i] = depths[i].data_ptr()
+    v.rows, v.cols = int(depths.shape[1]), int(depths.shape[2])
+    for i in range(9):
+        v.K[i] = float(K.ravel()[i])
+        v.Kinv[i] = float(Kinv.ravel()[i])
+    v.has_extrinsics = 0 if extrinsics is None else 1
+    if extrinsics is not None:
+        E = np.asarray(extrinsics, dtype=np.float64).reshape(v.n_views, 12)
+        for j in range(v.n_views):
+            for i in range(12):
+                v.E[j][i] = float(E[j, i])
+    return v
+
+
+def _mask_bufs(vol, want):
+    if not want:
+        return None, None
+    return (torch.zeros(vol.n_voxels, dtype=torch.uint8, device=vol.device),
+            torch.zeros(vol.n_voxels, dtype=torch.uint8, device=vol.device))
+
+
+def update_projective(vol, wf, lw, depths, K, Kinv=None, extrinsics=None, tdist=1.0, wmax=100.0,
+                      mode=_capi.MODE_HYBRID, want_masks=False, views=None):
+    """a3: warped projective TSDF update of the slab `vol` in place; returns (mask, frustum) bit-arrays or None."""
+    views = views if views is not None else make_views(depths, K, Kinv, extrinsics)
+    knn = wf.knn_table(vol.res, vol.x0, vol.x1)
+    ws = vol.workspace.struct()
+    mask, frus = _mask_bufs(vol, want_masks)
+    v = vol.struct()
+    s = wf.struct(lw, knn)
+    _capi.check(_capi.lib().dfb_tsdf_update_projective(C.byref(v), C.byref(s), C.byref(views), float(tdist), float(wmax),
+                                                       int(mode), C.byref(ws), _ptr(mask), _ptr(frus), _stream()))
+    return (mask, frus) if want_masks else None
+
+
+def update_volume(vol, wf, lw, curr, tdist, wmax=100.0, mode=_capi.MODE_HYBRID, want_masks=False, rigid=False):
+    """a1: Fusion.updateTSDF (or FusionDM.updateTSDF when rigid=True) on the slab in place."""
+    assert curr.is_cuda and curr.dtype == torch.float32 and curr.is_contiguous() and curr.dim() == 3
+    k = 0 if rigid else wf.k
+    knn = None if rigid else wf.knn_table(vol.res, vol.x0, vol.x1)
+    ws = vol.workspace.struct()
+    mask = torch.zeros(vol.n_voxels, dtype=torch.uint8, device=vol.device) if want_masks else None
+    v = vol.struct()
+    s = wf.struct(lw, knn, k=k) if wf is not None else _rigid_struct(lw)
+    _capi.check(_capi.lib().dfb_tsdf_update_volume(C.byref(v), C.byref(s), _ptr(curr), curr.shape[0], curr.shape[1],
+                                                   curr.shape[2], float(tdist), float(wmax), int(mode), C.byref(ws),
+                                                   _ptr(mask), _stream()))
+    return mask
+
+
+def _rigid_struct(lw):
+    s = _capi.WarpField()
+    s.k = 0
+    fill_lw(s, lw)
+    return s
+
+
+def fuse_depth_rigid(vol, tsdf_res, depth, lw34, K, Kinv=None, scale=1.0, center=None, tdist=1.0, wmax=100.0,
+                     mode=_capi.MODE_HYBRID, want_masks=False):
+    """a2: FusionDM.fuseDepths on the slab in place."""
+    assert depth.is_cuda and depth.dtype == torch.float32 and depth.is_contiguous() and depth.dim() == 2
+    K = np.ascontiguousarray(K, dtype=np.float64)
+    Kinv = np.ascontiguousarray(np.linalg.inv(K) if Kinv is None else Kinv, dtype=np.float64)
+    lw34 = np.ascontiguousarray(lw34, dtype=np.float64).reshape(12)
+    center = np.ascontiguousarray(np.zeros(3) if center is None else center, dtype=np.float64)
+    ws = vol.workspace.struct()
+    mask, frus = _mask_bufs(vol, want_masks)
+    v = vol.struct()
+    f64 = _capi.c_f64p
+    _capi.check(_capi.lib().dfb_fuse_depth_rigid(C.byref(v), int(tsdf_res), _ptr(depth), depth.shape[0], depth.shape[1],
+                                                 lw34.ctypes.data_as(f64), K.ctypes.data_as(f64), Kinv.ctypes.data_as(f64),
+                                                 float(scale), center.ctypes.data_as(f64), float(tdist), float(wmax), int(mode),
+                                                 C.byref(ws), _ptr(mask), _ptr(frus), _stream()))
+    return (mask, frus) if want_masks else None
+
+
+def warp_points(wf, lw, pts, normals=None, idx=None, k=None):
+    """a4: Fusion.warp for float32 points; returns float64 CUDA tensors."""
+    dev = wf.device
+    p = _to_dev(pts, torch.float32, dev).reshape(-1, 3)
+    n = None if normals is None else _to_dev(normals, torch.float32, dev).reshape(-1, 3)
+    k = wf.k if k is None else k
+    if k > 0:
+        idx = wf.knn_points(p, k) if idx is None else _to_dev(idx, torch.int32, dev).reshape(-1, k)
+    out = torch.empty((p.shape[0], 3), dtype=torch.float64, device=dev)
+    outn = torch.empty((p.shape[0], 3), dtype=torch.float64, device=dev) if n is not None else None
+    s = wf.struct(lw, None, k=k)
+    _capi.check(_capi.lib().dfb_warp_points(_ptr(p), _ptr(n), p.shape[0], _ptr(idx), C.byref(s), _ptr(out), _ptr(outn), _stream()))
+    return (out, outn) if n is not None else out

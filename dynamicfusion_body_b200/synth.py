@@ -229,7 +229,7 @@ class Scene:
 
 def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=480, cols=640, tdist=None,
                max_angle_deg=5.0, trans_sigma=None, lw_dtype=np.float64, unit_init=False, mesh_path=None,
-               focal=None, cam_dist=1.7):
+               focal=None, cam_dist=1.7, background=False):
     """Seeded benchmark / test scene.  `radius` in units of the 64^3 mesh; either `radius` or
     `n_nodes` (bisection on the radius) may be given.  One view: the global rigid dq `lw` is the camera
     extrinsic; several views: `lw` is a small rigid motion and cameras sit on a ring (extrinsics)."""
@@ -289,7 +289,11 @@ def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=4
     depths = []
     for vi in range(n_views):
         vc = wv if extr is None else wv @ extr[vi][:, :3].T + extr[vi][:, 3]
-        depths.append(render_depth(vc, faces, K, rows, cols))
+        dm = render_depth(vc, faces, K, rows, cols)
+        if background:
+            # a wall behind the capture volume: every pixel carries a measurement, as in a real sensor
+            dm[dm == 0] = -np.float32(dist + 0.9 * res)
+        depths.append(dm)
     if tdist is None:
         tdist = 3.0 * res / 64.0   # 0.2 world units of test.py:159 ~ 3 voxels at 64^3
     return Scene(res=res, k=k, vertices=verts, normals=nrm, faces=faces, node_pos=node_pos, node_idx=node_idx,

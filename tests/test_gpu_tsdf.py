@@ -1,0 +1,272 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C ABI vs the oracle.
+
+Bars (north_star): kNN ids and masks bit-exact; |dTSDF| <= 1e-5 * tdist; weights equal up to float32
+storage rounding (rel 1e-6)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TSDF_TOL = 1e-5   # fraction of the truncation distance
+W_RTOL = 1e-6
+
+
+def _engine():
+    import torch
+    from dynamicfusion_body_b200 import engine, _capi
+    assert torch.cuda.is_available()
+    return torch, engine, _capi
+
+
+def _wf(engine, sc, k=None):
+    wf = engine.DeviceWarpField(sc.k if k is None else k)
+    wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
+    return wf
+
+
+@pytest.mark.parametrize("k,n_nodes", [(4, 300), (8, 150), (3, 60)])
+def test_knn_volume_bit_exact(k, n_nodes):
+    torch, engine, _ = _engine()
+    from dynamicfusion_body_b200 import synth
+    import scenes
+    sc = synth.make_scene(res=40, k=k, n_nodes=n_nodes, seed=2, rows=48, cols=64)
+    wf = _wf(engine, sc)
+    res = (40, 36, 44)
+    t = wf.knn_table(res, 3, 29).cpu().numpy().view(np.uint16).astype(np.int64)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, k, 3, 29)
+    assert tie.sum() < len(tie) * 1e-3
+    assert np.array_equal(t[~tie], idx[~tie])
+    # on exact ties both orders are "k nearest": same set of ids
+    assert np.array_equal(np.sort(t[tie], 1), np.sort(idx[tie], 1))
+
+
+def test_knn_points_matches_oracle():
+    torch, engine, _ = _engine()
+    from dynamicfusion_body_b200 import synth
+    from oracle import dq as odq
+    sc = synth.make_scene(res=64, k=4, n_nodes=500, seed=5, rows=48, cols=64)
+    wf = _wf(engine, sc)
+    got = wf.knn_points(sc.vertices).cpu().numpy()
+    idx, d2 = odq.knn_bruteforce(sc.vertices, sc.node_pos, 4)
+    tie = odq.knn_has_tie(d2)
+    assert np.array_equal(got[~tie], idx[~tie])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("fresh", [True, False])
+def test_projective_single_view(small_scene, mode, fresh):
+    torch, engine, _ = _engine()
+    import scenes
+    from oracle import tsdf as ot
+    sc = small_scene
+    R = sc.res
+    res = (R, R, R)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k)
+    t0, w0 = scenes.initial_state(R ** 3, fresh=fresh, tdist=sc.tdist)
+    nw = np.full(sc.n_nodes, sc.node_w)
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, sc.node_pos, sc.node_dq,
+                                           nw, sc.lw, sc.depths, sc.K, sc.Kinv, sc.tdist)
+    wf = _wf(engine, sc)
+    vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+    depths = torch.from_numpy(sc.depths).cuda()
+    mask, frus = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist, mode=mode, want_masks=True)
+    torch.cuda.synchronize()
+    gv = vol.tsdf.cpu().numpy().ravel(); gw = vol.weight.cpu().numpy().ravel()
+    ok = ~tie
+    assert np.array_equal(scenes.bits(mask.cpu().numpy(), 0)[ok], om[0][ok])
+    assert np.array_equal(scenes.bits(frus.cpu().numpy(), 0)[ok], ofr[0][ok])
+    assert np.abs(gv - ov)[ok].max() <= TSDF_TOL * sc.tdist
+    assert (np.abs(gw - ow) / np.maximum(1, ow))[ok].max() <= W_RTOL
+    st = vol.workspace.stats()
+    print("mode", mode, "fresh", fresh, "deferred frac", st["deferred"] / R ** 3, "updated frac", om[0].mean())
+    if mode == 0:
+        assert st["deferred"] < 0.5 * R ** 3
+
+
+def test_projective_hybrid_equals_exact_bitwise(small_scene):
+    """The fp32 classify tier must never change a result: hybrid == all-exact, bit for bit."""
+    torch, engine, _ = _engine()
+    import scenes
+    sc = small_scene
+    R = sc.res
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    depths = torch.from_numpy(sc.depths).cuda()
+    wf = _wf(engine, sc)
+    out = []
+    for mode in (0, 1):
+        vol = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+        m, f = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist, mode=mode, want_masks=True)
+        out.append((vol.tsdf.cpu().numpy(), vol.weight.cpu().numpy(), m.cpu().numpy(), f.cpu().numpy()))
+    assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
+    assert np.array_equal(out[0][1], out[1][1])
+    # clamped updates are evaluated in float32 in the fast tier and float64 in the exact tier
+    assert np.abs(out[0][0] - out[1][0]).max() <= 2e-7 * sc.tdist * 4
+
+
+def test_projective_multi_view_k8():
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    from oracle import tsdf as ot
+    sc = synth.make_scene(res=40, k=8, n_nodes=200, seed=4, n_views=4, rows=96, cols=128)
+    R = sc.res
+    res = (R, R, R)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    nw = np.full(sc.n_nodes, sc.node_w)
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, sc.node_pos, sc.node_dq,
+                                           nw, sc.lw, sc.depths, sc.K, sc.Kinv, sc.tdist, extrinsics=sc.extrinsics)
+    wf = _wf(engine, sc)
+    vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+    depths = torch.from_numpy(sc.depths).cuda()
+    mask, frus = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, sc.extrinsics, sc.tdist, want_masks=True)
+    gv = vol.tsdf.cpu().numpy().ravel(); gw = vol.weight.cpu().numpy().ravel()
+    ok = ~tie
+    for v in range(4):
+        assert np.array_equal(scenes.bits(mask.cpu().numpy(), v)[ok], om[v][ok])
+        assert np.array_equal(scenes.bits(frus.cpu().numpy(), v)[ok], ofr[v][ok])
+    assert np.abs(gv - ov)[ok].max() <= TSDF_TOL * sc.tdist
+    assert (np.abs(gw - ow) / np.maximum(1, ow))[ok].max() <= W_RTOL
+    print("multi-view updated frac per view", om.mean(1), "deferred", vol.workspace.stats())
+
+
+def test_projective_slabs_equal_full_volume(small_scene):
+    """x-slab sharding: concatenated slabs == single-volume result, bit for bit."""
+    torch, engine, _ = _engine()
+    import scenes
+    sc = small_scene
+    R = sc.res
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    depths = torch.from_numpy(sc.depths).cuda()
+    wf = _wf(engine, sc)
+    full = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+    engine.update_projective(full, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist)
+    parts_v, parts_w = [], []
+    t3, w3 = t0.reshape(R, R, R), w0.reshape(R, R, R)
+    for x0, x1 in ((0, 11), (11, 30), (30, R)):
+        s = engine.DeviceVolume((R, R, R), x0, x1, tsdf=t3[x0:x1], weight=w3[x0:x1])
+        engine.update_projective(s, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist)
+        parts_v.append(s.tsdf.cpu().numpy()); parts_w.append(s.weight.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts_v), full.tsdf.cpu().numpy())
+    assert np.array_equal(np.concatenate(parts_w), full.weight.cpu().numpy())
+
+
+@pytest.mark.parametrize("lw_kind", ["f32", "f64", "none"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_volume_update_a1(lw_kind, mode):
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    from oracle import tsdf as ot
+    R = 36
+    sc = synth.make_scene(res=R, k=4, n_nodes=200, seed=1, rows=48, cols=64)
+    lw = {"f32": np.array([1, 0, 0, 0, 0, 0.1, 0, 0], np.float32), "f64": np.array([1, 0, 0, 0, 0, 0.1, 0, 0.05]), "none": None}[lw_kind]
+    nw = np.full(sc.n_nodes, sc.node_w)
+    wv = synth.blend_warp(sc.vertices, sc.node_pos, sc.node_dq, nw, sc.vert_knn, lw=None if lw is None else lw.astype(np.float64))
+    live = synth.mesh_sdf_volume((R + 2, R, R + 1), wv, sc.warped_normals)
+    tdist = float(live.max())          # reference usage: Fusion(volume, volume.max(), ...) test.py:110
+    res = (R, R, R)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=tdist)
+    ov, ow, om = ot.update_volume(t0.astype(np.float64), w0.astype(np.float64), live, vox, idx, sc.node_pos, sc.node_dq, nw, lw, tdist)
+    wf = _wf(engine, sc)
+    vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+    mask = engine.update_volume(vol, wf, lw, torch.from_numpy(live).cuda(), tdist, mode=mode, want_masks=True)
+    gv = vol.tsdf.cpu().numpy().ravel(); gw = vol.weight.cpu().numpy().ravel()
+    ok = ~tie
+    assert np.array_equal(mask.cpu().numpy().astype(bool)[ok], om[ok])
+    assert np.abs(gv - ov)[ok].max() <= TSDF_TOL * tdist
+    assert (np.abs(gw - ow) / np.maximum(1, ow))[ok].max() <= W_RTOL
+
+
+def test_rigid_volume_update():
+    """FusionDM.updateTSDF (core/fusion_dm.py:300-316)."""
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    from oracle import tsdf as ot
+    R = 32
+    sc = synth.make_scene(res=R, k=4, n_nodes=100, seed=1, rows=48, cols=64)
+    lw = np.array([1, 0, 0, 0, 0, 0.1, 0, 0], np.float32)
+    live = synth.mesh_sdf_volume((R, R, R), sc.vertices, sc.normals)
+    tdist = 4.0
+    vox = ot.voxel_grid((R, R, R))
+    t0, w0 = scenes.initial_state(R ** 3, tdist=tdist)
+    w0 = np.floor(w0)
+    ov, ow, om = ot.update_rigid_volume(t0.astype(np.float64), w0.astype(np.float64), live, vox, lw, tdist)
+    vol = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+    mask = engine.update_volume(vol, None, lw, torch.from_numpy(live).cuda(), tdist, want_masks=True, rigid=True)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), om)
+    assert np.abs(vol.tsdf.cpu().numpy().ravel() - ov).max() <= TSDF_TOL * tdist
+    assert np.array_equal(vol.weight.cpu().numpy().ravel(), ow.astype(np.float32))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fuse_depth_rigid_a2(mode):
+    """FusionDM.fuseDepths with the grid->world mapping of compute_live_tsdf (core/fusion_dm.py:166-170)."""
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    from oracle import tsdf as ot
+    R = 40
+    sc = synth.make_scene(res=R, k=4, n_nodes=100, seed=1, rows=48, cols=64)
+    K = np.array([[200., 0, 80], [0, 200, 60], [0, 0, 1]])
+    Kinv = np.linalg.inv(K)
+    ang = 0.1
+    Rm = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    scale = 12 * 1.3 / R
+    center = np.array([-0.03, -0.43, -5.6])
+    lw34 = np.concatenate([Rm, -Rm @ center[:, None] + np.array([[0.1], [0.05], [22.0]])], 1)
+    vw = scale * (sc.vertices.astype(np.float64) - R / 2) + center
+    dm = synth.render_depth(vw @ lw34[:, :3].T + lw34[:, 3], sc.faces, K, 120, 160)
+    tdist = 0.2
+    vox = ot.voxel_grid((R, R, R))
+    t0, w0 = scenes.initial_state(R ** 3, tdist=tdist)
+    ov, ow, om, ofr = ot.fuse_depth_rigid(t0.astype(np.float64), w0.astype(np.float64), vox, dm, lw34, K, Kinv, tdist, R,
+                                          scale=scale, center=center)
+    assert om.mean() > 0.02
+    vol = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+    mask, frus = engine.fuse_depth_rigid(vol, R, torch.from_numpy(dm).cuda(), lw34, K, Kinv, scale, center, tdist, mode=mode,
+                                         want_masks=True)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), om)
+    assert np.array_equal(frus.cpu().numpy().astype(bool), ofr)
+    assert np.abs(vol.tsdf.cpu().numpy().ravel() - ov).max() <= TSDF_TOL * tdist
+    assert np.array_equal(vol.weight.cpu().numpy().ravel(), ow.astype(np.float32))
+
+
+def test_warp_points_matches_oracle(small_scene):
+    torch, engine, _ = _engine()
+    from oracle import dq as odq
+    sc = small_scene
+    wf = _wf(engine, sc)
+    nw = np.full((len(sc.vertices), sc.k), sc.node_w)
+    for lw in (np.array([1, 0, 0, 0, 0, 0.1, 0, 0], np.float32), sc.lw, None):
+        p, n = engine.warp_points(wf, lw, sc.vertices, sc.normals, idx=sc.vert_knn)
+        op, on = odq.warp(sc.vertices, sc.node_pos[sc.vert_knn], sc.node_dq[sc.vert_knn], nw, lw=lw, normal=sc.normals)
+        assert np.abs(p.cpu().numpy() - op).max() <= 1e-9 * max(1.0, np.abs(op).max())
+        assert np.abs(n.cpu().numpy() - on).max() <= 1e-12
+
+
+def test_sequence_of_frames_stays_within_tolerance(small_scene):
+    """15-frame carry-over (BASELINE config 2 shape, reduced size): GPU float32 state vs float64 oracle state."""
+    torch, engine, _ = _engine()
+    import scenes
+    from oracle import tsdf as ot
+    sc = small_scene
+    R = sc.res
+    vox, idx, tie = scenes.oracle_knn((R, R, R), sc.node_pos, sc.k)
+    t0, w0 = scenes.initial_state(R ** 3, fresh=True, tdist=sc.tdist)
+    nw = np.full(sc.n_nodes, sc.node_w)
+    wf = _wf(engine, sc)
+    vol = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+    depths = torch.from_numpy(sc.depths).cuda()
+    ov, ow = t0.astype(np.float64), w0.astype(np.float64)
+    rng = np.random.default_rng(0)
+    for frame in range(5):
+        dq = sc.node_dq + (rng.normal(size=sc.node_dq.shape) * 1e-3).astype(np.float32)
+        wf.set_dq(dq)
+        ov, ow, om, _ = ot.update_projective(ov, ow, vox, idx, sc.node_pos, dq, nw, sc.lw, sc.depths, sc.K, sc.Kinv, sc.tdist)
+        m, _f = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist, want_masks=True)
+        assert np.array_equal(scenes.bits(m.cpu().numpy(), 0)[~tie], om[0][~tie])
+    assert np.abs(vol.tsdf.cpu().numpy().ravel() - ov)[~tie].max() <= TSDF_TOL * sc.tdist
+    assert np.array_equal(vol.weight.cpu().numpy().ravel()[~tie], ow.astype(np.float32)[~tie])
