@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the warped-TSDF hot path (BASELINE.json metric:
+"warped-TSDF voxels/sec ... (% HBM roofline); GN solve ms/iter").
+
+  python bench.py --gpus 1 --steps 20 --warmup 5
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...          (CPU: the reference path restated in oracle/, all host cores)
+
+A step = one frame of the a3 path over one GPU's slab: new depth frame + new node transforms ->
+node records packed -> warped projective TSDF update (fast pass + reference-exact pass).
+Workload at N=1: 512^3 voxels, ~4k nodes, k=4 DQB, one 640x480 depth view (north_star target config;
+BASELINE configs[4] at one GPU).  N>1: weak scaling -- the grid is (512*N^(1/3))^3 so every rank owns an
+x-slab of 512^3 voxels of it; rank 0 broadcasts the frame (depth + node transforms) over NCCL inside the step.
+
+`value`   : voxels/s with the frame already resident in HBM.
+`e2e`     : voxels/s through the reference-facing class call (Fusion.fuseFrame) with HOST numpy buffers:
+            H2D of depth + node transforms and D2H of the per-frame statistics are inside the timed region.
+            The TSDF volume itself is persistent device state (Fusion._tsdf), as in the reference where it
+            is an attribute that lives across frames.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALG_BYTES_PER_VOXEL = 16.0  # read v, read w, write v, write w (fp32) -- SURVEY 8d
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def build_scene(res, n_nodes, k, n_views, seed=0):
+    from dynamicfusion_body_b200 import synth
+    return synth.make_scene(res=res, k=k, n_nodes=n_nodes, seed=seed, n_views=n_views, background=True)
+
+
+def frame_dqs(sc, n_frames, seed=1):
+    """Per-frame node transforms: the scene's field plus a small per-frame perturbation (15-frame sequence shape)."""
+    rng = np.random.default_rng(seed)
+    return [(sc.node_dq + (rng.normal(size=sc.node_dq.shape) * 1e-4).astype(np.float32)) for _ in range(n_frames)]
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dynamicfusion_body_b200 import _capi, engine
+    from dynamicfusion_body_b200.fusion import Fusion
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    per_gpu_res = args.res
+    res = int(round(per_gpu_res * world ** (1.0 / 3.0)))
+    slab = int(round(per_gpu_res ** 3 / float(res * res)))          # x-thickness giving ~per_gpu_res^3 voxels per rank
+    res_x = slab * world
+    grid = (res_x, res, res)
+    x0, x1 = rank * slab, (rank + 1) * slab
+    sc = build_scene(res, args.nodes, args.k, args.views)
+    # the scene is generated for a cubic `res` grid; with world>1 res_x can differ from res by rounding
+    fus = Fusion(sc.tdist, knn=args.k, device=dev, use_cnn=False, write_warpfield=False)
+    fus.InitializeCanonicalSpace(tsdf_shape=grid, slab=(x0, x1), K=sc.K, vertices=sc.vertices, normals=sc.normals,
+                                 nodes=sc.nodes_as_reference_tuples())
+    fus._lw = sc.lw
+    nvox_rank = (x1 - x0) * res * res
+    n_frames = 15
+    dqs = frame_dqs(sc, n_frames)
+    dq_dev = [torch.from_numpy(d).to(dev) for d in dqs]
+    depth_dev = torch.from_numpy(sc.depths).to(dev)
+    depth_host = torch.from_numpy(sc.depths).pin_memory()
+    dq_host = [torch.from_numpy(d).pin_memory() for d in dqs]
+    fus.build_knn()                                                  # once per graph revision, outside the timed region
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        if world > 1:
+            # rank 0 owns the sensor + warp field: broadcast this frame (depth + node transforms) over NVLink
+            dist.broadcast(depth_dev, 0)
+            dist.broadcast(dq_dev[i % n_frames], 0)
+        fus.set_node_dqs(dq_dev[i % n_frames])
+        fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics)
+
+    def step_e2e(i):
+        d = depth_host.to(dev, non_blocking=True)
+        q = dq_host[i % n_frames].to(dev, non_blocking=True)
+        if world > 1:
+            dist.broadcast(d, 0)
+            dist.broadcast(q, 0)
+        fus.set_node_dqs(q)
+        fus.fuseFrame(d, extrinsics=sc.extrinsics)
+        return fus.frame_stats()                                     # D2H of the per-frame counters (32 B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup):
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step_fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    stats = fus.frame_stats()
+
+    # ---- roofline leg: the dominant kernel (fast pass) timed alone with CUDA events on its stream ----
+    fast_ms, exact_ms = [], []
+    for i in range(max(5, min(args.steps, 20))):
+        fus.set_node_dqs(dq_dev[i % n_frames])
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics, mode=_capi.MODE_FAST_ONLY)
+        b.record()
+        fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics, mode=_capi.MODE_LIST_ONLY)
+        c.record()
+        torch.cuda.synchronize()
+        fast_ms.append(a.elapsed_time(b)); exact_ms.append(b.elapsed_time(c))
+    fast_avg = float(np.mean(fast_ms[2:])); exact_avg = float(np.mean(exact_ms[2:]))
+
+    total_vox = nvox_rank * world
+    value = total_vox * args.steps / (ms_total * 1e-3)
+    e2e_value = total_vox * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = measured_peaks()
+    achieved = ALG_BYTES_PER_VOXEL * nvox_rank / (fast_avg * 1e-3) / 1e9
+    out = {
+        "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%d^3 voxels per GPU (grid %dx%dx%d), warped projective TSDF update (a3), k=%d DQB, %d nodes, "
+                               "%d view(s) 640x480, 15-frame dq sequence" % (per_gpu_res, res_x, res, res, args.k, sc.n_nodes, args.views),
+                   "l2": "inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % (nvox_rank * (8 + 2 * args.k) / 1e6),
+                   "parallelism": "x-slab per GPU, frame broadcast over NCCL" if world > 1 else "single GPU",
+                   "updated_voxel_fraction": stats.get("updated_fraction"), "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
+        "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(sc.depths.nbytes + dqs[0].nbytes),
+                "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "proj_fast_kernel<4>" if args.k <= 4 else "proj_fast_kernel<8>",
+                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "kernel_ms": fast_avg, "exact_pass_ms": exact_avg,
+                     "algorithmic_bytes_per_voxel": ALG_BYTES_PER_VOXEL, "step_frac_of_peak": ALG_BYTES_PER_VOXEL * nvox_rank / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(sc, (res_x, res, res), budget_s=args.cpu_seconds)
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sc, res, budget_s=12.0):
+    from oracle import driver
+    sd = driver.scene_dict(sc)
+    vps, n, dt = driver.time_projective(sd, res, 100_000)
+    n_sample = int(min(4_000_000, max(100_000, vps * budget_s)))
+    vps, n, dt = driver.time_projective(sd, res, n_sample, seed=1)
+    return {"value": vps, "unit": "voxels/s", "cores": 1, "kind": "port",
+            "sample": "%d random voxels of the same %dx%dx%d workload, numpy oracle (oracle/tsdf.py) incl. KD-tree kNN, %.1f s" % (n, res[0], res[1], res[2], dt)}
+
+
+def run_reference(args):
+    """The reference path on the host cores.  The reference is pure Python and does not exist on the GPU box, so
+    this times its numpy restatement (oracle/, kind="port") on a bounded voxel sample per step, all cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import driver
+    res = args.res
+    sc = build_scene(res, args.nodes, args.k, args.views)
+    sd = driver.scene_dict(sc)
+    cores = os.cpu_count() or 1
+    per_step = args.ref_sample
+    for _ in range(min(1, args.warmup)):
+        driver.time_projective_parallel(sd, (res, res, res), max(cores * 20000, per_step // 4), cores)
+    t0 = time.perf_counter()
+    nvox = 0
+    rates = []
+    for _ in range(args.steps):
+        r, n, wall = driver.time_projective_parallel(sd, (res, res, res), per_step, cores)
+        nvox += n
+        rates.append(n / wall)
+    wall = time.perf_counter() - t0
+    value = nvox / wall
+    out = {"impl": "reference", "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "%d^3 voxels, warped projective TSDF update (a3), k=%d DQB, %d nodes, %d view(s) 640x480; each step = a "
+                                  "bounded sample of %d voxels" % (res, args.k, sc.n_nodes, args.views, per_step)},
+           "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port",
+                            "sample": "%d random voxels per step over %d worker processes (numpy oracle incl. KD-tree kNN)" % (per_step, cores)},
+           "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=512, help="per-GPU cube edge (voxels per GPU = res^3)")
+    ap.add_argument("--nodes", type=int, default=4000)
+    ap.add_argument("--k", type=int, default=4)
+    ap.add_argument("--views", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-sample", type=int, default=1_600_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

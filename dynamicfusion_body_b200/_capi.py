@@ -12,6 +12,8 @@ DFB_MAX_VIEWS = 8
 DFB_NODE_REC_FLOATS = 12
 MODE_HYBRID = 0
 MODE_EXACT = 1
+MODE_FAST_ONLY = 2
+MODE_LIST_ONLY = 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdfb_b200.so")
@@ -47,8 +49,11 @@ class Workspace(C.Structure):
     _fields_ = [("list", C.c_void_p), ("capacity", C.c_uint32), ("counters", C.c_void_p)]
 
 
-def _dp(n):
-    return C.c_double * n
+class GNProblem(C.Structure):
+    _fields_ = [("n_vert", C.c_int64), ("vertices", C.c_void_p), ("normals", C.c_void_p), ("corr", C.c_void_p),
+                ("vert_knn", C.c_void_p), ("n_nodes", C.c_int), ("k", C.c_int), ("node_pos", C.c_void_p),
+                ("node_w", C.c_void_p), ("node_nbr", C.c_void_p), ("lw", C.c_double * 8), ("lw_is_f32", C.c_int),
+                ("rw", C.c_double), ("huber", C.c_int), ("f_scale", C.c_double)]
 
 
 def declare(lib, prefix="dfb_", device=True):
@@ -67,6 +72,15 @@ def declare(lib, prefix="dfb_", device=True):
         "tsdf_update_volume": ([C.POINTER(Volume), C.POINTER(WarpField), vp, C.c_int, C.c_int, C.c_int, C.c_double,
                                 C.c_double, C.c_int, C.POINTER(Workspace), vp, vp], C.c_int),
         "warp_points": ([vp, vp, C.c_int64, vp, C.POINTER(WarpField), vp, vp] + ([vp] if device else []), C.c_int),
+        "dq_blend_points": ([vp, C.c_int64, vp, C.POINTER(WarpField), vp] + ([vp] if device else []), C.c_int),
+        "gn_residuals": ([C.POINTER(GNProblem), vp, C.c_int, vp] + ([vp] if device else []), C.c_int),
+        "gn_residuals_lw": ([C.POINTER(GNProblem), vp, C.c_int, c_f64p, C.c_int, vp] + ([vp] if device else []), C.c_int),
+        "gn_pattern_rows": ([C.POINTER(GNProblem), vp, vp, vp], C.c_int),
+        "gn_pattern_cols": ([C.c_int, vp, vp, vp, vp], C.c_int),
+        "gn_normal_eq": ([C.POINTER(GNProblem), vp, vp, vp, C.c_int64, vp, vp, vp] + ([vp] if device else []), C.c_int),
+        "gn_lw_normal_eq": ([C.POINTER(GNProblem), vp, c_f64p, vp, vp, vp] + ([vp] if device else []), C.c_int),
+        "gn_solve_workspace_doubles": ([C.c_int], C.c_int64),
+        "gn_solve": ([C.c_int, vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, prefix + name, None)
@@ -104,5 +118,7 @@ def check(rc):
 
 EXPORTS = [
     "dfb_version", "dfb_last_error", "dfb_nodes_pack", "dfb_knn_build_volume", "dfb_knn_points",
-    "dfb_tsdf_update_projective", "dfb_tsdf_update_volume", "dfb_fuse_depth_rigid", "dfb_warp_points",
+    "dfb_tsdf_update_projective", "dfb_tsdf_update_volume", "dfb_fuse_depth_rigid", "dfb_warp_points", "dfb_dq_blend_points",
+    "dfb_gn_residuals", "dfb_gn_residuals_lw", "dfb_gn_pattern_rows", "dfb_gn_pattern_cols", "dfb_gn_normal_eq",
+    "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",
 ]

@@ -200,6 +200,17 @@ __global__ void warp_points_kernel(const float* pts, const float* normals, int64
     }
 }
 
+__global__ void dq_blend_points_kernel(const float* pts, int64_t m, const int32_t* idx, int k, const float* node_pos,
+                                       const float* node_dq, const float* node_w, double* out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (int64_t)gridDim.x * blockDim.x) {
+        int ids[DFB_MAX_K];
+        for (int j = 0; j < k; ++j) ids[j] = idx[t * k + j];
+        double se3[8];
+        dq_blend_ref(pts + 3 * t, ids, k, node_pos, node_dq, node_w, se3, nullptr);
+        for (int c = 0; c < 8; ++c) out[8 * t + c] = se3[c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // node packing
 // ------------------------------------------------------------------------------------------------
@@ -224,14 +235,15 @@ int exact_blocks(size_t nvox) {
 }
 
 int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol) {
-    DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
+    if (mode != DFB_MODE_LIST_ONLY) DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
-    if (mode == DFB_MODE_HYBRID) {
+    if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY) {
         int threads;
         const dim3 grid = fast_grid(vol, threads);
         if (P.k <= 4) proj_fast_kernel<4><<<grid, threads, 0, s>>>(P);
         else proj_fast_kernel<8><<<grid, threads, 0, s>>>(P);
         DFB_LAUNCH_CHECK("proj_fast_kernel");
+        if (mode == DFB_MODE_FAST_ONLY) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
     if (P.k <= 4) proj_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
@@ -280,14 +292,15 @@ extern "C" int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield
     VolParams P;
     if (int r = build_volume(P, vol, wf, curr, cx, cy, cz, tdist, wmax, mode, ws, mask_out)) return r;
     cudaStream_t s = (cudaStream_t)stream;
-    DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
+    if (mode != DFB_MODE_LIST_ONLY) DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
-    if (mode == DFB_MODE_HYBRID) {
+    if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY) {
         int threads;
         const dim3 grid = fast_grid(vol, threads);
         if (P.k <= 4) vol_fast_kernel<4><<<grid, threads, 0, s>>>(P);
         else vol_fast_kernel<8><<<grid, threads, 0, s>>>(P);
         DFB_LAUNCH_CHECK("vol_fast_kernel");
+        if (mode == DFB_MODE_FAST_ONLY) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
     if (P.k <= 4) vol_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
@@ -306,5 +319,16 @@ extern "C" int dfb_warp_points(const float* pts, const float* normals, int64_t m
     warp_points_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pts, normals, m, idx, wf->k, wf->node_pos, wf->node_dq,
                                                                  wf->node_w, *wf, out_pts, out_normals);
     DFB_LAUNCH_CHECK("warp_points_kernel");
+    return DFB_OK;
+}
+
+extern "C" int dfb_dq_blend_points(const float* pts, int64_t m, const int32_t* idx, const dfb_warpfield* wf, double* out_dq,
+                                   dfb_stream_t stream) {
+    if (int r = validate_warpfield(wf, false)) return r;
+    DFB_REQUIRE(pts && idx && out_dq && m >= 0 && wf->k > 0, "bad arguments");
+    if (m == 0) return DFB_OK;
+    const int blocks = (int)((m + 127) / 128 < 148 * 8 ? (m + 127) / 128 : 148 * 8);
+    dq_blend_points_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pts, m, idx, wf->k, wf->node_pos, wf->node_dq, wf->node_w, out_dq);
+    DFB_LAUNCH_CHECK("dq_blend_points_kernel");
     return DFB_OK;
 }

@@ -1,0 +1,437 @@
+"""Drop-in classes for the reference's hot-path objects, backed by libdfb_b200.so.
+
+The reference replaces a hot method by subclassing and overriding it (`FusionDM_GPU(FusionDM)`,
+core/fusion_dm.py:563-600); a driver then only swaps the class name (test.py:158-161).  `Fusion`,
+`FusionDM` and `FusionDM_GPU` below keep the reference's method names, argument meaning, attribute names
+and error behaviour for the two hot paths, with state living on the GPU:
+
+  * `_tsdf`, `_tsdfw`  -- device-resident float32 slabs; reading the attribute materialises a numpy copy,
+                          assigning a numpy array uploads it (the OpenCL path's per-call full-volume
+                          upload/readback, core/fusion_dm.py:693-703, is exactly what this avoids);
+  * `_nodes`           -- the reference's list of (vertex_idx, pos, dq, w) tuples (core/fusion.py:113-116)
+                          on read/assign, SoA tensors + packed records on the device;
+  * the per-voxel KD-tree query of `updateTSDF` (core/fusion.py:175) is replaced by an exact kNN table
+                          cached per graph revision.
+
+Graph maintenance that needs marching cubes (`update_graph`, `setupCorrespondences`, `marching_cubes`,
+mesh writers) is outside the hot path (SURVEY 8f "next") and raises NotImplementedError.
+"""
+import numpy as np
+import torch
+from scipy.spatial import KDTree
+
+from . import _capi, engine
+from . import gn as _gn
+
+
+def _as_np(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+class _FusionBase:
+    """State shared by Fusion and FusionDM."""
+
+    def _init_state(self, trunc_distance, knn, marching_cubes_step_size, verbose, write_warpfield, device):
+        self._device = engine._require_cuda(device)
+        _capi.lib()                                       # fail loudly now if the CUDA library is missing
+        self._itercounter = 0
+        self._curr_tsdf = None
+        self._tdist = abs(trunc_distance)
+        self._knn = knn
+        self._marching_cubes_step_size = marching_cubes_step_size
+        self._verbose = verbose
+        self._write_warpfield = write_warpfield
+        self._vol = None
+        self._wf = engine.DeviceWarpField(knn, self._device)
+        self._node_vertex_idx = np.zeros(0, dtype=np.int64)
+        self._neighbor_look_up = []
+        self._correspondences = []
+        self._vertices = None
+        self._normals = None
+        self._faces = None
+        self._radius = None
+        self._sess = None
+        self._mode = _capi.MODE_HYBRID
+        self._last_views = None
+
+    # ---- device-resident volume exposed under the reference's attribute names -------------------
+    @property
+    def _tsdf(self):
+        return None if self._vol is None else self._vol.tsdf.cpu().numpy()
+
+    @_tsdf.setter
+    def _tsdf(self, value):
+        self._set_volume(value, None)
+
+    @property
+    def _tsdfw(self):
+        return None if self._vol is None else self._vol.weight.cpu().numpy()
+
+    @_tsdfw.setter
+    def _tsdfw(self, value):
+        self._set_volume(None, value)
+
+    def _set_volume(self, tsdf, weight, shape=None, slab=None):
+        if tsdf is not None:
+            if not isinstance(tsdf, (np.ndarray, torch.Tensor)) or tsdf.ndim != 3:
+                raise ValueError('Only 3D numpy array is accepted as tsdf')
+        if self._vol is None or (tsdf is not None and tuple(tsdf.shape) != tuple(self._vol.tsdf.shape)):
+            if tsdf is None and weight is None:
+                full = tuple(shape)
+            else:
+                ref = tsdf if tsdf is not None else weight
+                full = tuple(shape) if shape is not None else tuple(ref.shape)
+            x0, x1 = slab if slab is not None else (0, full[0])
+            self._vol = engine.DeviceVolume(full, x0, x1, self._device, tsdf=tsdf, weight=weight, fill=self._tdist)
+            return
+        if tsdf is not None:
+            self._vol.tsdf.copy_(engine._to_dev(tsdf, torch.float32, self._device).reshape(self._vol.tsdf.shape))
+        if weight is not None:
+            self._vol.weight.copy_(engine._to_dev(weight, torch.float32, self._device).reshape(self._vol.weight.shape))
+
+    # ---- deformation graph under the reference's `_nodes` layout --------------------------------
+    @property
+    def _nodes(self):
+        if self._wf.n_nodes == 0:
+            return []
+        pos = self._wf.node_pos.cpu().numpy()
+        dq = self._wf.node_dq.cpu().numpy()
+        w = self._wf.node_w.cpu().numpy()
+        return [(int(self._node_vertex_idx[i]), pos[i], dq[i], float(w[i])) for i in range(len(pos))]
+
+    @_nodes.setter
+    def _nodes(self, nodes):
+        nodes = list(nodes)
+        if not nodes:
+            self._wf = engine.DeviceWarpField(self._knn, self._device)
+            self._node_vertex_idx = np.zeros(0, dtype=np.int64)
+            return
+        self._node_vertex_idx = np.array([n[0] for n in nodes], dtype=np.int64)
+        pos = np.array([n[1] for n in nodes], dtype=np.float32)
+        dq = np.array([n[2] for n in nodes], dtype=np.float32)
+        w = np.array([n[3] for n in nodes], dtype=np.float32)
+        same_pos = (self._wf.n_nodes == len(nodes) and np.array_equal(self._wf.node_pos.cpu().numpy(), pos)
+                    and np.array_equal(self._wf.node_w.cpu().numpy(), w))
+        if same_pos:
+            self._wf.set_dq(dq)                            # transforms only: the cached kNN tables stay valid
+        else:
+            self._wf.k = self._knn
+            self._wf.set_nodes(pos, dq, w)
+
+    def set_node_dqs(self, dq):
+        """Fast path for per-frame transform updates: (N,8) float32, host or device."""
+        self._wf.set_dq(dq)
+
+    @property
+    def _kdtree(self):
+        """Host KD-tree over the node positions (what the reference stores, core/fusion.py:119)."""
+        return KDTree(self._wf.node_pos.cpu().numpy()) if self._wf.n_nodes else None
+
+    def build_knn(self):
+        """Build (or fetch) the cached voxel->k-nearest-node table of this slab.  Called implicitly by the
+        update methods; exposed so that a driver can pay for it outside a timed region."""
+        return self._wf.knn_table(self._vol.res, self._vol.x0, self._vol.x1)
+
+    def knn_indices(self):
+        """(n_voxels, k) int64 node ids == KDTree.query(pos, k+1)[1][:-1] per voxel (core/fusion.py:175-176)."""
+        return self.build_knn().cpu().numpy().view(np.uint16).astype(np.int64)
+
+    def frame_stats(self):
+        """Counters of the last update call (a 32-byte device->host read)."""
+        s = self._vol.workspace.stats()
+        return s
+
+    # ---- warp helpers (core/fusion.py:502-551), evaluated on the device -------------------------
+    def _lookup(self, pos, k):
+        return self._wf.knn_points(np.asarray(pos, dtype=np.float32).reshape(-1, 3), k).cpu().numpy()
+
+    def warp(self, pos, dqs=None, locations=None, normal=None, dmax=None, m_lw=None):
+        """Fusion.warp (core/fusion.py:502-520) for one point or an (M,3) batch.  `dqs` given explicitly
+        must be the current node transforms of `locations` (the reference always passes those)."""
+        if dmax is not None:
+            raise NotImplementedError("dmax weighting is an unused option of the reference (core/fusion.py:539-541)")
+        p = np.asarray(pos, dtype=np.float32)
+        single = p.ndim == 1
+        p2 = p.reshape(-1, 3)
+        if locations is None:
+            # query(k+1)[:-1] (core/fusion.py:504-505) == the k nearest
+            loc = self._lookup(p2, self._knn)
+        else:
+            loc = np.asarray(locations, dtype=np.int32).reshape(len(p2), -1)
+        wf = self._wf
+        if dqs is not None:
+            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(len(p2), -1, 8))
+            loc = np.arange(loc.size, dtype=np.int32).reshape(loc.shape)
+        n2 = None if normal is None else np.asarray(normal, dtype=np.float32).reshape(-1, 3)
+        out = engine.warp_points(wf, m_lw, p2, n2, idx=loc, k=loc.shape[1])
+        if normal is None:
+            r = out.cpu().numpy()
+            return r[0] if single else r
+        r, rn = out[0].cpu().numpy(), out[1].cpu().numpy()
+        return (r[0], rn[0]) if single else (r, rn)
+
+    def _wf_with_dqs(self, loc, dqs):
+        """Temporary warp field whose node j is (pos/w of node loc.flat[j], dq = dqs.flat[j]) -- lets
+        `warp`/`dq_blend` honour explicitly passed transforms like the reference does."""
+        pos = self._wf.node_pos.cpu().numpy()[loc.reshape(-1)]
+        w = self._wf.node_w.cpu().numpy()[loc.reshape(-1)]
+        wf = engine.DeviceWarpField(loc.shape[1], self._device)
+        wf.set_nodes(pos, dqs.reshape(-1, 8), w)
+        return wf
+
+    def dq_blend(self, pos, dqs=None, locations=None, dmax=None):
+        """Fusion.dq_blend (core/fusion.py:527-551): blended, 8-norm-normalised dual quaternion (Q2)."""
+        if dmax is not None:
+            raise NotImplementedError("dmax weighting is an unused option of the reference")
+        p = np.asarray(pos, dtype=np.float32).reshape(1, 3)
+        loc = self._lookup(p, self._knn) if locations is None else np.asarray(locations, dtype=np.int32).reshape(1, -1)
+        wf = self._wf
+        if dqs is not None:
+            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(1, -1, 8))
+            loc = np.arange(loc.size, dtype=np.int32).reshape(loc.shape)
+        return _gn.dq_blend_points(wf, p, loc)[0]
+
+    # ---- out-of-scope graph / mesh maintenance ---------------------------------------------------
+    def marching_cubes(self, tsdf=None, step_size=0):
+        raise NotImplementedError("surface extraction is outside the accelerated hot path (SURVEY 8f rank 3)")
+
+    def update_graph(self):
+        raise NotImplementedError("deformation-graph maintenance needs marching cubes (SURVEY 8f rank 2)")
+
+    def setupCorrespondences(self, curr_tsdf, *a, **kw):
+        raise NotImplementedError("correspondence search needs marching cubes of the live TSDF (SURVEY 8f rank 1); "
+                                  "pass correspondences to solve() explicitly")
+
+
+class Fusion(_FusionBase):
+    """Non-rigid fusion object (core/fusion.py:49).  Constructor arguments as in the reference; `device`
+    selects the GPU.  `use_cnn` is accepted for signature compatibility (the CNN path is out of scope)."""
+
+    def __init__(self, trunc_distance, subsample_rate=5.0, knn=4, marching_cubes_step_size=3, verbose=False,
+                 use_cnn=True, write_warpfield=True, device=None):
+        self._init_state(trunc_distance, knn, marching_cubes_step_size, verbose, write_warpfield, device)
+        self._lw = np.array([1, 0, 0, 0, 0, 0.1, 0, 0], dtype=np.float32)   # core/fusion.py:57
+        self._subsample_rate = subsample_rate
+        self._K = None
+        self._Kinv = None
+
+    def InitializeCanonicalSpace(self, tsdf=None, depths=None, lws=None, K=None, tsdf_size=256, *, tsdf_shape=None,
+                                 slab=None, vertices=None, normals=None, faces=None, nodes=None, radius=None):
+        """core/fusion.py:73-96.  The reference extracts the canonical surface with marching cubes and samples
+        the nodes from it; surface extraction is out of scope here, so the canonical `vertices`/`normals`
+        (and optionally ready-made `nodes`) are passed in.  `slab=(x0,x1)` keeps only that x-range of the
+        volume on this GPU (multi-GPU sharding); `tsdf_shape` creates the fresh volume (tsdf=+tdist, w=0)."""
+        if K is not None:
+            self._K = np.asarray(K, dtype=np.float64)
+            self._Kinv = np.linalg.inv(self._K)
+        if tsdf is not None:
+            self._set_volume(tsdf, None, shape=tsdf_shape, slab=slab)
+            self._vol.weight.zero_()
+        else:
+            shape = tuple(tsdf_shape) if tsdf_shape is not None else (tsdf_size,) * 3
+            self._vol = None
+            self._set_volume(None, None, shape=shape, slab=slab)
+            if depths is not None and lws is not None and self._K is not None:
+                for dm, lw in zip(depths, lws):
+                    d = engine._to_dev(dm, torch.float32, self._device)
+                    engine.fuse_depth_rigid(self._vol, shape[0], d, lw, self._K, self._Kinv, 1.0, None, self._tdist, 100.0)
+        if vertices is not None:
+            self._vertices = np.asarray(vertices, dtype=np.float32)
+            self._normals = None if normals is None else np.asarray(normals, dtype=np.float32)
+            self._faces = faces
+        if radius is not None:
+            self._radius = float(radius)
+        elif self._vertices is not None and faces is not None and len(faces):
+            f = np.asarray(faces)
+            v = self._vertices.astype(np.float64)
+            e = (np.linalg.norm(v[f[:, 0]] - v[f[:, 1]], axis=1) + np.linalg.norm(v[f[:, 0]] - v[f[:, 2]], axis=1)
+                 + np.linalg.norm(v[f[:, 1]] - v[f[:, 2]], axis=1)) / 3
+            self._radius = self._subsample_rate * float(e.mean())     # core/fusion.py:89-92
+        if nodes is not None:
+            self._nodes = nodes
+            if self._vertices is not None:
+                self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
+        elif self._vertices is not None and self._radius is not None:
+            self.construct_graph()
+
+    def construct_graph(self):
+        """core/fusion.py:101-123: radius-based node sampling from the canonical vertices, initial node dq
+        [1,0,0,0,0,.01,.01,0] (Q5), w = 2*radius, vertex->node kNN table."""
+        from .synth import uniform_sample
+        nodes_v, nodes_idx = uniform_sample(self._vertices, self._radius)
+        dq0 = np.array([1, 0.00, 0.00, 0.00, 0.00, 0.01, 0.01, 0.00], dtype=np.float32)
+        self._nodes = [(int(nodes_idx[i]), nodes_v[i], dq0, 2 * self._radius) for i in range(len(nodes_v))]
+        self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
+
+    # ---- a1 ---------------------------------------------------------------------------------------
+    def updateTSDF(self, curr_tsdf=None, wmax=100.0):
+        """core/fusion.py:153-198 (volume-sampling warped update; Q1 trilinear, Q4 weights)."""
+        if curr_tsdf is not None:
+            self._curr_tsdf = curr_tsdf
+        if self._curr_tsdf is None:
+            raise ValueError('tsdf of live frame has not been loaded')
+        if not isinstance(self._curr_tsdf, (np.ndarray, torch.Tensor)):
+            raise ValueError('Only accept 3D np array as tsdf')
+        elif self._curr_tsdf.ndim != 3:
+            raise ValueError('Only accept 3D np array as tsdf')
+        curr = engine._to_dev(self._curr_tsdf, torch.float32, self._device)
+        engine.update_volume(self._vol, self._wf, self._lw, curr, self._tdist, wmax, mode=self._mode)
+
+    # ---- a3 ---------------------------------------------------------------------------------------
+    def fuseFrame(self, depths, K=None, extrinsics=None, wmax=100.0, mode=None, want_masks=False):
+        """The north-star path (README.md:9-14 TODO of the reference): warp every voxel centre canonical->live
+        (`warp`, m_lw=self._lw), project through K, fold the depth measurement(s) into (v,w) with the rule of
+        FusionDM.fuseDepths.  depths: (rows,cols) or (V,rows,cols), host numpy or CUDA tensor, negative depth."""
+        if K is not None:
+            self._K = np.asarray(K, dtype=np.float64)
+            self._Kinv = np.linalg.inv(self._K)
+        if self._K is None:
+            raise ValueError('camera intrinsics K have not been set')
+        d = engine._to_dev(depths, torch.float32, self._device)
+        if d.dim() == 2:
+            d = d[None]
+        if d.dim() != 3:
+            raise ValueError('depth maps must be (rows, cols) or (views, rows, cols)')
+        if extrinsics is not None and len(extrinsics) != d.shape[0]:
+            raise ValueError('length of camera matrix array must equal that of depth maps')
+        return engine.update_projective(self._vol, self._wf, self._lw, d, self._K, self._Kinv, extrinsics, self._tdist, wmax,
+                                        mode=self._mode if mode is None else mode, want_masks=want_masks)
+
+    # ---- solve (core/fusion.py:327-491) -------------------------------------------------------------
+    def _problem(self):
+        if self._vertices is None or self._normals is None:
+            raise ValueError('canonical vertices/normals have not been set')
+        corr = np.asarray(self._correspondences, dtype=np.float64)
+        if len(corr) != len(self._vertices):
+            raise ValueError("Please first call setupCorrespondences to compute point to point correspondences between canonical and live frame vertices!")
+        return _gn.Problem(self._wf, self._vertices, self._normals, corr, np.asarray(self._neighbor_look_up), self._node_vertex_idx)
+
+    def computef(self, x, tdw, trw, rw):
+        """core/fusion.py:459-491: residual vector (V + 3*k*N,), float64."""
+        return self._problem().residuals(np.asarray(x, dtype=np.float64), self._lw, rw).cpu().numpy()
+
+    def computef_lw(self, x, tdw, trw):
+        """core/fusion.py:444-456: data term as a function of the global rigid dq."""
+        return self._problem().residuals_lw(np.asarray(x, dtype=np.float64)).cpu().numpy()
+
+    def computeSparsity(self, n, m):
+        """Jacobian sparsity.  NOT the reference's pattern (core/fusion.py:416-442 declares only 3N of the 3kN
+        regularisation rows): this is the correct one -- data row i -> the 8 columns of each of its k
+        nodes; reg row (i,j,c) -> the 16 columns of nodes i and j."""
+        return _gn.sparsity(np.asarray(self._neighbor_look_up), self._node_vertex_idx, len(self._vertices), self._wf.n_nodes, n, m)
+
+    def solve(self, correspondences=None, method='cnn', precompute_lw=True, tukey_data_weight=0.2,
+              huber_regularization_weight=0.001, regularization_weight=1, *, gn_iterations=15, gn_options=None):
+        """core/fusion.py:327-412.  Same call surface and outer schedule (rigid lw fit, then up to 3 warp-field
+        rounds with the rw /= 8 relaxation); the inner optimiser is a damped Gauss-Newton on the explicitly
+        assembled normal equations instead of scipy's finite-difference TRF/LSMR."""
+        if correspondences is not None:
+            self._correspondences = correspondences
+            if len(self._correspondences) != len(self._vertices):
+                raise ValueError("Please first call setupCorrespondences to compute point to point correspondences between canonical and live frame vertices!")
+        iteration = 3 if method == 'clpts' else 1
+        self._itercounter += 1
+        opts = dict(gn_options or {})
+        prob = self._problem()
+        if precompute_lw:
+            self._lw = prob.solve_lw(np.asarray(self._lw, dtype=np.float64), max_iter=opts.get("lw_iterations", 20), verbose=self._verbose)
+            if method == 'clpts' and correspondences is None:
+                self.setupCorrespondences(self._curr_tsdf, method='clpts')
+        rw = regularization_weight
+        for it in range(iteration):
+            if it > 0 and correspondences is None:
+                self.setupCorrespondences(self._curr_tsdf, method='clpts')
+            x0 = self._wf.node_dq.double().reshape(-1)
+            res = prob.gauss_newton(x0, self._lw, rw, max_iter=gn_iterations, huber=opts.get("huber", True),
+                                    f_scale=opts.get("f_scale", 1.0), verbose=self._verbose, **opts.get("gn", {}))
+            self._wf.set_dq(res.x.reshape(-1, 8).float())        # written back un-normalised (core/fusion.py:400-403)
+            self.last_solve = res
+            reduct_rate = (res.cost0 - res.cost) / res.cost0 if res.cost0 > 0 else 0.0
+            if 0.05 < reduct_rate < 0.9:
+                rw /= 8
+            else:
+                break
+
+
+class FusionDM(_FusionBase):
+    """Multi-view rigid depth-map fusion (core/fusion_dm.py:53)."""
+
+    def __init__(self, trunc_distance, K, tsdf_res=256, subsample_rate=5.0, knn=4, marching_cubes_step_size=3,
+                 verbose=False, write_warpfield=True, device=None):
+        self._init_state(trunc_distance, knn, marching_cubes_step_size, verbose, write_warpfield, device)
+        self._tsdf_res = tsdf_res
+        self._set_volume(None, None, shape=(tsdf_res,) * 3)           # tsdf = +tdist, w = 0 (core/fusion_dm.py:61-62)
+        self._lw = np.array([1, 0, 0, 0, 0, 0, 0, 0], dtype=np.float32)
+        self._K = np.asarray(K, dtype=np.float64)
+        self._Kinv = np.linalg.inv(self._K)
+        self._IND = np.eye(4)
+        self._INDinv = np.linalg.inv(self._IND)
+        self._subsample_rate = subsample_rate
+
+    def fuseDepths(self, dm, lw, tsdf, tsdf_w, scale=1.0, center=np.zeros(3), wmax=100.0):
+        """core/fusion_dm.py:180-217.  numpy in -> numpy out exactly like the reference (one upload + one
+        read-back); CUDA tensors in -> updated in place on the device and returned, no host traffic."""
+        on_device = isinstance(tsdf, torch.Tensor) and tsdf.is_cuda
+        if tsdf.ndim != 3:
+            raise ValueError('Only 3D numpy array is accepted as tsdf')
+        if on_device:
+            if tsdf.dtype != torch.float32 or tsdf_w.dtype != torch.float32:
+                raise ValueError('device volumes must be float32')
+            vol = engine.DeviceVolume(tuple(tsdf.shape), device=tsdf.device, tsdf=tsdf, weight=tsdf_w)
+            vol.tsdf, vol.weight = tsdf, tsdf_w
+        else:
+            vol = engine.DeviceVolume(tuple(tsdf.shape), device=self._device, tsdf=tsdf, weight=tsdf_w)
+        d = engine._to_dev(dm, torch.float32, self._device)
+        if d.dim() != 2:
+            raise ValueError('depth map must be 2-D')
+        engine.fuse_depth_rigid(vol, self._tsdf_res, d, lw, self._K, self._Kinv, scale, center, self._tdist, wmax, mode=self._mode)
+        self._last_vol = vol
+        if on_device:
+            return (tsdf, tsdf_w)
+        out_t = vol.tsdf.cpu().numpy().astype(_as_np(tsdf).dtype, copy=False)
+        out_w = vol.weight.cpu().numpy().astype(_as_np(tsdf_w).dtype, copy=False)
+        if isinstance(tsdf, np.ndarray):
+            tsdf[...] = out_t
+            tsdf_w[...] = out_w
+            return (tsdf, tsdf_w)
+        return (out_t, out_w)
+
+    def compute_live_tsdf(self, depths, lws, UseAutoAlignment=False, useICP=False, outputMesh=False):
+        """core/fusion_dm.py:95-178, plain multi-view branch: the volume stays on the device across views."""
+        if len(depths) != len(lws):
+            raise ValueError('length of camera matrix array Ks must equal that of depth maps')
+        if UseAutoAlignment or useICP or outputMesh:
+            raise NotImplementedError("auto-alignment / ICP / mesh output are outside the hot path (SURVEY 2 row 2)")
+        avg = np.array([-0.03, -0.43, -5.6], dtype='float32')       # core/fusion_dm.py:106-107
+        std = 1.3
+        scale = 8 * std / self._tsdf_res
+        self._IND[0, 0] = self._IND[1, 1] = self._IND[2, 2] = scale
+        self._IND[0:3, 3] = avg - scale * self._tsdf_res / 2
+        self._INDinv = np.linalg.inv(self._IND)
+        self._vol = None
+        self._set_volume(None, None, shape=(self._tsdf_res,) * 3)
+        for idx in range(len(depths)):
+            self._depthidx = idx
+            d = engine._to_dev(depths[idx], torch.float32, self._device)
+            engine.fuse_depth_rigid(self._vol, self._tsdf_res, d, lws[idx], self._K, self._Kinv, 12 * std / self._tsdf_res, avg,
+                                    self._tdist, 100.0, mode=self._mode)
+        return (self._tsdf, self._tsdfw)
+
+    def updateTSDF(self, curr_tsdf, wmax=100.0):
+        """core/fusion_dm.py:300-316: rigid volume->volume fusion with the global dq `_lw`."""
+        if curr_tsdf is None:
+            raise ValueError('tsdf of live frame has not been loaded')
+        if curr_tsdf.ndim != 3:
+            raise ValueError('Only accept 3D np array as tsdf')
+        curr = engine._to_dev(curr_tsdf, torch.float32, self._device)
+        engine.update_volume(self._vol, None, self._lw, curr, self._tdist, wmax, mode=self._mode, rigid=True)
+
+    def solve(self, curr_tsdf):
+        raise NotImplementedError("FusionDM.solve needs marching-cubes correspondences (core/fusion_dm.py:219-244; SURVEY 8f rank 1); "
+                                  "use Fusion.solve(correspondences=...) with k-nearest nodes for the rigid+non-rigid fit")
+
+
+class FusionDM_GPU(FusionDM):
+    """Name kept for drop-in with test.py:158-159 (`FusionDM_GPU(0.2, K, tsdf_res=256, verbose=True)`)."""

@@ -97,21 +97,24 @@ def dq_apply(dq, p):
     return rot + 2 * (w * dv - dw * v + np.cross(v, dv))
 
 
-def smooth_warp_field(node_pos, rng, max_angle_deg=5.0, trans_sigma=0.5, extent=64.0):
-    """Smooth random SE(3) per node: a small rotation about the node itself plus a small translation,
-    both low-frequency functions of position; returned as unit dual quaternions (N,8) float32."""
+def smooth_warp_field(node_pos, rng, max_disp=0.3, extent=64.0):
+    """Smooth random SE(3) per node as unit dual quaternions (N,8) float32: a small rotation about the
+    node itself plus a small translation, both low-frequency functions of position.
+
+    The magnitudes are bounded on purpose.  The reference normalises the blended dual quaternion by its
+    8-vector norm (Q2, core/fusion.py:551), so a blend whose dual part is not << 1 -- i.e. a node
+    translation t = c - R c + d of more than a fraction of a voxel -- contracts space by
+    1/(1 + |t|^2/4).  `max_disp` (voxels) bounds |t| so that the synthetic live frame stays a plausible
+    small inter-frame motion under the reference's own arithmetic."""
     p = node_pos.astype(np.float64)
     n = len(p)
     f = rng.uniform(0.5, 1.5, size=(7, 3)) * (2 * np.pi / extent)
     ph = rng.uniform(0, 2 * np.pi, size=7)
     fields = np.sin(p @ f.T + ph)                       # (N,7) smooth in space
     axis = fields[:, 0:3] + 1e-3
-    angle = np.deg2rad(max_angle_deg) * 0.5 * (1 + fields[:, 3])
-    d = trans_sigma * fields[:, 4:7]
-    dq0 = axis_angle_dq(axis, angle, np.zeros((n, 3)))
-    rp = dq_apply(dq0, p)                               # R p
-    t = p - rp + d                                      # rotate about the node, then shift
-    return axis_angle_dq(axis, angle, t).astype(np.float32)
+    angle = 0.5 * max_disp / np.maximum(np.linalg.norm(p, axis=1), 1.0) * 0.5 * (1 + fields[:, 3])
+    d = 0.5 * max_disp * fields[:, 4:7]
+    return axis_angle_dq(axis, angle, d).astype(np.float32)
 
 
 def blend_warp(points, node_pos, node_dq, node_w, knn_idx, lw=None):
@@ -228,7 +231,7 @@ class Scene:
 
 
 def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=480, cols=640, tdist=None,
-               max_angle_deg=5.0, trans_sigma=None, lw_dtype=np.float64, unit_init=False, mesh_path=None,
+               max_disp=0.3, lw_dtype=np.float64, unit_init=False, mesh_path=None,
                focal=None, cam_dist=1.7, background=False):
     """Seeded benchmark / test scene.  `radius` in units of the 64^3 mesh; either `radius` or
     `n_nodes` (bisection on the radius) may be given.  One view: the global rigid dq `lw` is the camera
@@ -254,12 +257,10 @@ def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=4
     node_pos = verts[node_idx].copy()
     r_grid = float(radius * scale)
     node_w = 2.0 * r_grid
-    if trans_sigma is None:
-        trans_sigma = 0.5 * res / 64.0
     if unit_init:
         node_dq = np.tile(np.array([1, 0, 0, 0, 0, 0.01, 0.01, 0], dtype=np.float32), (len(node_pos), 1))  # Q5
     else:
-        node_dq = smooth_warp_field(node_pos, rng, max_angle_deg, trans_sigma, extent=float(res))
+        node_dq = smooth_warp_field(node_pos, rng, max_disp, extent=float(res))
     tree = cKDTree(node_pos.astype(np.float64))
     _, vert_knn = tree.query(verts.astype(np.float64), k=k)
     vert_knn = np.atleast_2d(vert_knn).reshape(len(verts), k).astype(np.int64)
@@ -295,7 +296,7 @@ def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=4
             dm[dm == 0] = -np.float32(dist + 0.9 * res)
         depths.append(dm)
     if tdist is None:
-        tdist = 3.0 * res / 64.0   # 0.2 world units of test.py:159 ~ 3 voxels at 64^3
+        tdist = 5.0 * res / 256.0  # test.py:159: 0.2 world units in a volume 8*std = 10.4 units wide (fusion_dm.py:107,136)
     return Scene(res=res, k=k, vertices=verts, normals=nrm, faces=faces, node_pos=node_pos, node_idx=node_idx,
                  node_dq=node_dq, node_w=node_w, radius=r_grid, lw=lw, K=K, Kinv=Kinv, rows=rows, cols=cols,
                  extrinsics=extr, depths=np.stack(depths), tdist=float(tdist), vert_knn=vert_knn,

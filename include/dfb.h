@@ -34,6 +34,8 @@ extern "C" {
 
 #define DFB_MODE_HYBRID 0 /* fp32 classify + clamped update, reference-exact fp64 pass for the rest */
 #define DFB_MODE_EXACT 1  /* every voxel through the reference-exact pass (validation / debugging) */
+#define DFB_MODE_FAST_ONLY 2 /* profiling: pass 1 only (deferred voxels are left untouched, list is filled) */
+#define DFB_MODE_LIST_ONLY 3 /* profiling: pass 2 only, over the list a DFB_MODE_FAST_ONLY call left behind */
 
 typedef void* dfb_stream_t; /* cudaStream_t */
 
@@ -115,6 +117,52 @@ int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const float* depth
  * idx [m][k]; outputs float64 [m][3], computed with the reference's arithmetic. */
 int dfb_warp_points(const float* pts, const float* normals, int64_t m, const int32_t* idx, const dfb_warpfield* wf,
                     double* out_pts, double* out_normals, dfb_stream_t stream);
+
+/* a5: Fusion.dq_blend (core/fusion.py:527-551) for float32 points: blended, 8-norm-normalised dq [m][8] float64. */
+int dfb_dq_blend_points(const float* pts, int64_t m, const int32_t* idx, const dfb_warpfield* wf, double* out_dq,
+                        dfb_stream_t stream);
+
+/* ---- warp-field least squares (Fusion.solve, core/fusion.py:327-491) ------------------------------------ */
+typedef struct dfb_gn_problem {
+    int64_t n_vert;
+    const float* vertices;    /* [V][3]  Fusion._vertices */
+    const float* normals;     /* [V][3]  Fusion._normals */
+    const double* corr;       /* [V][3]  Fusion._correspondences */
+    const int32_t* vert_knn;  /* [V][k]  Fusion._neighbor_look_up */
+    int n_nodes, k;
+    const float* node_pos;    /* [N][3] */
+    const float* node_w;      /* [N] */
+    const int32_t* node_nbr;  /* [N][k]  _neighbor_look_up[_nodes[i][0]] (core/fusion.py:477) */
+    double lw[8];             /* Fusion._lw */
+    int lw_is_f32;
+    double rw;                /* regularization_weight */
+    int huber;                /* 1: IRLS weights min(1, f_scale/|f|) (scipy loss='huber' counterpart) */
+    double f_scale;
+} dfb_gn_problem;
+
+/* a9: Fusion.computef (core/fusion.py:459-491): f [V + 3*k*N], reference arithmetic.  x = node dual quaternions
+ * [N][8] as float64 values; x_is_f32: they are float32 in the reference (its first call, core/fusion.py:373-375). */
+int dfb_gn_residuals(const dfb_gn_problem* prob, const double* x, int x_is_f32, double* f_out, dfb_stream_t stream);
+/* a11: Fusion.computef_lw (core/fusion.py:444-456): f [V] as a function of the global rigid dq `lw` (host, 8). */
+int dfb_gn_residuals_lw(const dfb_gn_problem* prob, const double* node_dq, int dq_is_f32, const double* lw, int lw_is_f32,
+                        double* f_out, dfb_stream_t stream);
+/* Block pattern of J^T J over node pairs (the CORRECT pattern; core/fusion.py:416-442 is not reproduced).
+ * rows: marks bitmap [N][ceil(N/32)], writes row_ptr [N+1] (row_ptr[N] = number of 8x8 blocks);
+ * cols: writes col_idx [row_ptr[N]] ascending per row. */
+int dfb_gn_pattern_rows(const dfb_gn_problem* prob, uint32_t* bitmap, int32_t* row_ptr, dfb_stream_t stream);
+int dfb_gn_pattern_cols(int n_nodes, const uint32_t* bitmap, const int32_t* row_ptr, int32_t* col_idx, dfb_stream_t stream);
+/* Analytic Jacobian -> BSR normal equations H = J^T W J [nnzb][8][8], g = J^T W f [N][8], cost[0] = robust cost,
+ * cost[1] = 0.5 |f|^2 (all zeroed first).  Replaces scipy's finite-difference Jacobian (core/fusion.py:382-392). */
+int dfb_gn_normal_eq(const dfb_gn_problem* prob, const double* x, const int32_t* row_ptr, const int32_t* col_idx, int64_t nnzb,
+                     double* H, double* g, double* cost, dfb_stream_t stream);
+/* 8x8 normal equations of the rigid fit (core/fusion.py:356-360): H8 [64], g8 [8], cost [2] on the device. */
+int dfb_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* node_dq, const double* lw, double* H8, double* g8, double* cost,
+                        dfb_stream_t stream);
+/* Damped node-space solve (H + lambda*mean(diag H)*I) delta = -g by block-Jacobi PCG, then x_new = x + delta.
+ * workspace: dfb_gn_solve_workspace_doubles(N) doubles; workspace[0..7] = {mu, rz, -, -, rz0, converged, iterations, trace}. */
+int64_t dfb_gn_solve_workspace_doubles(int n_nodes);
+int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, double lambda,
+                 int max_iter, double tol, const double* x, double* x_new, double* delta, double* workspace, dfb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -143,3 +143,95 @@ extern "C" int hs_warp_points(const float* pts, const float* normals, int64_t m,
     }
     return DFB_OK;
 }
+
+// ---- Gauss-Newton path: the kernels' per-residual functions (dfb_gn.h), dense assembly for small problems -------
+#include "../../dynamicfusion_body_b200/csrc/dfb_gn.h"
+
+static GNParams hs_params(const dfb_gn_problem* p) {
+    GNParams P;
+    P.n_vert = p->n_vert; P.vertices = p->vertices; P.normals = p->normals; P.corr = p->corr; P.vert_knn = p->vert_knn;
+    P.n_nodes = p->n_nodes; P.k = p->k; P.node_pos = p->node_pos; P.node_w = p->node_w; P.node_nbr = p->node_nbr;
+    for (int i = 0; i < 8; ++i) P.lw[i] = p->lw[i];
+    P.lw_is_f32 = p->lw_is_f32;
+    dq_to_affine(p->lw, P.A);
+    P.rw = p->rw; P.huber = p->huber; P.f_scale = p->f_scale > 0 ? p->f_scale : 1.0;
+    return P;
+}
+
+extern "C" int hs_gn_residuals(const dfb_gn_problem* prob, const double* x, int x_is_f32, double* f) {
+    const GNParams P = hs_params(prob);
+    for (int64_t i = 0; i < P.n_vert; ++i) f[i] = data_residual_ref(P, x, x_is_f32 != 0, P.lw, P.lw_is_f32 != 0, i);
+    for (int i = 0; i < P.n_nodes; ++i)
+        for (int jj = 0; jj < P.k; ++jj) reg_residual_ref(P, x, x_is_f32 != 0, i, jj, f + P.n_vert + 3 * ((int64_t)i * P.k + jj));
+    return 0;
+}
+
+extern "C" int hs_gn_residuals_lw(const dfb_gn_problem* prob, const double* dq, int dq_is_f32, const double* lw, int lw_is_f32, double* f) {
+    const GNParams P = hs_params(prob);
+    for (int64_t i = 0; i < P.n_vert; ++i) f[i] = data_residual_ref(P, dq, dq_is_f32 != 0, lw, lw_is_f32 != 0, i);
+    return 0;
+}
+
+// dense H [8N][8N], g [8N], cost[2] with the same per-residual functions / weights as normal_eq_*_kernel
+extern "C" int hs_gn_normal_eq_dense(const dfb_gn_problem* prob, const double* x, double* H, double* g, double* cost) {
+    const GNParams P = hs_params(prob);
+    const int64_t n8 = 8 * (int64_t)P.n_nodes;
+    for (int64_t i = 0; i < n8 * n8; ++i) H[i] = 0;
+    for (int64_t i = 0; i < n8; ++i) g[i] = 0;
+    cost[0] = cost[1] = 0;
+    for (int64_t i = 0; i < P.n_vert; ++i) {
+        double r, gv[8], wts[DFB_MAX_K];
+        data_residual_jac(P, x, i, &r, gv, wts);
+        const double om = huber_weight(r, P.huber, P.f_scale);
+        const int32_t* ids = P.vert_knn + i * P.k;
+        for (int a = 0; a < P.k; ++a) {
+            for (int b = 0; b < P.k; ++b)
+                for (int rr = 0; rr < 8; ++rr)
+                    for (int cc = 0; cc < 8; ++cc) H[(8 * (int64_t)ids[a] + rr) * n8 + 8 * ids[b] + cc] += om * wts[a] * wts[b] * gv[rr] * gv[cc];
+            for (int c = 0; c < 8; ++c) g[8 * (int64_t)ids[a] + c] += om * wts[a] * r * gv[c];
+        }
+        cost[0] += huber_rho(r, P.huber, P.f_scale);
+        cost[1] += 0.5 * r * r;
+    }
+    for (int i = 0; i < P.n_nodes; ++i)
+        for (int jj = 0; jj < P.k; ++jj) {
+            double r[3], Ji[3][8], Jj[3][8];
+            const int j = reg_residual_jac(P, x, i, jj, r, Ji, Jj);
+            for (int t = 0; t < 3; ++t) {
+                const double om = huber_weight(r[t], P.huber, P.f_scale);
+                cost[0] += huber_rho(r[t], P.huber, P.f_scale);
+                cost[1] += 0.5 * r[t] * r[t];
+                if (j == i) continue;
+                for (int a = 0; a < 8; ++a) {
+                    for (int b = 0; b < 8; ++b) {
+                        H[(8 * (int64_t)i + a) * n8 + 8 * i + b] += om * Ji[t][a] * Ji[t][b];
+                        H[(8 * (int64_t)i + a) * n8 + 8 * j + b] += om * Ji[t][a] * Jj[t][b];
+                        H[(8 * (int64_t)j + a) * n8 + 8 * i + b] += om * Jj[t][a] * Ji[t][b];
+                        H[(8 * (int64_t)j + a) * n8 + 8 * j + b] += om * Jj[t][a] * Jj[t][b];
+                    }
+                    g[8 * (int64_t)i + a] += om * Ji[t][a] * r[t];
+                    g[8 * (int64_t)j + a] += om * Jj[t][a] * r[t];
+                }
+            }
+        }
+    return 0;
+}
+
+extern "C" int hs_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* dq, const double* lw, double* H8, double* g8, double* cost) {
+    const GNParams P = hs_params(prob);
+    for (int i = 0; i < 64; ++i) H8[i] = 0;
+    for (int i = 0; i < 8; ++i) g8[i] = 0;
+    cost[0] = cost[1] = 0;
+    for (int64_t i = 0; i < P.n_vert; ++i) {
+        double r, J[8];
+        lw_residual_jac(P, dq, lw, i, &r, J);
+        const double om = huber_weight(r, P.huber, P.f_scale);
+        for (int a = 0; a < 8; ++a) {
+            for (int b = 0; b < 8; ++b) H8[a * 8 + b] += om * J[a] * J[b];
+            g8[a] += om * J[a] * r;
+        }
+        cost[0] += huber_rho(r, P.huber, P.f_scale);
+        cost[1] += 0.5 * r * r;
+    }
+    return 0;
+}

@@ -16,7 +16,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "dynamicfusion_body_b200", "csrc")
 
 
 def build(force=False):
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h")]
     if not force and os.path.isfile(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", _SRC, "-o", _SO])
@@ -167,3 +167,64 @@ def warp_points(pts, normals, idx, wf):
     s = wf.struct()
     _check(lib().hs_warp_points(_p(pts), _p(normals), len(pts), _p(idx), C.byref(s), _p(out), _p(outn)))
     return (out, outn) if normals is not None else out
+
+
+# ---- Gauss-Newton path ------------------------------------------------------------------------------------------
+class HostGN:
+    """Host arrays + dfb_gn_problem struct for the hostshim GN entry points."""
+
+    def __init__(self, vertices, normals, corr, vert_knn, node_pos, node_w, node_vertex_idx, lw, rw, huber=False, f_scale=1.0):
+        self.vertices = np.ascontiguousarray(vertices, dtype=np.float32)
+        self.normals = np.ascontiguousarray(normals, dtype=np.float32)
+        self.corr = np.ascontiguousarray(corr, dtype=np.float64)
+        self.vert_knn = np.ascontiguousarray(vert_knn, dtype=np.int32)
+        self.node_pos = np.ascontiguousarray(node_pos, dtype=np.float32)
+        n = len(self.node_pos)
+        self.node_w = np.ascontiguousarray(np.broadcast_to(np.asarray(node_w, dtype=np.float32), (n,)))
+        self.node_nbr = np.ascontiguousarray(self.vert_knn[np.asarray(node_vertex_idx)], dtype=np.int32)
+        p = _capi.GNProblem()
+        p.n_vert = len(self.vertices)
+        p.vertices = self.vertices.ctypes.data; p.normals = self.normals.ctypes.data; p.corr = self.corr.ctypes.data
+        p.vert_knn = self.vert_knn.ctypes.data
+        p.n_nodes = n; p.k = self.vert_knn.shape[1]
+        p.node_pos = self.node_pos.ctypes.data; p.node_w = self.node_w.ctypes.data; p.node_nbr = self.node_nbr.ctypes.data
+        lw = np.asarray(lw)
+        for i in range(8):
+            p.lw[i] = float(lw[i])
+        p.lw_is_f32 = 1 if lw.dtype == np.float32 else 0
+        p.rw = rw; p.huber = 1 if huber else 0; p.f_scale = f_scale
+        self.p = p
+        L = lib()
+        vp = C.c_void_p
+        L.hs_gn_residuals.argtypes = [C.POINTER(_capi.GNProblem), vp, C.c_int, vp]
+        L.hs_gn_residuals_lw.argtypes = [C.POINTER(_capi.GNProblem), vp, C.c_int, vp, C.c_int, vp]
+        L.hs_gn_normal_eq_dense.argtypes = [C.POINTER(_capi.GNProblem), vp, vp, vp, vp]
+        L.hs_gn_lw_normal_eq.argtypes = [C.POINTER(_capi.GNProblem), vp, vp, vp, vp, vp]
+
+    def residuals(self, x):
+        x = np.asarray(x)
+        xd = np.ascontiguousarray(x, dtype=np.float64)
+        f = np.zeros(self.p.n_vert + 3 * self.p.k * self.p.n_nodes)
+        lib().hs_gn_residuals(C.byref(self.p), _p(xd), 1 if x.dtype == np.float32 else 0, _p(f))
+        return f
+
+    def residuals_lw(self, node_dq, lw):
+        node_dq = np.asarray(node_dq); lw = np.asarray(lw)
+        dqd = np.ascontiguousarray(node_dq, dtype=np.float64); lwd = np.ascontiguousarray(lw, dtype=np.float64)
+        f = np.zeros(self.p.n_vert)
+        lib().hs_gn_residuals_lw(C.byref(self.p), _p(dqd), 1 if node_dq.dtype == np.float32 else 0, _p(lwd),
+                                 1 if lw.dtype == np.float32 else 0, _p(f))
+        return f
+
+    def normal_eq_dense(self, x):
+        xd = np.ascontiguousarray(x, dtype=np.float64)
+        n8 = 8 * self.p.n_nodes
+        H = np.zeros((n8, n8)); g = np.zeros(n8); cost = np.zeros(2)
+        lib().hs_gn_normal_eq_dense(C.byref(self.p), _p(xd), _p(H), _p(g), _p(cost))
+        return H, g, cost
+
+    def lw_normal_eq(self, node_dq, lw):
+        dqd = np.ascontiguousarray(node_dq, dtype=np.float64); lwd = np.ascontiguousarray(lw, dtype=np.float64)
+        H = np.zeros((8, 8)); g = np.zeros(8); cost = np.zeros(2)
+        lib().hs_gn_lw_normal_eq(C.byref(self.p), _p(dqd), _p(lwd), _p(H), _p(g), _p(cost))
+        return H, g, cost

@@ -1,0 +1,95 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/dfb.h declares
+(no compute without a GPU), the product refuses to run without CUDA, the synthetic-scene helpers behave."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    h = open(os.path.join(ROOT, "include", "dfb.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfb_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dynamicfusion_body_b200 import _capi, build
+    build.build()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), "missing export %s" % n
+    assert sorted(_capi.EXPORTS) == names
+    lib.dfb_version.restype = ctypes.c_int
+    assert lib.dfb_version() >= 100
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any CUDA call, so the error convention is testable on the CPU box."""
+    from dynamicfusion_body_b200 import _capi
+    lib = _capi.lib()
+    vol = _capi.Volume()
+    wf = _capi.WarpField()
+    views = _capi.Views()
+    ws = _capi.Workspace()
+    rc = lib.dfb_tsdf_update_projective(ctypes.byref(vol), ctypes.byref(wf), ctypes.byref(views), 1.0, 100.0, 0, ctypes.byref(ws), None, None, None)
+    assert rc == -1 and b"volume pointers are null" in lib.dfb_last_error()
+    rc = lib.dfb_knn_build_volume(None, 10, 4, 8, 8, 8, 0, 8, None, None)
+    assert rc == -1
+    rc = lib.dfb_knn_points(ctypes.c_void_p(8), 5, ctypes.c_void_p(8), 3, 4, ctypes.c_void_p(8), None)
+    assert rc == -1 and b"n_nodes=3 < k=4" in lib.dfb_last_error()
+    with pytest.raises(_capi.DfbError):
+        _capi.check(rc)
+
+
+def test_product_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from dynamicfusion_body_b200.fusion import Fusion, FusionDM
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Fusion(0.2, use_cnn=False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        FusionDM(0.2, np.eye(3), tsdf_res=8)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "dynamicfusion_body_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "hostshim" not in src or f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h"), f
+
+
+def test_uniform_sample_matches_reference_semantics():
+    """Greedy radius sampling (core/util.py:27-47): first alive point kept, strictly-closer points dropped."""
+    from dynamicfusion_body_b200 import synth
+    rng = np.random.default_rng(0)
+    pts = rng.random((300, 3)) * 10
+    s, idx = synth.uniform_sample(pts, 1.5)
+    cand = pts.copy(); loc = np.arange(len(pts)); keep = []
+    while len(cand):
+        keep.append(loc[0])
+        d = np.linalg.norm(cand - cand[0], axis=1)
+        cand, loc = cand[d >= 1.5], loc[d >= 1.5]
+    assert np.array_equal(idx, np.array(keep))
+    d = np.linalg.norm(s[:, None] - s[None], axis=2) + np.eye(len(s)) * 10
+    assert d.min() >= 1.5
+
+
+def test_scene_is_deterministic_and_consistent():
+    from dynamicfusion_body_b200 import synth
+    a = synth.make_scene(res=32, k=4, n_nodes=100, seed=7, rows=48, cols=64)
+    b = synth.make_scene(res=32, k=4, n_nodes=100, seed=7, rows=48, cols=64)
+    assert np.array_equal(a.depths, b.depths) and np.array_equal(a.node_dq, b.node_dq)
+    assert abs(a.n_nodes - 100) <= 5 and a.depths.shape == (1, 48, 64) and (a.depths <= 0).all()
+    assert np.allclose(np.linalg.norm(a.node_dq[:, :4], axis=1), 1, atol=1e-6)
+    t = a.nodes_as_reference_tuples()
+    assert len(t) == a.n_nodes and t[0][2].shape == (8,) and isinstance(t[0][3], float)

@@ -243,8 +243,8 @@ def test_warp_points_matches_oracle(small_scene):
     for lw in (np.array([1, 0, 0, 0, 0, 0.1, 0, 0], np.float32), sc.lw, None):
         p, n = engine.warp_points(wf, lw, sc.vertices, sc.normals, idx=sc.vert_knn)
         op, on = odq.warp(sc.vertices, sc.node_pos[sc.vert_knn], sc.node_dq[sc.vert_knn], nw, lw=lw, normal=sc.normals)
-        assert np.abs(p.cpu().numpy() - op).max() <= 1e-9 * max(1.0, np.abs(op).max())
-        assert np.abs(n.cpu().numpy() - on).max() <= 1e-12
+        assert np.abs(p.cpu().numpy() - op).max() <= 1e-7 * max(1.0, np.abs(op).max())
+        assert np.abs(n.cpu().numpy() - on).max() <= 1e-7
 
 
 def test_sequence_of_frames_stays_within_tolerance(small_scene):

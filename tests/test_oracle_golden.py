@@ -1,0 +1,131 @@
+"""Oracle (oracle/*.py) against the committed golden vectors produced by executing the unmodified reference
+(tests/golden/make_golden.py).  CPU only; needs neither the reference nor a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import dq as odq
+from oracle import gn as ogn
+from oracle import tsdf as ot
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.npz"))
+
+
+def test_quaternion_doctest_vector():
+    # core/util.py:258-260 / core/transformation.py:1371-1373
+    assert np.allclose(odq.quaternion_multiply([4, 1, -2, 3], [8, -5, 6, 7]), [28, -44, -14, 48])
+    assert np.array_equal(G["qmul_kat"], odq.quaternion_multiply([4, 1, -2, 3], [8, -5, 6, 7]))
+
+
+@pytest.mark.parametrize("tag", ["ff", "df", "fd", "dd"])
+def test_dqb_warp_bit_exact(tag):
+    assert np.array_equal(odq.dqb_warp(G["dqw_dq_" + tag], G["dqw_p_" + tag]), G["dqw_out_" + tag])
+    assert np.array_equal(odq.dqb_warp_normal(G["dqw_dq_" + tag], G["dqw_p_" + tag]), G["dqwn_out_" + tag])
+
+
+def test_interpolate_tsdf_and_none_cases():
+    val, valid = ot.interpolate_tsdf(G["interp_pts"], G["interp_vol"])
+    assert np.array_equal(valid, G["interp_valid"])
+    assert not valid[-5:-1].any() and valid[-7] and valid[-6]         # out-of-volume -> None (test.py:216-230)
+    assert np.array_equal(val[valid], G["interp_val"][valid])
+    with pytest.raises(ValueError):
+        ot.interpolate_tsdf(np.zeros(3), np.zeros((3, 3)))
+
+
+def _a1_inputs():
+    R = G["a1_tsdf0"].shape[0]
+    vox = ot.voxel_grid((R, R, R))
+    N = len(G["a1_node_pos"])
+    return R, vox, np.full(N, float(G["a1_node_w"]))
+
+
+def test_knn_matches_kdtree():
+    R, vox, _ = _a1_inputs()
+    idx, d2 = odq.knn_bruteforce(vox, G["a1_node_pos"], int(G["a1_k"]))
+    tie = odq.knn_has_tie(d2)
+    assert np.array_equal(idx[~tie], G["knn_idx"][~tie])
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_update_volume_a1_bit_exact(tag):
+    R, vox, nw = _a1_inputs()
+    v, w, m = ot.update_volume(G["a1_tsdf0"].ravel(), G["a1_w0"].ravel(), G["a1_curr"], vox, G["knn_idx"], G["a1_node_pos"],
+                               G["a1_node_dq"], nw, G["a1_lw_" + tag], float(G["a1_tdist"]))
+    assert np.array_equal(v, G["a1_tsdf_" + tag].ravel())
+    assert np.array_equal(w, G["a1_w_" + tag].ravel())
+    assert 0.3 < m.mean() < 1.0
+
+
+def test_fuse_depth_rigid_a2():
+    R, vox, _ = _a1_inputs()
+    K = G["a2_K"]
+    v, w, m, fr = ot.fuse_depth_rigid(G["a1_tsdf0"].ravel(), G["a1_w0"].ravel(), vox, G["a2_dm"], G["a2_lw34"], K, np.linalg.inv(K),
+                                      float(G["a1_tdist"]), R, scale=float(G["a2_scale"]), center=G["a2_center"])
+    assert np.abs(v - G["a2_tsdf"].ravel()).max() <= 1e-14      # matmul summation order only
+    assert np.array_equal(w, G["a2_w"].ravel())
+    assert m.sum() > 0
+
+
+def test_rigid_volume_update():
+    R, vox, _ = _a1_inputs()
+    v, w, m = ot.update_rigid_volume(G["a1_tsdf0"].ravel(), G["a1_w0"].ravel(), G["a1_curr"], vox,
+                                     np.array([1, 0, 0, 0, 0, 0.1, 0, 0], dtype=np.float32), float(G["a1_tdist"]))
+    assert np.array_equal(v, G["rigidvol_tsdf"].ravel())
+    assert np.array_equal(w, G["rigidvol_w"].ravel())
+
+
+def test_warp_and_blend():
+    nw = float(G["a1_node_w"])
+    kk = G["warp_knn"]
+    lw = np.array([1, 0, 0, 0, 0, 0.1, 0, 0], dtype=np.float32)
+    p, n = odq.warp(G["warp_pts"], G["a1_node_pos"][kk], G["a1_node_dq"][kk], np.full(kk.shape, nw), lw=lw, normal=G["warp_nrm"])
+    assert np.array_equal(p, G["warp_out_p"]) and np.array_equal(n, G["warp_out_n"])
+    b = odq.dq_blend(G["warp_pts"], G["a1_node_pos"][kk], G["a1_node_dq"][kk], np.full(kk.shape, nw))
+    assert np.abs(b - G["blend_out"]).max() <= 4e-16           # la.norm (ddot) vs einsum summation order
+    # warp() with its own lookup = query(k+1)[:-1] = k nearest
+    idx, _ = odq.knn_bruteforce(G["warp_pts"], G["a1_node_pos"], kk.shape[1])
+    p2 = odq.warp(G["warp_pts"], G["a1_node_pos"][idx], G["a1_node_dq"][idx], np.full(kk.shape, nw), lw=lw)
+    assert np.array_equal(p2, G["warp_auto_p"])
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_computef(tag):
+    lw = np.array([1, 0, 0, 0, 0, 0.1, 0, 0], dtype=np.float32) if tag == "f32" else G["a1_lw_f64"]
+    args = (G["cf_verts"], G["cf_norms"], G["cf_corr"], G["cf_knn"], G["a1_node_pos"], float(G["a1_node_w"]), G["cf_nvi"], lw, 0.5)
+    x32 = G["a1_node_dq"].reshape(-1)
+    f32 = ogn.computef(x32, *args)
+    f64 = ogn.computef(G["cf_x64_" + tag], *args)
+    k, N, V = 4, len(G["a1_node_pos"]), len(G["cf_verts"])
+    assert f32.shape == (V + 3 * k * N,)
+    assert np.abs(f32 - G["cf_f32_" + tag]).max() <= 1e-13
+    assert np.abs(f64 - G["cf_f64_" + tag]).max() <= 1e-13
+    flw = ogn.computef_lw(lw.astype(np.float64) + 1e-3, G["cf_verts"], G["cf_norms"], G["cf_corr"], G["cf_knn"], G["a1_node_pos"],
+                          G["a1_node_dq"], float(G["a1_node_w"]))
+    assert np.abs(flw - G["cflw_" + tag]).max() <= 1e-13
+
+
+def test_analytic_jacobian_vs_finite_differences():
+    """The Jacobian oracle against scipy's finite differences (what the reference's least_squares call computes)."""
+    from scipy.optimize._numdiff import approx_derivative
+    lw = G["a1_lw_f64"]
+    args = (G["cf_verts"], G["cf_norms"], G["cf_corr"], G["cf_knn"], G["a1_node_pos"], float(G["a1_node_w"]), G["cf_nvi"], lw, 0.5)
+    x = G["cf_x64_f64"]
+    J, r = ogn.jacobian(x, *args)
+    smooth = lambda xx: ogn.jacobian(xx, *args)[1]
+    Jfd = approx_derivative(smooth, x, method="3-point")
+    assert np.abs(J.toarray() - Jfd).max() <= 1e-7 * np.abs(Jfd).max()
+    # the reference-arithmetic residual differs from the smooth model only by its float32 roundings (Q3)
+    assert np.abs(ogn.computef(x, *args) - r).max() <= 1e-4
+    # 2-point FD of the reference-arithmetic function is exactly what scipy's jac='2-point' hands the reference's
+    # optimiser (core/fusion.py:385).  Its step (1.5e-8 |x|) is far below the float32 quantisation of the warped point
+    # (Q3, core/util.py:69), so that Jacobian is dominated by rounding noise -- errors of the order of the entries
+    # themselves.  Recorded here as a fact about the reference; the analytic Jacobian is the one of the smooth model.
+    J2 = approx_derivative(lambda xx: ogn.computef(xx, *args), x, method="2-point")
+    assert np.isfinite(J2).all()
+    assert np.abs(J.toarray() - J2).max() > 1e3 * np.abs(J.toarray() - Jfd).max()
+    pat = ogn.sparsity_pattern(G["cf_knn"], G["cf_nvi"], len(G["a1_node_pos"])).toarray() > 0
+    assert not (np.abs(Jfd) > 1e-9)[~pat].any()
+    Jl, rl = ogn.lw_jacobian(lw, *args[:5], G["a1_node_dq"], float(G["a1_node_w"]))
+    Jlfd = approx_derivative(lambda q: ogn.lw_jacobian(q, *args[:5], G["a1_node_dq"], float(G["a1_node_w"]))[1], lw, method="3-point")
+    assert np.abs(Jl - Jlfd).max() <= 1e-7 * np.abs(Jlfd).max()
