@@ -112,6 +112,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from dynamicfusion_body_b200 import _capi, engine
+    from dynamicfusion_body_b200 import dist as ddist
     from dynamicfusion_body_b200.fusion import Fusion
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -148,19 +149,15 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step_resident(i):
-        if world > 1:
-            # rank 0 owns the sensor + warp field: broadcast this frame (depth + node transforms) over NVLink
-            dist.broadcast(depth_dev, 0)
-            dist.broadcast(dq_dev[i % n_frames], 0)
+        # rank 0 owns the sensor + warp field: broadcast this frame (depth + node transforms) over NVLink
+        ddist.broadcast_frame(depth_dev, dq_dev[i % n_frames])
         fus.set_node_dqs(dq_dev[i % n_frames])
         fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics)
 
     def step_e2e(i):
         d = depth_host.to(dev, non_blocking=True)
         q = dq_host[i % n_frames].to(dev, non_blocking=True)
-        if world > 1:
-            dist.broadcast(d, 0)
-            dist.broadcast(q, 0)
+        ddist.broadcast_frame(d, q)
         fus.set_node_dqs(q)
         fus.fuseFrame(d, extrinsics=sc.extrinsics)
         return fus.frame_stats()                                     # D2H of the per-frame counters (32 B)
@@ -232,12 +229,60 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": None, "kernel_ms": fast_avg, "exact_pass_ms": exact_avg,
                      "algorithmic_bytes_per_voxel": ALG_BYTES_PER_VOXEL, "step_frac_of_peak": ALG_BYTES_PER_VOXEL * nvox_rank / (ms_total / args.steps * 1e-3) / 1e9 / peak},
     }
+    if not args.no_gn:
+        out["gn"] = bench_gn(args, dev, rank, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sc, (res_x, res, res), budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_gn(args, dev, rank, world):
+    """Second half of the BASELINE metric: Gauss-Newton ms/iteration (config 3: ~1k nodes, k=4, ~300k data residuals of
+    one 640x480 frame, 15 iterations).  N>1: data residuals sharded over ranks, normal equations all-reduced (NCCL)."""
+    import torch
+    from dynamicfusion_body_b200 import dist as ddist
+    from dynamicfusion_body_b200 import engine, gn, synth
+    sc = synth.make_scene(res=256, k=4, n_nodes=args.gn_nodes, seed=0, background=True)
+    pd = synth.make_gn_problem(sc, args.gn_points, seed=0)
+    wf = engine.DeviceWarpField(4, dev)
+    wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
+    shard = ddist.residual_partition(len(pd.vertices), world)[rank]
+    prob = gn.Problem(wf, pd.vertices, pd.normals, pd.corr, pd.vert_knn, pd.node_vertex_idx, shard=shard, reg_owner=(rank == 0))
+    x = torch.from_numpy(pd.x0).to(dev)
+    allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c)) if world > 1 else None
+    prob.pattern()
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce)         # warm-up
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record()
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce)
+    e[1].record()
+    torch.cuda.synchronize()
+    total_ms = ddist.max_over_ranks(e[0].elapsed_time(e[1]), dev)
+    # breakdown of one iteration
+    H, g, c = prob.normal_equations(x, sc.lw, 0.05, huber=True)
+    torch.cuda.synchronize()
+    t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t[0].record()
+    H, g, c = prob.normal_equations(x, sc.lw, 0.05, huber=True)
+    t[1].record()
+    if allreduce:
+        allreduce(H, g, c)
+    t[2].record()
+    x_new, delta, info = prob.solve_step(H, g, x, 1e-3, 400, 1e-9)
+    t[3].record()
+    torch.cuda.synchronize()
+    row_ptr, col_idx, nnzb = prob.pattern()
+    return {"metric": "gn_solve_ms_per_iter", "value": total_ms / max(1, res.iterations), "unit": "ms", "iterations": res.iterations,
+            "accepted": res.accepted, "cost0": res.cost0, "cost": res.cost,
+            "config": {"workload": "warp-field Gauss-Newton, %d nodes, k=4, %d data + %d regularisation residuals, %d unknowns, %d 8x8 blocks"
+                                   % (sc.n_nodes, len(pd.vertices), 3 * 4 * sc.n_nodes, 8 * sc.n_nodes, nnzb)},
+            "breakdown_ms": {"normal_equations": t[0].elapsed_time(t[1]), "allreduce": t[1].elapsed_time(t[2]),
+                             "pcg_solve_and_update": t[2].elapsed_time(t[3]), "pcg_iterations": int(info[6].item())},
+            "reference_published_ms_per_iter": 70100.0}
 
 
 def cpu_baseline(sc, res, budget_s=12.0):
@@ -295,6 +340,10 @@ def main():
     ap.add_argument("--k", type=int, default=4)
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gn", action="store_true")
+    ap.add_argument("--gn-nodes", type=int, default=1000)
+    ap.add_argument("--gn-points", type=int, default=300000)
+    ap.add_argument("--gn-iters", type=int, default=15)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-sample", type=int, default=1_600_000)
     args = ap.parse_args()

@@ -166,8 +166,8 @@ class Problem:
                                              _ptr(x), _ptr(x_new), _ptr(delta), _ptr(self._ws), _stream()))
         return x_new, delta, self._ws[:8]
 
-    def gauss_newton(self, x0, lw, rw, max_iter=15, huber=True, f_scale=1.0, lam0=1e-3, pcg_iters=200, pcg_tol=1e-10,
-                     ftol=1e-9, verbose=False, allreduce=None):
+    def gauss_newton(self, x0, lw, rw, max_iter=15, huber=True, f_scale=1.0, lam0=1e-3, lam_min=1e-5, pcg_iters=400,
+                     pcg_tol=1e-9, ftol=1e-9, verbose=False, allreduce=None):
         """Damped Gauss-Newton (Levenberg-Marquardt accept/reject).  `allreduce(H, g, cost)` is called after every
         assembly when the residuals are sharded over ranks (dist.py)."""
         x = _to_dev(x0, torch.float64, self.device).reshape(-1).clone()
@@ -196,7 +196,7 @@ class Problem:
             if ok:
                 rel = (cost - cost_new) / max(cost, 1e-300)
                 x, H, g, cost = x_new, H2, g2, cost_new
-                lam = max(lam / 3.0, 1e-12)
+                lam = max(lam / 3.0, lam_min)
                 accepted += 1
                 if rel < ftol:
                     break

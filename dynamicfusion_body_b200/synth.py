@@ -301,3 +301,48 @@ def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=4
                  node_dq=node_dq, node_w=node_w, radius=r_grid, lw=lw, K=K, Kinv=Kinv, rows=rows, cols=cols,
                  extrinsics=extr, depths=np.stack(depths), tdist=float(tdist), vert_knn=vert_knn,
                  warped_vertices=wv, warped_normals=wn)
+
+
+@dataclasses.dataclass
+class GNProblemData:
+    vertices: np.ndarray      # (V,3) f32 canonical surface samples
+    normals: np.ndarray       # (V,3) f32
+    corr: np.ndarray          # (V,3) f64 live-frame correspondences
+    vert_knn: np.ndarray      # (V,k) int64
+    node_vertex_idx: np.ndarray
+    x0: np.ndarray            # (8N,) f64 initial node transforms (perturbed truth)
+    x_true: np.ndarray
+
+
+def make_gn_problem(sc, n_points, seed=0, noise=0.02, perturb=2e-3):
+    """Solver workload (BASELINE config 3 shape): `n_points` area-weighted samples of the canonical mesh as
+    (vertex, normal, correspondence) triples -- the stand-in for the valid pixels of one depth frame -- with
+    correspondences produced by the scene's true warp field (+ noise) and a perturbed initial field."""
+    rng = np.random.default_rng(seed)
+    v = sc.vertices.astype(np.float64)
+    f = sc.faces
+    if len(f) == 0:
+        idx = rng.integers(0, len(v), n_points)
+        pts, nrm = v[idx], sc.normals[idx].astype(np.float64)
+    else:
+        a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+        area = 0.5 * np.linalg.norm(np.cross(b - a, c - a), axis=1)
+        tri = rng.choice(len(f), size=n_points, p=area / area.sum())
+        r1, r2 = rng.random(n_points), rng.random(n_points)
+        s1 = np.sqrt(r1)
+        w0, w1, w2 = 1 - s1, s1 * (1 - r2), s1 * r2
+        pts = w0[:, None] * a[tri] + w1[:, None] * b[tri] + w2[:, None] * c[tri]
+        n0 = sc.normals.astype(np.float64)
+        nrm = w0[:, None] * n0[f[tri, 0]] + w1[:, None] * n0[f[tri, 1]] + w2[:, None] * n0[f[tri, 2]]
+        nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-12)
+    pts32 = pts.astype(np.float32)
+    tree = cKDTree(sc.node_pos.astype(np.float64))
+    _, knn = tree.query(pts32.astype(np.float64), k=sc.k)
+    knn = knn.reshape(len(pts32), sc.k).astype(np.int64)
+    nw = np.full(sc.n_nodes, np.float32(sc.node_w))
+    corr = blend_warp(pts32, sc.node_pos, sc.node_dq, nw, knn, lw=sc.lw.astype(np.float64)) + rng.normal(size=pts.shape) * noise
+    _, nvi = cKDTree(pts32.astype(np.float64)).query(sc.node_pos.astype(np.float64))
+    x_true = sc.node_dq.reshape(-1).astype(np.float64)
+    x0 = x_true + rng.normal(size=x_true.shape) * perturb
+    return GNProblemData(vertices=pts32, normals=nrm.astype(np.float32), corr=corr, vert_knn=knn, node_vertex_idx=nvi.astype(np.int64),
+                         x0=x0, x_true=x_true)
