@@ -1,0 +1,228 @@
+// dfb_brick.h -- brick-level conservative classification for the projective TSDF passes (a2/a3).
+//
+// A brick is 4 x 4 x 32 voxels (x,y,z): sixteen 128-byte rows of the z-fastest volume.  Per frame every brick is
+// classified as
+//     SKIP   : no voxel of the brick can be updated by any view          -> no memory traffic at all
+//     CLAMP  : every voxel is certainly updated with min(tdist, tl) = tdist by a fixed set of views
+//                                                                         -> pure streaming pass (16 B/voxel)
+//     MIXED  : anything else                                              -> per-voxel kernel (dfb_voxel.h)
+//
+// Rigour.  For a voxel x with neighbours S and ANY positive blend weights w_i, the reference's warped point is
+//     p'(x) = Q(b,x)/|b|^2,  b = sum_i w_i q_i      (Q2: 8-norm normalisation; Q = dqb_warp's quadratic form)
+//           = sum_ij (w_i w_j <q_i,q_j>) P_ij(x) / sum_ij (w_i w_j <q_i,q_j>),   P_ij(x) = Qpol(q_i,q_j,x)/<q_i,q_j>
+// where Qpol is the polarisation of Q.  If <q_i,q_j> > 0 for all pairs, p'(x) is a CONVEX COMBINATION of the points
+// P_ij(x), and each P_ij is an affine map of x.  Hence p'(brick) lies in the bounding box of the boxes
+// P_ij(brick), i,j in C, where C is the union of the kNN sets of the brick's voxels (cached per graph revision).
+// The bound needs no knowledge of the weights -- it holds for the reference's float32/powf/exp-evaluated ones as well.
+// The box is pushed through lw / extrinsics / intrinsics with interval arithmetic, the depth image is scanned over
+// the resulting pixel rectangle, and the decision is taken only if it holds for the whole box (plus rounding slack).
+#pragma once
+#include "dfb_voxel.h"
+
+namespace dfb {
+
+constexpr int BRICK_X = 4, BRICK_Y = 4, BRICK_Z = 32;
+constexpr int BRICK_MAXC = 24;        // cached candidate nodes per brick (more -> always MIXED)
+constexpr int BRICK_CLS_MIXED = 0xFF;
+constexpr int BRICK_MAX_RECT = 512;   // depth pixels scanned per brick and view before giving up
+
+struct Box3 { float lo[3], hi[3]; };
+
+#if defined(DFB_BRICK_DEBUG)   // tests: report which condition sent a brick to the per-voxel path
+#define DFB_MIXED(n) (*frus = -(n), BRICK_CLS_MIXED)
+#else
+#define DFB_MIXED(n) BRICK_CLS_MIXED
+#endif
+
+// affine map (row-major 3x4) of dqb_warp(q, .) for a possibly non-unit q, fp32
+DFB_HD void dq_affine_f(const float* q, float* A) {
+    const float w = q[0], x = q[1], y = q[2], z = q[3], dw = q[4], dx = q[5], dy = q[6], dz = q[7];
+    const float s = w * w - (x * x + y * y + z * z);
+    A[0] = s + 2 * x * x;        A[1] = 2 * (x * y - w * z);  A[2] = 2 * (x * z + w * y);
+    A[4] = 2 * (x * y + w * z);  A[5] = s + 2 * y * y;        A[6] = 2 * (y * z - w * x);
+    A[8] = 2 * (x * z - w * y);  A[9] = 2 * (y * z + w * x);  A[10] = s + 2 * z * z;
+    A[3] = 2 * (w * dx - dw * x + (y * dz - z * dy));
+    A[7] = 2 * (w * dy - dw * y + (z * dx - x * dz));
+    A[11] = 2 * (w * dz - dw * z + (x * dy - y * dx));
+}
+
+DFB_HD void box_extend_affine(const float* A, float inv, const float* c, const float* h, Box3& b) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float m = (A[4 * r] * c[0] + A[4 * r + 1] * c[1] + A[4 * r + 2] * c[2] + A[4 * r + 3]) * inv;
+        const float rad = (fabsf(A[4 * r]) * h[0] + fabsf(A[4 * r + 1]) * h[1] + fabsf(A[4 * r + 2]) * h[2]) * fabsf(inv);
+        const float slack = 4e-6f * (fabsf(m) + rad) + 1e-6f;
+        b.lo[r] = fminf(b.lo[r], m - rad - slack);
+        b.hi[r] = fmaxf(b.hi[r], m + rad + slack);
+    }
+}
+
+// interval of row . [p,1] over the box (centre c, half h), with rounding slack
+DFB_HD void row_interval(const float* row, const float* c, const float* h, float& lo, float& hi) {
+    const float m = row[0] * c[0] + row[1] * c[1] + row[2] * c[2] + row[3];
+    const float rad = fabsf(row[0]) * h[0] + fabsf(row[1]) * h[1] + fabsf(row[2]) * h[2];
+    const float mag = fabsf(row[0] * c[0]) + fabsf(row[1] * c[1]) + fabsf(row[2] * c[2]) + fabsf(row[3]);
+    const float slack = 2e-6f * (mag + rad) + 1e-6f;
+    lo = m - rad - slack;
+    hi = m + rad + slack;
+}
+
+DFB_HD void div_interval(float nlo, float nhi, float dlo, float dhi, float& lo, float& hi) {  // requires dlo > 0
+    const float a = nlo / dlo, b = nlo / dhi, c = nhi / dlo, d = nhi / dhi;
+    lo = fminf(fminf(a, b), fminf(c, d));
+    hi = fmaxf(fmaxf(a, b), fmaxf(c, d));
+    const float slack = 4e-6f * fmaxf(fabsf(lo), fabsf(hi)) + 1e-5f;
+    lo -= slack;
+    hi += slack;
+}
+
+// Execution context: the same code runs with one warp per brick on the GPU (lanes split the node pairs and the depth
+// pixels, reductions by shuffle) and with a single "lane" on the host (tests/hostshim).
+struct SerialCtx {
+    DFB_HD int lane() const { return 0; }
+    DFB_HD int nlanes() const { return 1; }
+    DFB_HD float rmin(float v) const { return v; }
+    DFB_HD float rmax(float v) const { return v; }
+    DFB_HD bool any(bool b) const { return b; }
+};
+#if defined(__CUDACC__)
+struct WarpCtx {
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int nlanes() const { return 32; }
+    __device__ __forceinline__ float rmin(float v) const {
+        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ float rmax(float v) const {
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    __device__ __forceinline__ bool any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
+};
+#endif
+
+// Classify brick (bxs,by,bz) (bxs slab-local).  Returns BRICK_CLS_MIXED or the per-view CLAMP bit mask (0 = SKIP);
+// *frus = per-view "certainly inside the image" bits (meaningful when the result is not MIXED).
+// All control flow is uniform across the lanes of `ctx`.
+template <class Ctx>
+DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, int nby, int nbz,
+                           int bxs, int by, int bz, int* frus, const Ctx ctx) {
+    *frus = 0;
+    const int xlo = P.x0 + bxs * BRICK_X, ylo = by * BRICK_Y, zlo = bz * BRICK_Z;
+    const int xhi = (xlo + BRICK_X - 1 < P.x1 - 1) ? xlo + BRICK_X - 1 : P.x1 - 1;
+    const int yhi = (ylo + BRICK_Y - 1 < P.ry - 1) ? ylo + BRICK_Y - 1 : P.ry - 1;
+    const int zhi = (zlo + BRICK_Z - 1 < P.rz - 1) ? zlo + BRICK_Z - 1 : P.rz - 1;
+    const float c[3] = {0.5f * (xlo + xhi), 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
+    const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
+    Box3 bx;
+    if (P.rigid) {
+        for (int r = 0; r < 3; ++r) { bx.lo[r] = c[r] - h[r]; bx.hi[r] = c[r] + h[r]; }
+    } else {
+        const size_t b = ((size_t)bxs * nby + by) * nbz + bz;
+        const int cnt = brick_count[b];
+        if (cnt == 0 || cnt > BRICK_MAXC) return DFB_MIXED(1);
+        for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
+        const uint16_t* ids = brick_nodes + b * BRICK_MAXC;
+        bool bad = false;
+        int p = 0;
+        for (int i = 0; i < cnt; ++i) {
+            for (int j = 0; j <= i; ++j, ++p) {
+                if (p % ctx.nlanes() != ctx.lane()) continue;
+                const float4 r0 = P.node_rec[3 * (size_t)ids[i]];
+                const float4 r1 = P.node_rec[3 * (size_t)ids[i] + 1];
+                const float4 r2 = P.node_rec[3 * (size_t)ids[i] + 2];
+                const float qi[8] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                float nii = 0.f;
+                for (int t = 0; t < 8; ++t) nii += qi[t] * qi[t];
+                float Ai[12];
+                dq_affine_f(qi, Ai);
+                if (j == i) {
+                    // every blend weight must be positive in the reference's float64 exp: farthest voxel of the brick
+                    const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
+                    if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -900.f) || !(nii > 1e-20f)) { bad = true; continue; }
+                    box_extend_affine(Ai, 1.0f / nii, c, h, bx);
+                } else {
+                    const float4 s1 = P.node_rec[3 * (size_t)ids[j] + 1];
+                    const float4 s2 = P.node_rec[3 * (size_t)ids[j] + 2];
+                    const float qj[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+                    float ip = 0.f, njj = 0.f, qs[8];
+                    for (int t = 0; t < 8; ++t) { ip += qi[t] * qj[t]; njj += qj[t] * qj[t]; qs[t] = qi[t] + qj[t]; }
+                    // <q_i,q_j> must be safely positive (else the convex-combination argument does not apply)
+                    if (!(ip > 0.25f * sqrtf(nii * njj))) { bad = true; continue; }
+                    float As[12], Aj[12], Ap[12];
+                    dq_affine_f(qs, As);
+                    dq_affine_f(qj, Aj);
+                    for (int t = 0; t < 12; ++t) Ap[t] = As[t] - Ai[t] - Aj[t];   // = 2 * Qpol(q_i, q_j, .)
+                    box_extend_affine(Ap, 0.5f / ip, c, h, bx);
+                }
+            }
+        }
+        if (ctx.any(bad)) return DFB_MIXED(2);
+        // reference-side rounding of p' (Q3: float32 cast) and float64 noise; polarisation cancellation slack
+        for (int r = 0; r < 3; ++r) {
+            const float m = 2e-3f + 2e-6f * P.coord_mag;
+            bx.lo[r] = ctx.rmin(bx.lo[r]) - m;
+            bx.hi[r] = ctx.rmax(bx.hi[r]) + m;
+        }
+    }
+    const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
+    const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
+    int mask = 0, fr = 0;
+    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
+    for (int v = 0; v < P.n_views; ++v) {
+        const ViewFast& V = P.vf[v];
+        // camera-space box, then a = X/Z, b = Y/Z, (u,v) = K[0:2] * (a, b, 1): dividing X by Z (not K*lpos rows by each
+        // other) keeps the interval dependency problem away from the principal-point term
+        float xl, xh, yl, yh, lzl, lzh;
+        row_interval(V.T, c3, h3, xl, xh);
+        row_interval(V.T + 4, c3, h3, yl, yh);
+        row_interval(V.T + 8, c3, h3, lzl, lzh);
+        if (!P.k_pinhole) return DFB_MIXED(9);
+        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
+        float al, ah, bl, bh;
+        div_interval(xl, xh, lzl, lzh, al, ah);
+        div_interval(yl, yh, lzl, lzh, bl, bh);
+        float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        {
+            const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
+            ul -= su; uh += su; vl -= sv; vh += sv;
+        }
+        const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
+        if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
+        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
+        fr |= 1 << v;
+        const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
+        const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
+        if (npx > BRICK_MAX_RECT) return DFB_MIXED(5);
+        float zmin = 3.0e38f, zmax = -3.0e38f;
+        bool nan = false;
+        for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
+            const int iv = iv0 + t / nu, iu = iu0 + t % nu;
+            const float z = -P.depth[v][(size_t)iv * P.cols + iu];
+            nan |= !(z == z);
+            zmin = fminf(zmin, z);
+            zmax = fmaxf(zmax, z);
+        }
+        if (ctx.any(nan)) return DFB_MIXED(6);
+        zmin = ctx.rmin(zmin);
+        zmax = ctx.rmax(zmax);
+        // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
+        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
+        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
+        const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
+        const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+        if (!(kzl > 0.f)) return DFB_MIXED(7);
+        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
+        const float zs = 1e-6f * fabsf(zmax) * kzh;
+        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
+        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
+        return DFB_MIXED(8);
+    }
+    *frus = fr;
+    return mask;
+}
+
+}  // namespace dfb

@@ -95,6 +95,8 @@ inline void fill_common(ProjParams& P, const dfb_volume* vol, const dfb_workspac
 inline void fill_intrinsics(ProjParams& P, const double* K, const double* Kinv) {
     for (int i = 0; i < 9; ++i) { P.K[i] = K[i]; P.Kinv[i] = Kinv[i]; }
     for (int i = 0; i < 3; ++i) P.kin[i] = (float)Kinv[6 + i];
+    for (int i = 0; i < 6; ++i) P.kf[i] = (float)K[i];
+    P.k_pinhole = (K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0) ? 1 : 0;
     P.knorm = (float)fmax(fabs(K[0]) + fabs(K[1]) + fabs(K[2]), fabs(K[3]) + fabs(K[4]) + fabs(K[5]));
     P.kin_uv = (float)(fabs(Kinv[6]) + fabs(Kinv[7]));
 }
@@ -140,6 +142,7 @@ inline int build_projective(ProjParams& P, const dfb_volume* vol, const dfb_warp
         k_mul34(views->K, T, PK);
         for (int i = 0; i < 12; ++i) P.vf[v].P[i] = (float)PK[i];
         for (int i = 0; i < 4; ++i) P.vf[v].L[i] = (float)T[8 + i];
+        for (int i = 0; i < 12; ++i) P.vf[v].T[i] = (float)T[i];
     }
     P.coord_mag = (float)(2.0 * mag + 8.0);
     return DFB_OK;
@@ -174,6 +177,7 @@ inline int build_rigid(ProjParams& P, const dfb_volume* vol, int tsdf_res, const
     k_mul34(K, T, PK);
     for (int i = 0; i < 12; ++i) P.vf[0].P[i] = (float)PK[i];
     for (int i = 0; i < 4; ++i) P.vf[0].L[i] = (float)T[8 + i];
+    for (int i = 0; i < 12; ++i) P.vf[0].T[i] = (float)T[i];
     const double mag = fmax(affine_corner_mag(G, vol->rx, vol->ry, vol->rz), affine_corner_mag(T, vol->rx, vol->ry, vol->rz));
     P.coord_mag = (float)(2.0 * mag + 8.0 * scale);
     return DFB_OK;

@@ -11,6 +11,7 @@ enum { CLS_SKIP = 0, CLS_CLAMP = 1, CLS_UNCERTAIN = 2 };
 struct ViewFast {
     float P[12];  // K * E_v * A_lw   (rows: u*z, v*z, z_k)
     float L[4];   // third row of E_v * A_lw  (lpos_z)
+    float T[12];  // E_v * A_lw  (lpos), used by the brick classifier
 };
 
 struct ProjParams {
@@ -38,6 +39,8 @@ struct ProjParams {
     double K[9], Kinv[9];
     double E[8][12];
     ViewFast vf[8];
+    float kf[6];     // K rows 0,1 in fp32
+    int k_pinhole;   // K row 2 == (0,0,1): u = K00*X/Z + K01*Y/Z + K02 (brick classifier requirement)
     float kin[3];    // Kinv row 2, fp32
     float knorm;     // max abs row sum of K rows 0,1 (error propagation to pixels)
     float kin_uv;    // |Kinv20| + |Kinv21|

@@ -10,6 +10,7 @@
 //   own arithmetic (dfb_math.h exact tier).  If the list overflowed it re-scans the volume instead.
 #include "common.h"
 #include "dfb_params.h"
+#include "dfb_brick.h"
 
 using namespace dfb;
 
@@ -76,6 +77,173 @@ __global__ void __launch_bounds__(256) proj_fast_kernel(const __grid_constant__ 
     }
     if (P.mask_out) P.mask_out[i] = (uint8_t)m;
     if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// brick culling (dfb_brick.h): per-graph candidate sets, per-frame classification, streaming + mixed passes
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void brick_thread_coords(int b, int nby, int nbz, int& bxs, int& by, int& bz) {
+    bz = b % nbz;
+    const int t = b / nbz;
+    by = t % nby;
+    bxs = t / nby;
+}
+
+// thread t of a 128-thread CTA owns 4 consecutive z voxels of one of the brick's 16 rows
+__device__ __forceinline__ void brick_lane(int t, int& dx, int& dy, int& dz) {
+    const int row = t >> 3;
+    dx = row >> 2;
+    dy = row & 3;
+    dz = (t & 7) * 4;
+}
+
+__global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, int k, int sx, int ry, int rz, int nby, int nbz,
+                                                          uint16_t* brick_nodes, uint8_t* brick_count) {
+    __shared__ unsigned int set[64];
+    __shared__ int n_out, overflow;
+    const int b = blockIdx.x;
+    int bxs, by, bz;
+    brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    if (threadIdx.x < 64) set[threadIdx.x] = 0xffffffffu;
+    if (threadIdx.x == 0) { n_out = 0; overflow = 0; }
+    __syncthreads();
+    int dx, dy, dz;
+    brick_lane(threadIdx.x, dx, dy, dz);
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy;
+    if (xs < sx && y < ry) {
+        for (int q = 0; q < 4; ++q) {
+            const int z = bz * BRICK_Z + dz + q;
+            if (z >= rz) break;
+            const size_t i = ((size_t)xs * ry + y) * rz + z;
+            for (int j = 0; j < k; ++j) {
+                const unsigned int id = knn[i * (size_t)k + j];
+                unsigned int slot = (id * 2654435761u) >> 26;
+                int probes = 0;
+                while (true) {
+                    const unsigned int old = atomicCAS(&set[slot], 0xffffffffu, id);
+                    if (old == 0xffffffffu || old == id) break;
+                    slot = (slot + 1) & 63;
+                    if (++probes >= 64) { overflow = 1; break; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && set[threadIdx.x] != 0xffffffffu) {
+        const int pos = atomicAdd(&n_out, 1);
+        if (pos < BRICK_MAXC) brick_nodes[(size_t)b * BRICK_MAXC + pos] = (uint16_t)set[threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) brick_count[b] = (overflow || n_out > BRICK_MAXC) ? 255 : (uint8_t)n_out;
+}
+
+// one warp per brick (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h WarpCtx)
+__global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
+                                                             const uint8_t* brick_count, int nbx, int nby, int nbz, uint8_t* cls_out,
+                                                             uint32_t* stream_list, uint32_t* mixed_list) {
+    const int nb = nbx * nby * nbz;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += nwarps) {
+        int bxs, by, bz, fr = 0;
+        brick_thread_coords(b, nby, nbz, bxs, by, bz);
+        const int cls = brick_classify(P, brick_nodes, brick_count, nby, nbz, bxs, by, bz, &fr, WarpCtx());
+        if (lane == 0) {
+            cls_out[b] = (uint8_t)cls;
+            cls_out[nb + b] = (uint8_t)fr;
+            if (cls == BRICK_CLS_MIXED) mixed_list[atomicAdd(P.counters + 3, 1u)] = (uint32_t)b;
+            else if (cls != 0 || (P.frustum_out != nullptr && fr != 0)) stream_list[atomicAdd(P.counters + 2, 1u)] = (uint32_t)b;
+        }
+    }
+}
+
+// CLAMP bricks: v' = (scale*v*w + tdist)/(scale*(w+1)), w' = min(w+1, wmax) once per view bit -- no warp, no kNN read.
+__global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                           const uint8_t* cls, const uint32_t* list) {
+    const uint32_t count = P.counters[2];
+    const int nb = nbx * nby * nbz;
+    int dx, dy, dz;
+    brick_lane(threadIdx.x, dx, dy, dz);
+    const float sc = (float)P.scale;
+    const bool vec = (P.rz & 3) == 0;
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
+        const int b = (int)list[t];
+        int bxs, by, bz;
+        brick_thread_coords(b, nby, nbz, bxs, by, bz);
+        const int m = cls[b], fr = cls[nb + b];
+        const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z = bz * BRICK_Z + dz;
+        if (xs >= P.x1 - P.x0 || y >= P.ry || z >= P.rz) continue;
+        const size_t i = ((size_t)xs * P.ry + y) * P.rz + z;
+        if (vec) {
+            if (m) {
+                float4 v = *reinterpret_cast<const float4*>(P.tsdf + i);
+                float4 w = *reinterpret_cast<const float4*>(P.weight + i);
+                for (int vi = 0; vi < P.n_views; ++vi)
+                    if (m & (1 << vi)) {
+                        clamp_update(v.x, w.x, P.tdist_f, P.wmax_f, sc);
+                        clamp_update(v.y, w.y, P.tdist_f, P.wmax_f, sc);
+                        clamp_update(v.z, w.z, P.tdist_f, P.wmax_f, sc);
+                        clamp_update(v.w, w.w, P.tdist_f, P.wmax_f, sc);
+                    }
+                *reinterpret_cast<float4*>(P.tsdf + i) = v;
+                *reinterpret_cast<float4*>(P.weight + i) = w;
+            }
+            if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i) = make_uchar4(m, m, m, m);
+            if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i) = make_uchar4(fr, fr, fr, fr);
+        } else {
+            for (int q = 0; q < 4 && z + q < P.rz; ++q) {
+                if (m) {
+                    float v = P.tsdf[i + q], w = P.weight[i + q];
+                    for (int vi = 0; vi < P.n_views; ++vi)
+                        if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
+                    P.tsdf[i + q] = v;
+                    P.weight[i + q] = w;
+                }
+                if (P.mask_out) P.mask_out[i + q] = (uint8_t)m;
+                if (P.frustum_out) P.frustum_out[i + q] = (uint8_t)fr;
+            }
+        }
+    }
+}
+
+// MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
+template <int KMAX>
+__global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                          const uint32_t* list) {
+    const uint32_t count = P.counters[3];
+    int dx, dy, dz;
+    brick_lane(threadIdx.x, dx, dy, dz);
+    const float sc = (float)P.scale;
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
+        const int b = (int)list[t];
+        int bxs, by, bz;
+        brick_thread_coords(b, nby, nbz, bxs, by, bz);
+        const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
+        const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
+        for (int q = 0; q < 4; ++q) {
+            const int z = z0 + q;
+            const bool in = row_in && z < P.rz;
+            const size_t i = in ? ((size_t)xs * P.ry + y) * P.rz + z : 0;
+            int cls = CLS_SKIP, m = 0, f = 0;
+            if (in) {
+                uint16_t ids[KMAX];
+                if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
+                cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
+            }
+            push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+            if (!in || cls == CLS_UNCERTAIN) continue;
+            if (m) {
+                float v = P.tsdf[i], w = P.weight[i];
+                for (int vi = 0; vi < P.n_views; ++vi)
+                    if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
+                P.tsdf[i] = v;
+                P.weight[i] = w;
+            }
+            if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+            if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+        }
+    }
 }
 
 // mode: 0 = work list (or re-scan on overflow), 1 = every voxel
@@ -234,15 +402,38 @@ int exact_blocks(size_t nvox) {
     return (int)(want < 148 * 16 ? (want ? want : 1) : 148 * 16);
 }
 
-int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol) {
+struct BrickArgs {
+    const uint16_t* nodes;
+    const uint8_t* count;
+    uint8_t* cls;
+    uint32_t* lists;
+};
+
+int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol, const BrickArgs& B) {
     if (mode != DFB_MODE_LIST_ONLY) DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY) {
-        int threads;
-        const dim3 grid = fast_grid(vol, threads);
-        if (P.k <= 4) proj_fast_kernel<4><<<grid, threads, 0, s>>>(P);
-        else proj_fast_kernel<8><<<grid, threads, 0, s>>>(P);
-        DFB_LAUNCH_CHECK("proj_fast_kernel");
+        const bool bricks = B.cls != nullptr && B.lists != nullptr && (P.rigid || (B.nodes != nullptr && B.count != nullptr));
+        if (bricks) {
+            const int nbx = (P.x1 - P.x0 + BRICK_X - 1) / BRICK_X, nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
+            const int nb = nbx * nby * nbz;
+            uint32_t* stream_list = B.lists;
+            uint32_t* mixed_list = B.lists + nb;
+            brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+            DFB_LAUNCH_CHECK("brick_classify_kernel");
+            const int grid = nb < 148 * 16 ? nb : 148 * 16;
+            brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
+            DFB_LAUNCH_CHECK("brick_stream_kernel");
+            if (P.k <= 4) brick_mixed_kernel<4><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+            else brick_mixed_kernel<8><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+            DFB_LAUNCH_CHECK("brick_mixed_kernel");
+        } else {
+            int threads;
+            const dim3 grid = fast_grid(vol, threads);
+            if (P.k <= 4) proj_fast_kernel<4><<<grid, threads, 0, s>>>(P);
+            else proj_fast_kernel<8><<<grid, threads, 0, s>>>(P);
+            DFB_LAUNCH_CHECK("proj_fast_kernel");
+        }
         if (mode == DFB_MODE_FAST_ONLY) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
@@ -271,7 +462,8 @@ extern "C" int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpf
                                           uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream) {
     ProjParams P;
     if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
-    return run_projective(P, mode, (cudaStream_t)stream, vol);
+    const BrickArgs B = {wf->brick_nodes, wf->brick_count, ws->brick_cls, ws->brick_lists};
+    return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
 extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const float* depth, int rows, int cols,
@@ -283,7 +475,8 @@ extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const f
     if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
                             mask_out, frustum_out))
         return r;
-    return run_projective(P, mode, (cudaStream_t)stream, vol);
+    const BrickArgs B = {nullptr, nullptr, ws->brick_cls, ws->brick_lists};
+    return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
 extern "C" int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield* wf, const float* curr, int cx,
@@ -330,5 +523,22 @@ extern "C" int dfb_dq_blend_points(const float* pts, int64_t m, const int32_t* i
     const int blocks = (int)((m + 127) / 128 < 148 * 8 ? (m + 127) / 128 : 148 * 8);
     dq_blend_points_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(pts, m, idx, wf->k, wf->node_pos, wf->node_dq, wf->node_w, out_dq);
     DFB_LAUNCH_CHECK("dq_blend_points_kernel");
+    return DFB_OK;
+}
+
+extern "C" int64_t dfb_brick_count(int sx, int ry, int rz) {
+    return (int64_t)((sx + BRICK_X - 1) / BRICK_X) * ((ry + BRICK_Y - 1) / BRICK_Y) * ((rz + BRICK_Z - 1) / BRICK_Z);
+}
+
+extern "C" int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* brick_nodes,
+                                     uint8_t* brick_count, dfb_stream_t stream) {
+    DFB_REQUIRE(knn && brick_nodes && brick_count, "null pointer");
+    DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K && rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad arguments");
+    const int sx = x1 - x0;
+    const int nby = (ry + BRICK_Y - 1) / BRICK_Y, nbz = (rz + BRICK_Z - 1) / BRICK_Z;
+    const int64_t nb = dfb_brick_count(sx, ry, rz);
+    DFB_REQUIRE(nb < ((int64_t)1 << 31), "too many bricks");
+    brick_nodes_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(knn, k, sx, ry, rz, nby, nbz, brick_nodes, brick_count);
+    DFB_LAUNCH_CHECK("brick_nodes_kernel");
     return DFB_OK;
 }

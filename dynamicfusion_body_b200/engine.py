@@ -35,21 +35,28 @@ def _to_dev(a, dtype, device):
 class Workspace:
     """Deferred-voxel list for the exact pass.  capacity defaults to 1/4 of the slab."""
 
-    def __init__(self, n_voxels, device, fraction=0.25):
+    def __init__(self, n_voxels, device, fraction=0.25, n_bricks=0):
         self.capacity = int(max(1024, n_voxels * fraction))
         self.list = torch.empty(self.capacity, dtype=torch.int32, device=device)
         self.counters = torch.zeros(8, dtype=torch.int32, device=device)
+        self.n_bricks = int(n_bricks)
+        self.brick_cls = torch.zeros(2 * self.n_bricks, dtype=torch.uint8, device=device) if n_bricks else None
+        self.brick_lists = torch.zeros(2 * self.n_bricks, dtype=torch.int32, device=device) if n_bricks else None
 
-    def struct(self):
+    def struct(self, use_bricks=True):
         s = _capi.Workspace()
         s.list = self.list.data_ptr()
         s.capacity = self.capacity
         s.counters = self.counters.data_ptr()
+        if use_bricks and self.brick_cls is not None:
+            s.brick_cls = self.brick_cls.data_ptr()
+            s.brick_lists = self.brick_lists.data_ptr()
         return s
 
     def stats(self):
         c = self.counters.cpu().numpy().astype(np.int64) & 0xffffffff
-        return {"deferred": int(c[0]), "exact_processed": int(c[1])}
+        return {"deferred": int(c[0]), "exact_processed": int(c[1]), "bricks_streamed": int(c[2]), "bricks_mixed": int(c[3]),
+                "bricks": self.n_bricks}
 
 
 class DeviceVolume:
@@ -69,7 +76,8 @@ class DeviceVolume:
             self.weight = _to_dev(weight, torch.float32, self.device).reshape(shape)
         else:
             self.weight = torch.zeros(shape, dtype=torch.float32, device=self.device)
-        self.workspace = Workspace(self.n_voxels, self.device)
+        nb = int(_capi.lib().dfb_brick_count(self.x1 - self.x0, self.res[1], self.res[2]))
+        self.workspace = Workspace(self.n_voxels, self.device, n_bricks=nb)
 
     @property
     def n_voxels(self):
@@ -94,6 +102,7 @@ class DeviceWarpField:
         self.n_nodes = 0
         self.node_pos = self.node_dq = self.node_w = self.node_rec = None
         self._knn = {}
+        self._bricks = {}
 
     def set_nodes(self, node_pos, node_dq, node_w):
         n = len(node_pos)
@@ -102,6 +111,7 @@ class DeviceWarpField:
         self.node_w = _to_dev(w, torch.float32, self.device).reshape(n)
         self.n_nodes = n
         self._knn = {}
+        self._bricks = {}
         self.set_dq(node_dq)
 
     def set_dq(self, node_dq):
@@ -126,6 +136,21 @@ class DeviceWarpField:
             self._knn[key] = t
         return t
 
+    def brick_nodes(self, res, x0, x1):
+        """(nodes uint16 [n_bricks,24], count uint8 [n_bricks]): union of the kNN sets of each 4x4x32 brick; cached with
+        the kNN table (same validity: until the node positions change)."""
+        key = (tuple(res), x0, x1)
+        t = self._bricks.get(key)
+        if t is None:
+            knn = self.knn_table(res, x0, x1)
+            nb = int(_capi.lib().dfb_brick_count(x1 - x0, res[1], res[2]))
+            nodes = torch.zeros((nb, 24), dtype=torch.int16, device=self.device)
+            count = torch.zeros(nb, dtype=torch.uint8, device=self.device)
+            _capi.check(_capi.lib().dfb_brick_nodes_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(nodes), _ptr(count), _stream()))
+            t = (nodes, count)
+            self._bricks[key] = t
+        return t
+
     def knn_points(self, pts, k=None):
         k = self.k if k is None else k
         p = _to_dev(pts, torch.float32, self.device).reshape(-1, 3)
@@ -133,8 +158,11 @@ class DeviceWarpField:
         _capi.check(_capi.lib().dfb_knn_points(_ptr(p), p.shape[0], _ptr(self.node_pos), self.n_nodes, k, _ptr(out), _stream()))
         return out
 
-    def struct(self, lw=None, knn=None, k=None):
+    def struct(self, lw=None, knn=None, k=None, bricks=None):
         s = _capi.WarpField()
+        if bricks is not None:
+            s.brick_nodes = bricks[0].data_ptr()
+            s.brick_count = bricks[1].data_ptr()
         k = self.k if k is None else k
         if k > 0:
             s.node_rec = self.node_rec.data_ptr()
@@ -195,14 +223,15 @@ def _mask_bufs(vol, want):
 
 
 def update_projective(vol, wf, lw, depths, K, Kinv=None, extrinsics=None, tdist=1.0, wmax=100.0,
-                      mode=_capi.MODE_HYBRID, want_masks=False, views=None):
+                      mode=_capi.MODE_HYBRID, want_masks=False, views=None, use_bricks=True):
     """a3: warped projective TSDF update of the slab `vol` in place; returns (mask, frustum) bit-arrays or None."""
     views = views if views is not None else make_views(depths, K, Kinv, extrinsics)
     knn = wf.knn_table(vol.res, vol.x0, vol.x1)
-    ws = vol.workspace.struct()
+    bricks = wf.brick_nodes(vol.res, vol.x0, vol.x1) if use_bricks else None
+    ws = vol.workspace.struct(use_bricks)
     mask, frus = _mask_bufs(vol, want_masks)
     v = vol.struct()
-    s = wf.struct(lw, knn)
+    s = wf.struct(lw, knn, bricks=bricks)
     _capi.check(_capi.lib().dfb_tsdf_update_projective(C.byref(v), C.byref(s), C.byref(views), float(tdist), float(wmax),
                                                        int(mode), C.byref(ws), _ptr(mask), _ptr(frus), _stream()))
     return (mask, frus) if want_masks else None
@@ -213,7 +242,7 @@ def update_volume(vol, wf, lw, curr, tdist, wmax=100.0, mode=_capi.MODE_HYBRID, 
     assert curr.is_cuda and curr.dtype == torch.float32 and curr.is_contiguous() and curr.dim() == 3
     k = 0 if rigid else wf.k
     knn = None if rigid else wf.knn_table(vol.res, vol.x0, vol.x1)
-    ws = vol.workspace.struct()
+    ws = vol.workspace.struct(False)
     mask = torch.zeros(vol.n_voxels, dtype=torch.uint8, device=vol.device) if want_masks else None
     v = vol.struct()
     s = wf.struct(lw, knn, k=k) if wf is not None else _rigid_struct(lw)
@@ -231,14 +260,14 @@ def _rigid_struct(lw):
 
 
 def fuse_depth_rigid(vol, tsdf_res, depth, lw34, K, Kinv=None, scale=1.0, center=None, tdist=1.0, wmax=100.0,
-                     mode=_capi.MODE_HYBRID, want_masks=False):
+                     mode=_capi.MODE_HYBRID, want_masks=False, use_bricks=True):
     """a2: FusionDM.fuseDepths on the slab in place."""
     assert depth.is_cuda and depth.dtype == torch.float32 and depth.is_contiguous() and depth.dim() == 2
     K = np.ascontiguousarray(K, dtype=np.float64)
     Kinv = np.ascontiguousarray(np.linalg.inv(K) if Kinv is None else Kinv, dtype=np.float64)
     lw34 = np.ascontiguousarray(lw34, dtype=np.float64).reshape(12)
     center = np.ascontiguousarray(np.zeros(3) if center is None else center, dtype=np.float64)
-    ws = vol.workspace.struct()
+    ws = vol.workspace.struct(use_bricks)
     mask, frus = _mask_bufs(vol, want_masks)
     v = vol.struct()
     f64 = _capi.c_f64p

@@ -132,7 +132,9 @@ class _FusionBase:
     def build_knn(self):
         """Build (or fetch) the cached voxel->k-nearest-node table of this slab.  Called implicitly by the
         update methods; exposed so that a driver can pay for it outside a timed region."""
-        return self._wf.knn_table(self._vol.res, self._vol.x0, self._vol.x1)
+        t = self._wf.knn_table(self._vol.res, self._vol.x0, self._vol.x1)
+        self._wf.brick_nodes(self._vol.res, self._vol.x0, self._vol.x1)
+        return t
 
     def knn_indices(self):
         """(n_voxels, k) int64 node ids == KDTree.query(pos, k+1)[1][:-1] per voxel (core/fusion.py:175-176)."""

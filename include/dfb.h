@@ -58,6 +58,9 @@ typedef struct dfb_warpfield {
     int lw_is_f32;       /* lw is a float32 array in the reference (its initial state): the first
                             dual-quaternion product of dqb_warp then runs in float32 (core/util.py:69-70) */
     double lw[8];
+    /* optional (NULL = no brick culling): per-brick union of the voxels' kNN sets, from dfb_brick_nodes_build */
+    const uint16_t* brick_nodes; /* [n_bricks][24] */
+    const uint8_t* brick_count;  /* [n_bricks], 255 = more than 24 */
 } dfb_warpfield;
 
 typedef struct dfb_views {
@@ -73,8 +76,12 @@ typedef struct dfb_views {
 typedef struct dfb_workspace {
     uint32_t* list;     /* device [capacity]: voxels deferred to the exact pass */
     uint32_t capacity;
-    uint32_t* counters; /* device [8]; counters[0] = deferred count of the last call,
-                           counters[1] = voxels the exact pass processed */
+    uint32_t* counters; /* device [8]; counters[0] = voxels deferred to the exact pass by the last call,
+                           counters[1] = voxels the exact pass processed, counters[2] = bricks streamed (CLAMP),
+                           counters[3] = bricks evaluated per voxel (MIXED) */
+    /* optional (NULL = no brick culling), n_bricks = dfb_brick_count(x1-x0, ry, rz): */
+    uint8_t* brick_cls;    /* device [2*n_bricks] */
+    uint32_t* brick_lists; /* device [2*n_bricks] */
 } dfb_workspace;
 
 int dfb_version(void);
@@ -88,6 +95,11 @@ int dfb_nodes_pack(const float* node_pos, const float* node_dq, const float* nod
  * k nearest node ids in ascending float64 distance (lower id first on exact ties). */
 int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
                          uint16_t* knn, dfb_stream_t stream);
+/* Brick culling support (4x4x32-voxel bricks): number of bricks of a slab, and the per-brick candidate node sets
+ * derived from the kNN table (once per graph revision). */
+int64_t dfb_brick_count(int slab_x, int ry, int rz);
+int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* brick_nodes,
+                          uint8_t* brick_count, dfb_stream_t stream);
 /* KDTree.query(vert, k) for arbitrary float32 points (core/fusion.py:122,232). */
 int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
                    dfb_stream_t stream);

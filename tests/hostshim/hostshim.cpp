@@ -5,9 +5,11 @@
 // the uncertain voxels) with plain loops and HOST pointers.  The product never loads this library.
 #include <stdarg.h>
 #include <stdio.h>
+#include <algorithm>
 #include <vector>
 
 #include "../../dynamicfusion_body_b200/csrc/dfb_params.h"
+#include "../../dynamicfusion_body_b200/csrc/dfb_brick.h"
 
 namespace dfb {
 static char g_err[512];
@@ -33,14 +35,72 @@ extern "C" void hs_nodes_pack(const float* pos, const float* dq, const float* w,
     }
 }
 
+extern "C" void hs_brick_nodes_build(const uint16_t* knn, int k, int sx, int ry, int rz, uint16_t* brick_nodes, uint8_t* brick_count) {
+    const int nbx = (sx + BRICK_X - 1) / BRICK_X, nby = (ry + BRICK_Y - 1) / BRICK_Y, nbz = (rz + BRICK_Z - 1) / BRICK_Z;
+    for (int bx = 0; bx < nbx; ++bx)
+        for (int by = 0; by < nby; ++by)
+            for (int bz = 0; bz < nbz; ++bz) {
+                const size_t b = ((size_t)bx * nby + by) * nbz + bz;
+                std::vector<uint16_t> set;
+                for (int x = bx * BRICK_X; x < std::min(sx, (bx + 1) * BRICK_X); ++x)
+                    for (int y = by * BRICK_Y; y < std::min(ry, (by + 1) * BRICK_Y); ++y)
+                        for (int z = bz * BRICK_Z; z < std::min(rz, (bz + 1) * BRICK_Z); ++z)
+                            for (int j = 0; j < k; ++j) {
+                                const uint16_t id = knn[(((size_t)x * ry + y) * rz + z) * k + j];
+                                bool found = false;
+                                for (uint16_t s : set) found |= (s == id);
+                                if (!found) set.push_back(id);
+                            }
+                brick_count[b] = set.size() > (size_t)BRICK_MAXC ? 255 : (uint8_t)set.size();
+                for (size_t t = 0; t < set.size() && t < (size_t)BRICK_MAXC; ++t) brick_nodes[b * BRICK_MAXC + t] = set[t];
+            }
+}
+
+// per-voxel brick class for the tests: 0xFF mixed, else clamp mask; frus bits in brick_frus
+static const uint16_t* g_brick_nodes = nullptr;
+static const uint8_t* g_brick_count = nullptr;
+static uint8_t* g_brick_cls_vox = nullptr;
+extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, uint8_t* cls_vox) {
+    g_brick_nodes = nodes; g_brick_count = count; g_brick_cls_vox = cls_vox;
+}
+
 template <int KMAX>
 static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
     const size_t plane = (size_t)P.ry * P.rz;
     uint32_t n_unc = 0;
+    const bool bricks = mode == DFB_MODE_HYBRID && (P.rigid || (g_brick_nodes && g_brick_count)) && g_brick_cls_vox;
+    const int nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
+    std::vector<int> brick_cache((size_t)((P.x1 - P.x0 + BRICK_X - 1) / BRICK_X) * nby * nbz, -1);
     for (int xs = 0; xs < P.x1 - P.x0; ++xs)
         for (int y = 0; y < P.ry; ++y)
             for (int z = 0; z < P.rz; ++z) {
                 const size_t i = xs * plane + (size_t)y * P.rz + z;
+                if (bricks) {
+                    const size_t bid = ((size_t)(xs / BRICK_X) * nby + y / BRICK_Y) * nbz + z / BRICK_Z;
+                    if (brick_cache[bid] < 0) {
+                        int fr0 = 0;
+                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
+                        brick_cache[bid] = c0 | (fr0 << 8);
+                    }
+                    const int bc = brick_cache[bid] & 0xff, fr = brick_cache[bid] >> 8;
+#if defined(DFB_BRICK_DEBUG)
+                    g_brick_cls_vox[i] = (uint8_t)(bc == BRICK_CLS_MIXED ? 200 - (int8_t)(brick_cache[bid] >> 8) : bc);
+#else
+                    g_brick_cls_vox[i] = (uint8_t)bc;
+#endif
+                    if (bc != BRICK_CLS_MIXED) {
+                        if (bc) {
+                            float v = P.tsdf[i], w = P.weight[i];
+                            for (int vi = 0; vi < P.n_views; ++vi)
+                                if (bc & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, (float)P.scale);
+                            P.tsdf[i] = v; P.weight[i] = w;
+                        }
+                        if (P.mask_out) P.mask_out[i] = (uint8_t)bc;
+                        if (P.frustum_out) P.frustum_out[i] = (uint8_t)fr;
+                        if (cls_out) cls_out[i] = bc ? CLS_CLAMP : CLS_SKIP;
+                        continue;
+                    }
+                }
                 uint16_t ids[KMAX] = {0};
                 for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
                 int m = 0, f = 0, cls = CLS_UNCERTAIN;

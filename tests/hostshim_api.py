@@ -16,7 +16,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "dynamicfusion_body_b200", "csrc")
 
 
 def build(force=False):
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h", "dfb_brick.h")]
     if not force and os.path.isfile(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", _SRC, "-o", _SO])
@@ -41,6 +41,31 @@ def lib():
                                                C.c_double, C.c_double, C.c_int, C.POINTER(_capi.Workspace), vp, vp]
         _lib.hs_warp_points.argtypes = [vp, vp, C.c_int64, vp, C.POINTER(_capi.WarpField), vp, vp]
     return _lib
+
+
+def set_bricks(knn=None, k=4, slab_shape=None, enable=True):
+    """Enable/disable the brick-culling emulation.  Returns the per-voxel brick-class array (0xFF = mixed) that the next
+    update_projective / fuse_depth_rigid call fills."""
+    L = lib()
+    L.hs_brick_nodes_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.hs_set_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    if not enable:
+        L.hs_set_bricks(None, None, None)
+        return None
+    sx, ry, rz = slab_shape
+    nb = ((sx + 3) // 4) * ((ry + 3) // 4) * ((rz + 31) // 32)
+    cls_vox = np.zeros(sx * ry * rz, np.uint8)
+    keep = [cls_vox]
+    if knn is not None:
+        knn = np.ascontiguousarray(knn, dtype=np.uint16)
+        nodes = np.zeros((nb, 24), np.uint16); count = np.zeros(nb, np.uint8)
+        L.hs_brick_nodes_build(_p(knn), k, sx, ry, rz, _p(nodes), _p(count))
+        L.hs_set_bricks(_p(nodes), _p(count), _p(cls_vox))
+        keep += [knn, nodes, count]
+    else:
+        L.hs_set_bricks(None, None, _p(cls_vox))
+    set_bricks._keep = keep
+    return cls_vox
 
 
 def _p(a):

@@ -103,6 +103,29 @@ def test_projective_hybrid_equals_exact_bitwise(small_scene):
     assert np.abs(out[0][0] - out[1][0]).max() <= 2e-7 * sc.tdist * 4
 
 
+def test_brick_culling_is_invisible():
+    """Brick culling (dfb_brick.h) only removes work: results with and without it are bit-identical, and on a
+    realistically sized scene most bricks never reach the per-voxel kernel."""
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    sc = synth.make_scene(res=192, k=4, n_nodes=1000, seed=0, background=True)
+    R = sc.res
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    depths = torch.from_numpy(sc.depths).cuda()
+    wf = _wf(engine, sc)
+    out = []
+    for use_bricks in (False, True):
+        vol = engine.DeviceVolume((R, R, R), tsdf=t0, weight=w0)
+        m, f = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist, want_masks=True, use_bricks=use_bricks)
+        out.append((vol.tsdf.cpu().numpy(), vol.weight.cpu().numpy(), m.cpu().numpy(), f.cpu().numpy()))
+        st = vol.workspace.stats()
+    print("brick stats", st)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert st["bricks_mixed"] < 0.5 * st["bricks"]
+
+
 def test_projective_multi_view_k8():
     torch, engine, _ = _engine()
     import scenes

@@ -136,3 +136,31 @@ def test_gn_residuals_and_normal_equations(sc, huber):
         wl = ogn.huber_weights(rl, 0.2, huber)
         Hl, gl, cl = Gp.lw_normal_eq(x.reshape(-1, 8), lw)
         assert np.abs(Jl.T @ (wl[:, None] * Jl) - Hl).max() <= 1e-10 * np.abs(Hl).max()
+
+
+def test_brick_culling_is_conservative():
+    """dfb_brick.h: a brick classified CLAMP/SKIP must agree with the oracle for every one of its voxels, and the final
+    volume must be identical to the un-culled result."""
+    s = synth.make_scene(res=128, k=4, n_nodes=600, seed=3, background=True, rows=240, cols=320)
+    R = s.res
+    from scipy.spatial import cKDTree
+    vox = ot.voxel_grid((R, R, R))
+    _, idx = cKDTree(s.node_pos.astype(np.float64)).query(vox.astype(np.float64), k=4)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=s.tdist)
+    nw = np.full(s.n_nodes, s.node_w)
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, s.node_pos, s.node_dq, nw, s.lw,
+                                           s.depths, s.K, s.Kinv, s.tdist)
+    wf = hs.HostWarpField(s.node_pos, s.node_dq, np.float32(s.node_w), 4, knn=idx, lw=s.lw)
+    res = []
+    for bricks in (False, True):
+        cv = hs.set_bricks(idx, 4, (R, R, R), enable=bricks)
+        tv, tw = t0.copy(), w0.copy()
+        mask, frus, cls, nunc = hs.update_projective(tv, tw, (R, R, R), wf, s.depths, s.K, s.Kinv, s.tdist)
+        res.append((tv, tw, mask, frus))
+        assert np.array_equal(scenes.bits(mask, 0), om[0]) and np.array_equal(scenes.bits(frus, 0), ofr[0])
+    hs.set_bricks(enable=False)
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    assert (cv != 255).mean() > 0.3                      # a sizeable part of the volume never needs the per-voxel tier
+    assert not (om[0] & (cv == 0)).any()                 # SKIP bricks contain no updated voxel
+    assert om[0][(cv != 0) & (cv != 255)].all()          # CLAMP bricks contain only updated voxels
