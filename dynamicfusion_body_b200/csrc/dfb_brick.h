@@ -46,6 +46,21 @@ DFB_HD void dq_affine_f(const float* q, float* A) {
     A[11] = 2 * (w * dz - dw * z + (x * dy - y * dx));
 }
 
+// 2 * (polarisation of dqb_warp's quadratic form): the affine map x -> 2*Qpol(a, b, x); for a == b it is 2*A(a)
+DFB_HD void dq_affine_polar2(const float* a, const float* b, float* A) {
+    const float wa = a[0], xa = a[1], ya = a[2], za = a[3], dwa = a[4], dxa = a[5], dya = a[6], dza = a[7];
+    const float wb = b[0], xb = b[1], yb = b[2], zb = b[3], dwb = b[4], dxb = b[5], dyb = b[6], dzb = b[7];
+    const float s = 2.f * (wa * wb - (xa * xb + ya * yb + za * zb));
+    const float xy = xa * yb + ya * xb, xz = xa * zb + za * xb, yz = ya * zb + za * yb;
+    const float wx = wa * xb + xa * wb, wy = wa * yb + ya * wb, wz = wa * zb + za * wb;
+    A[0] = s + 4.f * xa * xb;   A[1] = 2.f * (xy - wz);       A[2] = 2.f * (xz + wy);
+    A[4] = 2.f * (xy + wz);     A[5] = s + 4.f * ya * yb;     A[6] = 2.f * (yz - wx);
+    A[8] = 2.f * (xz - wy);     A[9] = 2.f * (yz + wx);       A[10] = s + 4.f * za * zb;
+    A[3] = 2.f * ((wa * dxb + wb * dxa) - (dwa * xb + dwb * xa) + (ya * dzb + yb * dza) - (za * dyb + zb * dya));
+    A[7] = 2.f * ((wa * dyb + wb * dya) - (dwa * yb + dwb * ya) + (za * dxb + zb * dxa) - (xa * dzb + xb * dza));
+    A[11] = 2.f * ((wa * dzb + wb * dza) - (dwa * zb + dwb * za) + (xa * dyb + xb * dya) - (ya * dxb + yb * dxa));
+}
+
 DFB_HD void box_extend_affine(const float* A, float inv, const float* c, const float* h, Box3& b) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
@@ -124,37 +139,36 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
         for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
         const uint16_t* ids = brick_nodes + b * BRICK_MAXC;
         bool bad = false;
-        int p = 0;
-        for (int i = 0; i < cnt; ++i) {
-            for (int j = 0; j <= i; ++j, ++p) {
-                if (p % ctx.nlanes() != ctx.lane()) continue;
+        const int npairs = cnt * (cnt + 1) / 2;
+        for (int p = ctx.lane(); p < npairs; p += ctx.nlanes()) {
+            // p -> (i, j), j <= i, row-major lower triangle
+            int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+            while (i * (i + 1) / 2 > p) --i;
+            while ((i + 1) * (i + 2) / 2 <= p) ++i;
+            const int j = p - i * (i + 1) / 2;
+            const float4 r1 = P.node_rec[3 * (size_t)ids[i] + 1];
+            const float4 r2 = P.node_rec[3 * (size_t)ids[i] + 2];
+            const float qi[8] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+            float nii = 0.f;
+            for (int t = 0; t < 8; ++t) nii += qi[t] * qi[t];
+            float Ap[12];
+            if (j == i) {
+                // every blend weight must be positive in the reference's float64 exp: farthest voxel of the brick
                 const float4 r0 = P.node_rec[3 * (size_t)ids[i]];
-                const float4 r1 = P.node_rec[3 * (size_t)ids[i] + 1];
-                const float4 r2 = P.node_rec[3 * (size_t)ids[i] + 2];
-                const float qi[8] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
-                float nii = 0.f;
-                for (int t = 0; t < 8; ++t) nii += qi[t] * qi[t];
-                float Ai[12];
-                dq_affine_f(qi, Ai);
-                if (j == i) {
-                    // every blend weight must be positive in the reference's float64 exp: farthest voxel of the brick
-                    const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
-                    if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -900.f) || !(nii > 1e-20f)) { bad = true; continue; }
-                    box_extend_affine(Ai, 1.0f / nii, c, h, bx);
-                } else {
-                    const float4 s1 = P.node_rec[3 * (size_t)ids[j] + 1];
-                    const float4 s2 = P.node_rec[3 * (size_t)ids[j] + 2];
-                    const float qj[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
-                    float ip = 0.f, njj = 0.f, qs[8];
-                    for (int t = 0; t < 8; ++t) { ip += qi[t] * qj[t]; njj += qj[t] * qj[t]; qs[t] = qi[t] + qj[t]; }
-                    // <q_i,q_j> must be safely positive (else the convex-combination argument does not apply)
-                    if (!(ip > 0.25f * sqrtf(nii * njj))) { bad = true; continue; }
-                    float As[12], Aj[12], Ap[12];
-                    dq_affine_f(qs, As);
-                    dq_affine_f(qj, Aj);
-                    for (int t = 0; t < 12; ++t) Ap[t] = As[t] - Ai[t] - Aj[t];   // = 2 * Qpol(q_i, q_j, .)
-                    box_extend_affine(Ap, 0.5f / ip, c, h, bx);
-                }
+                const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
+                if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -900.f) || !(nii > 1e-20f)) { bad = true; continue; }
+                dq_affine_polar2(qi, qi, Ap);
+                box_extend_affine(Ap, 0.5f / nii, c, h, bx);
+            } else {
+                const float4 s1 = P.node_rec[3 * (size_t)ids[j] + 1];
+                const float4 s2 = P.node_rec[3 * (size_t)ids[j] + 2];
+                const float qj[8] = {s1.x, s1.y, s1.z, s1.w, s2.x, s2.y, s2.z, s2.w};
+                float ip = 0.f, njj = 0.f;
+                for (int t = 0; t < 8; ++t) { ip += qi[t] * qj[t]; njj += qj[t] * qj[t]; }
+                // <q_i,q_j> must be safely positive (else the convex-combination argument does not apply)
+                if (!(ip > 0.25f * sqrtf(nii * njj))) { bad = true; continue; }
+                dq_affine_polar2(qi, qj, Ap);
+                box_extend_affine(Ap, 0.5f / ip, c, h, bx);
             }
         }
         if (ctx.any(bad)) return DFB_MIXED(2);
