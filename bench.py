@@ -35,6 +35,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_VOXEL = 16.0  # read v, read w, write v, write w (fp32) -- SURVEY 8d
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
+TRAFFIC_PER_LAUNCH = {}
 
 
 def measured_peaks():
@@ -192,25 +194,36 @@ def run_ours(args):
     ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     stats = fus.frame_stats()
 
-    # ---- roofline leg: the dominant kernel (fast pass) timed alone with CUDA events on its stream ----
-    fast_ms, exact_ms = [], []
-    for i in range(max(5, min(args.steps, 20))):
+    # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----
+    names = [("brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
+             ("brick_mixed_kernel<%d>" % (4 if args.k <= 4 else 8), _capi.MODE_BRICK_MIXED), ("proj_exact_kernel<%d>" % (4 if args.k <= 4 else 8), _capi.MODE_LIST_ONLY)]
+    per_kernel = {n: [] for n, _ in names}
+    for i in range(max(6, min(args.steps, 20))):
         fus.set_node_dqs(dq_dev[i % n_frames])
-        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        a.record()
-        fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics, mode=_capi.MODE_FAST_ONLY)
-        b.record()
-        fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics, mode=_capi.MODE_LIST_ONLY)
-        c.record()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ev[0].record()
+        for j, (n, mode) in enumerate(names):
+            fus.fuseFrame(depth_dev, extrinsics=sc.extrinsics, mode=mode)
+            ev[j + 1].record()
         torch.cuda.synchronize()
-        fast_ms.append(a.elapsed_time(b)); exact_ms.append(b.elapsed_time(c))
-    fast_avg = float(np.mean(fast_ms[2:])); exact_avg = float(np.mean(exact_ms[2:]))
-
+        for j, (n, _) in enumerate(names):
+            per_kernel[n].append(ev[j].elapsed_time(ev[j + 1]))
+    kms = {n: float(np.mean(v[2:])) for n, v in per_kernel.items()}
+    stats = fus.frame_stats()
+    vox_per_brick = 4 * 4 * 32
+    units = {names[0][0]: nvox_rank, names[1][0]: stats["bricks_streamed"] * vox_per_brick, names[2][0]: stats["bricks_mixed"] * vox_per_brick,
+             names[3][0]: stats["deferred"]}
+    dominant = max(kms, key=kms.get)
     total_vox = nvox_rank * world
     value = total_vox * args.steps / (ms_total * 1e-3)
     e2e_value = total_vox * args.steps / (ms_e2e * 1e-3)
     peak, peak_src = measured_peaks()
-    achieved = ALG_BYTES_PER_VOXEL * nvox_rank / (fast_avg * 1e-3) / 1e9
+    step_ms = ms_total / args.steps
+    kernels = [{"kernel": n, "ms": kms[n], "voxels": int(units[n]),
+                "achieved_GBps": ALG_BYTES_PER_VOXEL * units[n] / (kms[n] * 1e-3) / 1e9,
+                "frac": ALG_BYTES_PER_VOXEL * units[n] / (kms[n] * 1e-3) / 1e9 / peak} for n, _ in names]
+    achieved = ALG_BYTES_PER_VOXEL * units[dominant] / (kms[dominant] * 1e-3) / 1e9
+    step_achieved = ALG_BYTES_PER_VOXEL * nvox_rank / (step_ms * 1e-3) / 1e9
     out = {
         "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -219,15 +232,19 @@ def run_ours(args):
                                "%d view(s) 640x480, 15-frame dq sequence" % (per_gpu_res, res_x, res, res, args.k, sc.n_nodes, args.views),
                    "l2": "inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % (nvox_rank * (8 + 2 * args.k) / 1e6),
                    "parallelism": "x-slab per GPU, frame broadcast over NCCL" if world > 1 else "single GPU",
-                   "updated_voxel_fraction": stats.get("updated_fraction"), "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
+                   "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
         "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(sc.depths.nbytes + dqs[0].nbytes),
                 "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 5 * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "proj_fast_kernel<4>" if args.k <= 4 else "proj_fast_kernel<8>",
-                     "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "kernel_ms": fast_avg, "exact_pass_ms": exact_avg,
-                     "algorithmic_bytes_per_voxel": ALG_BYTES_PER_VOXEL, "step_frac_of_peak": ALG_BYTES_PER_VOXEL * nvox_rank / (ms_total / args.steps * 1e-3) / 1e9 / peak},
+        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": TRAFFIC_PER_LAUNCH.get(dominant.split("<")[0]),
+                     "note": "dominant kernel by time; its units = the voxels that launch processes x 16 B. The step as a whole "
+                             "(all voxels of the slab x 16 B / step time) is in `step`.",
+                     "algorithmic_bytes_per_voxel": ALG_BYTES_PER_VOXEL,
+                     "step": {"achieved": step_achieved, "frac": step_achieved / peak, "ms": step_ms},
+                     "kernels": kernels,
+                     "bricks": {"total": stats["bricks"], "streamed": stats["bricks_streamed"], "mixed": stats["bricks_mixed"]}},
     }
     if not args.no_gn:
         out["gn"] = bench_gn(args, dev, rank, world)

@@ -14,6 +14,9 @@ MODE_HYBRID = 0
 MODE_EXACT = 1
 MODE_FAST_ONLY = 2
 MODE_LIST_ONLY = 3
+MODE_BRICK_CLASSIFY = 4
+MODE_BRICK_STREAM = 5
+MODE_BRICK_MIXED = 6
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdfb_b200.so")

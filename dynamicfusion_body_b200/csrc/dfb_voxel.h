@@ -85,8 +85,9 @@ struct VolParams {
 // float64 exp, or zero blend) -> caller treats the voxel as uncertain.
 // amin_out: most negative exp argument (natural-log units) among the k nodes: scales the error bound.
 template <int KMAX>
-DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k, float px, float py, float pz, float* out,
-                            float* amin_out) {
+DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, float px, float py, float pz, float* out,
+                            float* amin_out, bool exact_k = false) {
+    const int k = exact_k ? KMAX : k_rt;   // exact_k is a compile-time constant at every call site: predicates fold away
     float a[KMAX];
     float amax = -3.0e38f, amin = 0.f;
 #pragma unroll
@@ -218,7 +219,7 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
 
 // fast classification of a voxel for a2/a3.  Returns CLS_UNCERTAIN, or CLS_SKIP/CLS_CLAMP-style result:
 // *mask gets the per-view clamp bits (all certain), *frus the per-view frustum bits.
-template <int KMAX>
+template <int KMAX, bool EXACTK = false>
 DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus) {
     float pw[3];
     float e;
@@ -227,7 +228,7 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
         e = 1.1920929e-7f * P.coord_mag * 32.f;
     } else {
         float amin;
-        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin)) return CLS_UNCERTAIN;
+        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin, EXACTK)) return CLS_UNCERTAIN;
         e = pos_err_bound(P.coord_mag, amin);
     }
     int m = 0, f = 0;

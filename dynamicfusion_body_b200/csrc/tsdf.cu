@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
 }
 
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
-template <int KMAX>
+template <int KMAX, bool EXACTK>
 __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
                                                           const uint32_t* list) {
     const uint32_t count = P.counters[3];
@@ -228,8 +228,8 @@ __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant_
             int cls = CLS_SKIP, m = 0, f = 0;
             if (in) {
                 uint16_t ids[KMAX];
-                if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
-                cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
+                if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
+                cls = voxel_projective_classify<KMAX, EXACTK>(P, xs + P.x0, y, z, ids, &m, &f);
             }
             push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
             if (!in || cls == CLS_UNCERTAIN) continue;
@@ -410,23 +410,36 @@ struct BrickArgs {
 };
 
 int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol, const BrickArgs& B) {
-    if (mode != DFB_MODE_LIST_ONLY) DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
+    const bool bricks = B.cls != nullptr && B.lists != nullptr && (P.rigid || (B.nodes != nullptr && B.count != nullptr));
+    const bool do_classify = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_CLASSIFY;
+    const bool do_stream = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_STREAM;
+    const bool do_mixed = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_MIXED;
+    if (mode >= DFB_MODE_BRICK_CLASSIFY) DFB_REQUIRE(bricks, "brick modes need the brick workspace / candidate sets");
+    if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_EXACT || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_CLASSIFY)
+        DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
-    if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY) {
-        const bool bricks = B.cls != nullptr && B.lists != nullptr && (P.rigid || (B.nodes != nullptr && B.count != nullptr));
+    if (mode != DFB_MODE_EXACT && mode != DFB_MODE_LIST_ONLY) {
         if (bricks) {
             const int nbx = (P.x1 - P.x0 + BRICK_X - 1) / BRICK_X, nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
             const int nb = nbx * nby * nbz;
             uint32_t* stream_list = B.lists;
             uint32_t* mixed_list = B.lists + nb;
-            brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-            DFB_LAUNCH_CHECK("brick_classify_kernel");
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
-            brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
-            DFB_LAUNCH_CHECK("brick_stream_kernel");
-            if (P.k <= 4) brick_mixed_kernel<4><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
-            else brick_mixed_kernel<8><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
-            DFB_LAUNCH_CHECK("brick_mixed_kernel");
+            if (do_classify) {
+                brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                DFB_LAUNCH_CHECK("brick_classify_kernel");
+            }
+            if (do_stream) {
+                brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
+                DFB_LAUNCH_CHECK("brick_stream_kernel");
+            }
+            if (do_mixed) {
+                if (P.k == 4 && !P.rigid) brick_mixed_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else if (P.k == 8 && !P.rigid) brick_mixed_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else if (P.k <= 4) brick_mixed_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else brick_mixed_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                DFB_LAUNCH_CHECK("brick_mixed_kernel");
+            }
         } else {
             int threads;
             const dim3 grid = fast_grid(vol, threads);
@@ -434,7 +447,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
             else proj_fast_kernel<8><<<grid, threads, 0, s>>>(P);
             DFB_LAUNCH_CHECK("proj_fast_kernel");
         }
-        if (mode == DFB_MODE_FAST_ONLY) return DFB_OK;
+        if (mode != DFB_MODE_HYBRID) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
     if (P.k <= 4) proj_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);

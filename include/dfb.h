@@ -36,6 +36,9 @@ extern "C" {
 #define DFB_MODE_EXACT 1  /* every voxel through the reference-exact pass (validation / debugging) */
 #define DFB_MODE_FAST_ONLY 2 /* profiling: pass 1 only (deferred voxels are left untouched, list is filled) */
 #define DFB_MODE_LIST_ONLY 3 /* profiling: pass 2 only, over the list a DFB_MODE_FAST_ONLY call left behind */
+#define DFB_MODE_BRICK_CLASSIFY 4 /* profiling: brick classification only (fills the brick lists) */
+#define DFB_MODE_BRICK_STREAM 5   /* profiling: streaming pass over the CLAMP bricks of the last classification */
+#define DFB_MODE_BRICK_MIXED 6    /* profiling: per-voxel pass over the MIXED bricks of the last classification */
 
 typedef void* dfb_stream_t; /* cudaStream_t */
 
