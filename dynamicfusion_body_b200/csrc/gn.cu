@@ -8,8 +8,12 @@
 // graph.  It is a scatter-add of tiny outer products, not a dense contraction: CUDA cores + float64 atomics,
 // no tensor cores.  Everything is float64 so that the solved update agrees with the float64
 // oracle to ~1e-9, far inside the 1e-4 tolerance of the north star.
+#include <cooperative_groups.h>
+
 #include "common.h"
 #include "dfb_gn.h"
+
+namespace cg = cooperative_groups;
 
 using namespace dfb;
 
@@ -368,6 +372,74 @@ __global__ void pcg_rotate_kernel(double* S, double tol2) {
     if (!(S[1] > tol2 * S[4])) S[5] = 1.0;  // converged (or NaN): freeze
 }
 
+
+// The whole PCG loop in ONE cooperative launch: the system is tiny (8N <= 32k rows, ~10 MB of L2-resident blocks), so
+// separate launches are pure launch latency (4 dependent launches ~ 37 us/iteration measured); grid.sync() costs ~2 us.
+__global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv, int n,
+                                                        int max_iter, double tol2, double* delta, double* r, double* z, double* p, double* q,
+                                                        double* S) {
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    for (int it = 0; it < max_iter; ++it) {
+        // A: q = (H + mu I) p, pq = p.q
+        const double mu = S[0];
+        double part = 0.0;
+        for (int t = tid; t < 8 * n; t += nthreads) {
+            const int i = t >> 3, a = t & 7;
+            double acc = mu * p[t];
+            for (int s = row_ptr[i]; s < row_ptr[i + 1]; ++s) {
+                const double* Hb = H + (size_t)s * 64 + a * 8;
+                const double* pj = p + 8 * (size_t)col_idx[s];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc += Hb[b] * pj[b];
+            }
+            q[t] = acc;
+            part += acc * p[t];
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0 && part != 0.0) atomicAdd(S + 2, part);
+        grid.sync();
+        // B: delta += alpha p, r -= alpha q, z = Minv r, rz_new = r.z
+        const double pq = S[2], rz = S[1];
+        const double alpha = (pq != 0.0) ? rz / pq : 0.0;
+        part = 0.0;
+        for (int i = tid; i < n; i += nthreads) {
+            double rr[8];
+            for (int a = 0; a < 8; ++a) {
+                const size_t t = 8 * (size_t)i + a;
+                delta[t] += alpha * p[t];
+                rr[a] = r[t] - alpha * q[t];
+                r[t] = rr[a];
+            }
+            for (int a = 0; a < 8; ++a) {
+                double zz = 0.0;
+                for (int b = 0; b < 8; ++b) zz += Minv[(size_t)i * 64 + a * 8 + b] * rr[b];
+                z[8 * (size_t)i + a] = zz;
+                part += rr[a] * zz;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0 && part != 0.0) atomicAdd(S + 3, part);
+        grid.sync();
+        // C: p = z + beta p; rotate the scalars
+        const double rzn = S[3];
+        const double beta = (rz != 0.0) ? rzn / rz : 0.0;
+        for (int t = tid; t < 8 * n; t += nthreads) p[t] = z[t] + beta * p[t];
+        grid.sync();   // every thread has read S[1], S[2], S[3]
+        if (tid == 0) {
+            S[1] = rzn;
+            S[2] = 0.0;
+            S[3] = 0.0;
+            S[6] += 1.0;
+            if (!(rzn > tol2 * S[4])) S[5] = 1.0;
+        }
+        grid.sync();
+        if (S[5] != 0.0) break;
+    }
+}
+
 __global__ void apply_delta_kernel(const double* x, const double* delta, int n8, double* x_new) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n8) x_new[t] = x[t] + delta[t];
@@ -487,13 +559,22 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
     pcg_init_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, g, n, lambda, Minv, delta, r, p, S);
     DFB_LAUNCH_CHECK("pcg_init_kernel");
     const double tol2 = tol * tol;
-    for (int it = 0; it < max_iter; ++it) {
-        pcg_spmv_kernel<<<nb_row, 128, 0, s>>>(row_ptr, col_idx, H, p, n, q, S);
-        pcg_update_kernel<<<nb_node, 128, 0, s>>>(Minv, q, p, n, delta, r, z, S);
-        pcg_direction_kernel<<<nb_row, 128, 0, s>>>(z, n, p, S, tol2);
-        pcg_rotate_kernel<<<1, 1, 0, s>>>(S, tol2);
+    {
+        static int coop_blocks = -1;   // co-resident CTAs of pcg_fused_kernel on this device
+        if (coop_blocks < 0) {
+            int dev = 0, sms = 0, per_sm = 0;
+            DFB_CUDA(cudaGetDevice(&dev));
+            DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel, 256, 0));
+            coop_blocks = sms * (per_sm > 0 ? 1 : 0);
+        }
+        DFB_REQUIRE(coop_blocks > 0, "cooperative launch not possible on this device");
+        int blocks = (8 * n + 255) / 256;
+        if (blocks > coop_blocks) blocks = coop_blocks;
+        void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
+                        (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&q, (void*)&S};
+        DFB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_fused_kernel, dim3(blocks), dim3(256), args, 0, s));
     }
-    DFB_LAUNCH_CHECK("pcg iteration kernels");
     apply_delta_kernel<<<nb_row, 128, 0, s>>>(x, delta, 8 * n, x_new);
     DFB_LAUNCH_CHECK("apply_delta_kernel");
     return DFB_OK;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant_
 
 // mode: 0 = work list (or re-scan on overflow), 1 = every voxel
 template <int KMAX>
-__global__ void __launch_bounds__(128) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
+__global__ void __launch_bounds__(128, 5) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
     const bool use_list = !all_mode && count <= P.capacity;
