@@ -39,7 +39,7 @@ class WarpField(C.Structure):
     _fields_ = [("node_rec", C.c_void_p), ("node_pos", C.c_void_p), ("node_dq", C.c_void_p),
                 ("node_w", C.c_void_p), ("n_nodes", C.c_int), ("k", C.c_int), ("knn", C.c_void_p),
                 ("has_lw", C.c_int), ("lw_is_f32", C.c_int), ("lw", C.c_double * 8),
-                ("brick_nodes", C.c_void_p), ("brick_count", C.c_void_p)]
+                ("brick_nodes", C.c_void_p), ("brick_count", C.c_void_p), ("brick_pairs", C.c_void_p)]
 
 
 class Views(C.Structure):
@@ -70,7 +70,7 @@ def declare(lib, prefix="dfb_", device=True):
         "nodes_pack": ([vp, vp, vp, C.c_int, vp] + ([vp] if device else []), None if not device else C.c_int),
         "knn_build_volume": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
         "brick_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
-        "brick_nodes_build": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
+        "brick_nodes_build": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp], C.c_int),
         "knn_points": ([vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp], C.c_int),
         "tsdf_update_projective": ([C.POINTER(Volume), C.POINTER(WarpField), C.POINTER(Views), C.c_double, C.c_double,
                                     C.c_int, C.POINTER(Workspace), vp, vp, vp], C.c_int),

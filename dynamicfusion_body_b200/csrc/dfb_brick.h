@@ -10,6 +10,8 @@
 // Rigour.  For a voxel x with neighbours S and ANY positive blend weights w_i, the reference's warped point is
 //     p'(x) = Q(b,x)/|b|^2,  b = sum_i w_i q_i      (Q2: 8-norm normalisation; Q = dqb_warp's quadratic form)
 //           = sum_ij (w_i w_j <q_i,q_j>) P_ij(x) / sum_ij (w_i w_j <q_i,q_j>),   P_ij(x) = Qpol(q_i,q_j,x)/<q_i,q_j>
+// (only pairs i,j that occur together in the kNN set of at least one voxel of the brick matter; they are cached as a
+// bit mask over the lower triangle of the candidate list)
 // where Qpol is the polarisation of Q.  If <q_i,q_j> > 0 for all pairs, p'(x) is a CONVEX COMBINATION of the points
 // P_ij(x), and each P_ij is an affine map of x.  Hence p'(brick) lies in the bounding box of the boxes
 // P_ij(brick), i,j in C, where C is the union of the kNN sets of the brick's voxels (cached per graph revision).
@@ -23,6 +25,7 @@ namespace dfb {
 
 constexpr int BRICK_X = 4, BRICK_Y = 4, BRICK_Z = 32;
 constexpr int BRICK_MAXC = 24;        // cached candidate nodes per brick (more -> always MIXED)
+constexpr int BRICK_PAIR_WORDS = 10;   // bit p = i*(i+1)/2 + j (j <= i) of the 24*25/2 = 300 candidate pairs
 constexpr int BRICK_CLS_MIXED = 0xFF;
 constexpr int BRICK_MAX_RECT = 512;   // depth pixels scanned per brick and view before giving up
 
@@ -120,8 +123,8 @@ struct WarpCtx {
 // *frus = per-view "certainly inside the image" bits (meaningful when the result is not MIXED).
 // All control flow is uniform across the lanes of `ctx`.
 template <class Ctx>
-DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, int nby, int nbz,
-                           int bxs, int by, int bz, int* frus, const Ctx ctx) {
+DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, const uint32_t* brick_pairs,
+                           int nby, int nbz, int bxs, int by, int bz, int* frus, const Ctx ctx) {
     *frus = 0;
     const int xlo = P.x0 + bxs * BRICK_X, ylo = by * BRICK_Y, zlo = bz * BRICK_Z;
     const int xhi = (xlo + BRICK_X - 1 < P.x1 - 1) ? xlo + BRICK_X - 1 : P.x1 - 1;
@@ -140,7 +143,9 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
         const uint16_t* ids = brick_nodes + b * BRICK_MAXC;
         bool bad = false;
         const int npairs = cnt * (cnt + 1) / 2;
+        const uint32_t* pm = brick_pairs ? brick_pairs + b * BRICK_PAIR_WORDS : nullptr;
         for (int p = ctx.lane(); p < npairs; p += ctx.nlanes()) {
+            if (pm && !((pm[p >> 5] >> (p & 31)) & 1u)) continue;      // this pair never blends inside the brick
             // p -> (i, j), j <= i, row-major lower triangle
             int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
             while (i * (i + 1) / 2 > p) --i;

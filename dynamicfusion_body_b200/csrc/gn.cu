@@ -308,71 +308,6 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
     if (i == 0) S[0] = mu;
 }
 
-__global__ void pcg_spmv_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* p, int n, double* q, double* S) {
-    if (S[5] != 0.0) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;  // scalar row
-    double part = 0.0;
-    if (t < 8 * n) {
-        const int i = t >> 3, a = t & 7;
-        double acc = S[0] * p[t];
-        for (int s = row_ptr[i]; s < row_ptr[i + 1]; ++s) {
-            const double* Hb = H + (size_t)s * 64 + a * 8;
-            const double* pj = p + 8 * (size_t)col_idx[s];
-#pragma unroll
-            for (int b = 0; b < 8; ++b) acc += Hb[b] * pj[b];
-        }
-        q[t] = acc;
-        part = acc * p[t];
-    }
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(S + 2, part);
-}
-
-__global__ void pcg_update_kernel(const double* Minv, const double* q, const double* p, int n, double* delta, double* r, double* z, double* S) {
-    if (S[5] != 0.0) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // node
-    const double alpha = (S[2] != 0.0) ? S[1] / S[2] : 0.0;
-    double part = 0.0;
-    if (i < n) {
-        double rr[8];
-        for (int a = 0; a < 8; ++a) {
-            const size_t t = 8 * (size_t)i + a;
-            delta[t] += alpha * p[t];
-            rr[a] = r[t] - alpha * q[t];
-            r[t] = rr[a];
-        }
-        for (int a = 0; a < 8; ++a) {
-            double zz = 0.0;
-            for (int b = 0; b < 8; ++b) zz += Minv[(size_t)i * 64 + a * 8 + b] * rr[b];
-            z[8 * (size_t)i + a] = zz;
-            part += rr[a] * zz;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(S + 3, part);
-}
-
-__global__ void pcg_direction_kernel(const double* z, int n, double* p, double* S, double tol2) {
-    if (S[5] != 0.0) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const double rz = S[1], rzn = S[3];
-    const double beta = (rz != 0.0) ? rzn / rz : 0.0;
-    if (t < 8 * n) p[t] = z[t] + beta * p[t];
-    // the last block to finish rotates the scalars (grid-wide ordering via a ticket in S[6]'s fractional twin is
-    // avoided: a dedicated 1-thread kernel does it instead, see pcg_rotate_kernel)
-    (void)tol2;
-}
-
-__global__ void pcg_rotate_kernel(double* S, double tol2) {
-    if (S[5] != 0.0) return;
-    S[1] = S[3];
-    S[2] = 0.0;
-    S[3] = 0.0;
-    S[6] += 1.0;
-    if (!(S[1] > tol2 * S[4])) S[5] = 1.0;  // converged (or NaN): freeze
-}
-
-
 // The whole PCG loop in ONE cooperative launch: the system is tiny (8N <= 32k rows, ~10 MB of L2-resident blocks), so
 // separate launches are pure launch latency (4 dependent launches ~ 37 us/iteration measured); grid.sync() costs ~2 us.
 __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv, int n,
@@ -383,41 +318,61 @@ __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, 
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
     for (int it = 0; it < max_iter; ++it) {
-        // A: q = (H + mu I) p, pq = p.q
+        // A: q = (H + mu I) p, pq = p.q.  One warp per block row: lane = (column group cgp = lane>>3, row a = lane&7);
+        //    the 8 lanes of a group read one 512-byte block row-by-row (coalesced), groups stride over the row's blocks.
         const double mu = S[0];
         double part = 0.0;
-        for (int t = tid; t < 8 * n; t += nthreads) {
-            const int i = t >> 3, a = t & 7;
-            double acc = mu * p[t];
-            for (int s = row_ptr[i]; s < row_ptr[i + 1]; ++s) {
-                const double* Hb = H + (size_t)s * 64 + a * 8;
-                const double* pj = p + 8 * (size_t)col_idx[s];
+        {
+            const int warp = tid >> 5, nwarps = nthreads >> 5;
+            const int a = lane & 7, cgp = lane >> 3;
+            for (int i = warp; i < n; i += nwarps) {
+                double acc = 0.0;
+                for (int s = row_ptr[i] + cgp; s < row_ptr[i + 1]; s += 4) {
+                    const double* Hb = H + (size_t)s * 64 + a * 8;
+                    const double* pj = p + 8 * (size_t)col_idx[s];
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc += Hb[b] * pj[b];
+                    for (int b = 0; b < 8; ++b) acc += Hb[b] * pj[b];
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+                if (cgp == 0) {
+                    const double pa = p[8 * (size_t)i + a];
+                    acc += mu * pa;
+                    q[8 * (size_t)i + a] = acc;
+                    part += acc * pa;
+                }
             }
-            q[t] = acc;
-            part += acc * p[t];
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0 && part != 0.0) atomicAdd(S + 2, part);
         grid.sync();
-        // B: delta += alpha p, r -= alpha q, z = Minv r, rz_new = r.z
+        // B: delta += alpha p, r -= alpha q, z = Minv r, rz_new = r.z.  8 lanes per node (lane a owns component a).
         const double pq = S[2], rz = S[1];
         const double alpha = (pq != 0.0) ? rz / pq : 0.0;
         part = 0.0;
-        for (int i = tid; i < n; i += nthreads) {
-            double rr[8];
-            for (int a = 0; a < 8; ++a) {
-                const size_t t = 8 * (size_t)i + a;
-                delta[t] += alpha * p[t];
-                rr[a] = r[t] - alpha * q[t];
-                r[t] = rr[a];
-            }
-            for (int a = 0; a < 8; ++a) {
+        {
+            const int grp = tid >> 3, ngrp = nthreads >> 3, a = lane & 7;
+            const int nloop = (n + ngrp - 1) / ngrp;
+            for (int l = 0; l < nloop; ++l) {
+                const int i = grp + l * ngrp;
+                const bool ok = i < n;
+                const size_t t = 8 * (size_t)(ok ? i : 0) + a;
+                double ra = 0.0;
+                if (ok) {
+                    delta[t] += alpha * p[t];
+                    ra = r[t] - alpha * q[t];
+                    r[t] = ra;
+                }
                 double zz = 0.0;
-                for (int b = 0; b < 8; ++b) zz += Minv[(size_t)i * 64 + a * 8 + b] * rr[b];
-                z[8 * (size_t)i + a] = zz;
-                part += rr[a] * zz;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const double rb = __shfl_sync(0xffffffffu, ra, (lane & 24) | b);
+                    if (ok) zz += Minv[(size_t)i * 64 + a * 8 + b] * rb;
+                }
+                if (ok) {
+                    z[t] = zz;
+                    part += ra * zz;
+                }
             }
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
@@ -569,7 +524,7 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
             coop_blocks = sms * (per_sm > 0 ? 1 : 0);
         }
         DFB_REQUIRE(coop_blocks > 0, "cooperative launch not possible on this device");
-        int blocks = (8 * n + 255) / 256;
+        int blocks = (32 * n + 255) / 256;   // one warp per block row
         if (blocks > coop_blocks) blocks = coop_blocks;
         void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
                         (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&q, (void*)&S};

@@ -99,8 +99,10 @@ __device__ __forceinline__ void brick_lane(int t, int& dx, int& dy, int& dz) {
 }
 
 __global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, int k, int sx, int ry, int rz, int nby, int nbz,
-                                                          uint16_t* brick_nodes, uint8_t* brick_count) {
+                                                          uint16_t* brick_nodes, uint8_t* brick_count, uint32_t* brick_pairs) {
     __shared__ unsigned int set[64];
+    __shared__ unsigned int list[BRICK_MAXC];
+    __shared__ unsigned int pairs[BRICK_PAIR_WORDS];
     __shared__ int n_out, overflow;
     const int b = blockIdx.x;
     int bxs, by, bz;
@@ -130,25 +132,54 @@ __global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, i
         }
     }
     __syncthreads();
+    if (threadIdx.x < BRICK_PAIR_WORDS) pairs[threadIdx.x] = 0u;
     if (threadIdx.x < 64 && set[threadIdx.x] != 0xffffffffu) {
         const int pos = atomicAdd(&n_out, 1);
-        if (pos < BRICK_MAXC) brick_nodes[(size_t)b * BRICK_MAXC + pos] = (uint16_t)set[threadIdx.x];
+        if (pos < BRICK_MAXC) {
+            brick_nodes[(size_t)b * BRICK_MAXC + pos] = (uint16_t)set[threadIdx.x];
+            list[pos] = set[threadIdx.x];
+        }
     }
     __syncthreads();
-    if (threadIdx.x == 0) brick_count[b] = (overflow || n_out > BRICK_MAXC) ? 255 : (uint8_t)n_out;
+    const bool ok = !overflow && n_out <= BRICK_MAXC;
+    if (threadIdx.x == 0) brick_count[b] = ok ? (uint8_t)n_out : 255;
+    if (!ok) return;
+    // pairs of candidates that share a voxel: bit i*(i+1)/2 + j, j <= i (local indices into the brick's list)
+    if (xs < sx && y < ry) {
+        for (int q = 0; q < 4; ++q) {
+            const int z = bz * BRICK_Z + dz + q;
+            if (z >= rz) break;
+            const size_t i = ((size_t)xs * ry + y) * rz + z;
+            int loc[DFB_MAX_K];
+            for (int j = 0; j < k; ++j) {
+                const unsigned int id = knn[i * (size_t)k + j];
+                int l = 0;
+                while (l < n_out && list[l] != id) ++l;
+                loc[j] = l;
+            }
+            for (int a = 0; a < k; ++a)
+                for (int c2 = 0; c2 <= a; ++c2) {
+                    const int hi = loc[a] > loc[c2] ? loc[a] : loc[c2], lo = loc[a] > loc[c2] ? loc[c2] : loc[a];
+                    const int p = hi * (hi + 1) / 2 + lo;
+                    atomicOr(&pairs[p >> 5], 1u << (p & 31));
+                }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < BRICK_PAIR_WORDS) brick_pairs[(size_t)b * BRICK_PAIR_WORDS + threadIdx.x] = pairs[threadIdx.x];
 }
 
 // one warp per brick (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h WarpCtx)
 __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
-                                                             const uint8_t* brick_count, int nbx, int nby, int nbz, uint8_t* cls_out,
-                                                             uint32_t* stream_list, uint32_t* mixed_list) {
+                                                             const uint8_t* brick_count, const uint32_t* brick_pairs, int nbx, int nby, int nbz,
+                                                             uint8_t* cls_out, uint32_t* stream_list, uint32_t* mixed_list) {
     const int nb = nbx * nby * nbz;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += nwarps) {
         int bxs, by, bz, fr = 0;
         brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int cls = brick_classify(P, brick_nodes, brick_count, nby, nbz, bxs, by, bz, &fr, WarpCtx());
+        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, nby, nbz, bxs, by, bz, &fr, WarpCtx());
         if (lane == 0) {
             cls_out[b] = (uint8_t)cls;
             cls_out[nb + b] = (uint8_t)fr;
@@ -405,6 +436,7 @@ int exact_blocks(size_t nvox) {
 struct BrickArgs {
     const uint16_t* nodes;
     const uint8_t* count;
+    const uint32_t* pairs;
     uint8_t* cls;
     uint32_t* lists;
 };
@@ -426,7 +458,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
             uint32_t* mixed_list = B.lists + nb;
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
             if (do_classify) {
-                brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream) {
@@ -475,7 +507,7 @@ extern "C" int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpf
                                           uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream) {
     ProjParams P;
     if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
-    const BrickArgs B = {wf->brick_nodes, wf->brick_count, ws->brick_cls, ws->brick_lists};
+    const BrickArgs B = {wf->brick_nodes, wf->brick_count, wf->brick_pairs, ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
@@ -488,7 +520,7 @@ extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const f
     if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
                             mask_out, frustum_out))
         return r;
-    const BrickArgs B = {nullptr, nullptr, ws->brick_cls, ws->brick_lists};
+    const BrickArgs B = {nullptr, nullptr, nullptr, ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
@@ -544,14 +576,14 @@ extern "C" int64_t dfb_brick_count(int sx, int ry, int rz) {
 }
 
 extern "C" int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* brick_nodes,
-                                     uint8_t* brick_count, dfb_stream_t stream) {
-    DFB_REQUIRE(knn && brick_nodes && brick_count, "null pointer");
+                                     uint8_t* brick_count, uint32_t* brick_pairs, dfb_stream_t stream) {
+    DFB_REQUIRE(knn && brick_nodes && brick_count && brick_pairs, "null pointer");
     DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K && rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad arguments");
     const int sx = x1 - x0;
     const int nby = (ry + BRICK_Y - 1) / BRICK_Y, nbz = (rz + BRICK_Z - 1) / BRICK_Z;
     const int64_t nb = dfb_brick_count(sx, ry, rz);
     DFB_REQUIRE(nb < ((int64_t)1 << 31), "too many bricks");
-    brick_nodes_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(knn, k, sx, ry, rz, nby, nbz, brick_nodes, brick_count);
+    brick_nodes_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(knn, k, sx, ry, rz, nby, nbz, brick_nodes, brick_count, brick_pairs);
     DFB_LAUNCH_CHECK("brick_nodes_kernel");
     return DFB_OK;
 }

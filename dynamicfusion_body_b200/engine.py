@@ -146,8 +146,10 @@ class DeviceWarpField:
             nb = int(_capi.lib().dfb_brick_count(x1 - x0, res[1], res[2]))
             nodes = torch.zeros((nb, 24), dtype=torch.int16, device=self.device)
             count = torch.zeros(nb, dtype=torch.uint8, device=self.device)
-            _capi.check(_capi.lib().dfb_brick_nodes_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(nodes), _ptr(count), _stream()))
-            t = (nodes, count)
+            pairs = torch.zeros((nb, 10), dtype=torch.int32, device=self.device)
+            _capi.check(_capi.lib().dfb_brick_nodes_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(nodes), _ptr(count),
+                                                          _ptr(pairs), _stream()))
+            t = (nodes, count, pairs)
             self._bricks[key] = t
         return t
 
@@ -163,6 +165,7 @@ class DeviceWarpField:
         if bricks is not None:
             s.brick_nodes = bricks[0].data_ptr()
             s.brick_count = bricks[1].data_ptr()
+            s.brick_pairs = bricks[2].data_ptr()
         k = self.k if k is None else k
         if k > 0:
             s.node_rec = self.node_rec.data_ptr()

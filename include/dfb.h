@@ -64,6 +64,7 @@ typedef struct dfb_warpfield {
     /* optional (NULL = no brick culling): per-brick union of the voxels' kNN sets, from dfb_brick_nodes_build */
     const uint16_t* brick_nodes; /* [n_bricks][24] */
     const uint8_t* brick_count;  /* [n_bricks], 255 = more than 24 */
+    const uint32_t* brick_pairs; /* [n_bricks][10]: bit i*(i+1)/2+j set when candidates i>=j share a voxel's kNN set (NULL = all pairs) */
 } dfb_warpfield;
 
 typedef struct dfb_views {
@@ -102,7 +103,7 @@ int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int 
  * derived from the kNN table (once per graph revision). */
 int64_t dfb_brick_count(int slab_x, int ry, int rz);
 int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* brick_nodes,
-                          uint8_t* brick_count, dfb_stream_t stream);
+                          uint8_t* brick_count, uint32_t* brick_pairs, dfb_stream_t stream);
 /* KDTree.query(vert, k) for arbitrary float32 points (core/fusion.py:122,232). */
 int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
                    dfb_stream_t stream);

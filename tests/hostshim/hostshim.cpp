@@ -35,7 +35,8 @@ extern "C" void hs_nodes_pack(const float* pos, const float* dq, const float* w,
     }
 }
 
-extern "C" void hs_brick_nodes_build(const uint16_t* knn, int k, int sx, int ry, int rz, uint16_t* brick_nodes, uint8_t* brick_count) {
+extern "C" void hs_brick_nodes_build(const uint16_t* knn, int k, int sx, int ry, int rz, uint16_t* brick_nodes, uint8_t* brick_count,
+                                     uint32_t* brick_pairs) {
     const int nbx = (sx + BRICK_X - 1) / BRICK_X, nby = (ry + BRICK_Y - 1) / BRICK_Y, nbz = (rz + BRICK_Z - 1) / BRICK_Z;
     for (int bx = 0; bx < nbx; ++bx)
         for (int by = 0; by < nby; ++by)
@@ -53,15 +54,33 @@ extern "C" void hs_brick_nodes_build(const uint16_t* knn, int k, int sx, int ry,
                             }
                 brick_count[b] = set.size() > (size_t)BRICK_MAXC ? 255 : (uint8_t)set.size();
                 for (size_t t = 0; t < set.size() && t < (size_t)BRICK_MAXC; ++t) brick_nodes[b * BRICK_MAXC + t] = set[t];
+                for (int t = 0; t < BRICK_PAIR_WORDS; ++t) brick_pairs[b * BRICK_PAIR_WORDS + t] = 0;
+                if (set.size() > (size_t)BRICK_MAXC) continue;
+                for (int x = bx * BRICK_X; x < std::min(sx, (bx + 1) * BRICK_X); ++x)
+                    for (int y = by * BRICK_Y; y < std::min(ry, (by + 1) * BRICK_Y); ++y)
+                        for (int z = bz * BRICK_Z; z < std::min(rz, (bz + 1) * BRICK_Z); ++z) {
+                            int loc[DFB_MAX_K];
+                            for (int j = 0; j < k; ++j) {
+                                const uint16_t id = knn[(((size_t)x * ry + y) * rz + z) * k + j];
+                                loc[j] = (int)(std::find(set.begin(), set.end(), id) - set.begin());
+                            }
+                            for (int a = 0; a < k; ++a)
+                                for (int c2 = 0; c2 <= a; ++c2) {
+                                    const int hi = std::max(loc[a], loc[c2]), lo = std::min(loc[a], loc[c2]);
+                                    const int p = hi * (hi + 1) / 2 + lo;
+                                    brick_pairs[b * BRICK_PAIR_WORDS + (p >> 5)] |= 1u << (p & 31);
+                                }
+                        }
             }
 }
 
 // per-voxel brick class for the tests: 0xFF mixed, else clamp mask; frus bits in brick_frus
 static const uint16_t* g_brick_nodes = nullptr;
 static const uint8_t* g_brick_count = nullptr;
+static const uint32_t* g_brick_pairs = nullptr;
 static uint8_t* g_brick_cls_vox = nullptr;
-extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, uint8_t* cls_vox) {
-    g_brick_nodes = nodes; g_brick_count = count; g_brick_cls_vox = cls_vox;
+extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox) {
+    g_brick_nodes = nodes; g_brick_count = count; g_brick_pairs = pairs; g_brick_cls_vox = cls_vox;
 }
 
 template <int KMAX>
@@ -79,7 +98,7 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                     const size_t bid = ((size_t)(xs / BRICK_X) * nby + y / BRICK_Y) * nbz + z / BRICK_Z;
                     if (brick_cache[bid] < 0) {
                         int fr0 = 0;
-                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
+                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, g_brick_pairs, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
                         brick_cache[bid] = c0 | (fr0 << 8);
                     }
                     const int bc = brick_cache[bid] & 0xff, fr = brick_cache[bid] >> 8;

@@ -43,14 +43,14 @@ def lib():
     return _lib
 
 
-def set_bricks(knn=None, k=4, slab_shape=None, enable=True):
+def set_bricks(knn=None, k=4, slab_shape=None, enable=True, use_pairs=True):
     """Enable/disable the brick-culling emulation.  Returns the per-voxel brick-class array (0xFF = mixed) that the next
     update_projective / fuse_depth_rigid call fills."""
     L = lib()
-    L.hs_brick_nodes_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-    L.hs_set_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_brick_nodes_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_set_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     if not enable:
-        L.hs_set_bricks(None, None, None)
+        L.hs_set_bricks(None, None, None, None)
         return None
     sx, ry, rz = slab_shape
     nb = ((sx + 3) // 4) * ((ry + 3) // 4) * ((rz + 31) // 32)
@@ -58,12 +58,12 @@ def set_bricks(knn=None, k=4, slab_shape=None, enable=True):
     keep = [cls_vox]
     if knn is not None:
         knn = np.ascontiguousarray(knn, dtype=np.uint16)
-        nodes = np.zeros((nb, 24), np.uint16); count = np.zeros(nb, np.uint8)
-        L.hs_brick_nodes_build(_p(knn), k, sx, ry, rz, _p(nodes), _p(count))
-        L.hs_set_bricks(_p(nodes), _p(count), _p(cls_vox))
-        keep += [knn, nodes, count]
+        nodes = np.zeros((nb, 24), np.uint16); count = np.zeros(nb, np.uint8); pairs = np.zeros((nb, 10), np.uint32)
+        L.hs_brick_nodes_build(_p(knn), k, sx, ry, rz, _p(nodes), _p(count), _p(pairs))
+        L.hs_set_bricks(_p(nodes), _p(count), _p(pairs) if use_pairs else None, _p(cls_vox))
+        keep += [knn, nodes, count, pairs]
     else:
-        L.hs_set_bricks(None, None, _p(cls_vox))
+        L.hs_set_bricks(None, None, None, _p(cls_vox))
     set_bricks._keep = keep
     return cls_vox
 
