@@ -17,6 +17,7 @@ MODE_LIST_ONLY = 3
 MODE_BRICK_CLASSIFY = 4
 MODE_BRICK_STREAM = 5
 MODE_BRICK_MIXED = 6
+MODE_BRICK_UPDATE = 7
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libdfb_b200.so")

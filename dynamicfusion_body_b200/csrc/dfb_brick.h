@@ -94,6 +94,25 @@ DFB_HD void div_interval(float nlo, float nhi, float dlo, float dhi, float& lo, 
     hi += slack;
 }
 
+// position of the n-th (0-based) set bit of w
+DFB_HD int nth_set_bit(uint32_t w, int n) {
+#if defined(__CUDA_ARCH__)
+    return (int)__fns(w, 0, n + 1);
+#else
+    for (int b = 0; b < 32; ++b)
+        if ((w >> b) & 1u) { if (n == 0) return b; --n; }
+    return 32;
+#endif
+}
+
+DFB_HD int popc32(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+    return __popc(w);
+#else
+    return __builtin_popcount(w);
+#endif
+}
+
 // Execution context: the same code runs with one warp per brick on the GPU (lanes split the node pairs and the depth
 // pixels, reductions by shuffle) and with a single "lane" on the host (tests/hostshim).
 struct SerialCtx {
@@ -142,10 +161,25 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
         for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
         const uint16_t* ids = brick_nodes + b * BRICK_MAXC;
         bool bad = false;
-        const int npairs = cnt * (cnt + 1) / 2;
-        const uint32_t* pm = brick_pairs ? brick_pairs + b * BRICK_PAIR_WORDS : nullptr;
-        for (int p = ctx.lane(); p < npairs; p += ctx.nlanes()) {
-            if (pm && !((pm[p >> 5] >> (p & 31)) & 1u)) continue;      // this pair never blends inside the brick
+        const int npairs_all = cnt * (cnt + 1) / 2;
+        // pairs to visit: the set bits of the cached co-occurrence mask (all pairs when no mask is given), dealt out to
+        // the lanes in compact order so that no lane idles on pairs that never blend inside this brick
+        uint32_t pm[BRICK_PAIR_WORDS];
+        int pre[BRICK_PAIR_WORDS + 1];
+        pre[0] = 0;
+        for (int w = 0; w < BRICK_PAIR_WORDS; ++w) {
+            uint32_t m = brick_pairs ? brick_pairs[b * BRICK_PAIR_WORDS + w] : 0xffffffffu;
+            const int rem = npairs_all - 32 * w;
+            if (rem <= 0) m = 0u;
+            else if (rem < 32) m &= (1u << rem) - 1u;
+            pm[w] = m;
+            pre[w + 1] = pre[w] + popc32(m);
+        }
+        const int npairs = pre[BRICK_PAIR_WORDS];
+        for (int t = ctx.lane(); t < npairs; t += ctx.nlanes()) {
+            int w = 0;
+            while (pre[w + 1] <= t) ++w;
+            const int p = 32 * w + nth_set_bit(pm[w], t - pre[w]);
             // p -> (i, j), j <= i, row-major lower triangle
             int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
             while (i * (i + 1) / 2 > p) --i;

@@ -111,7 +111,7 @@ inline int build_projective(ProjParams& P, const dfb_volume* vol, const dfb_warp
     if (int r = validate_ws(ws)) return r;
     DFB_REQUIRE(views && views->n_views >= 1 && views->n_views <= DFB_MAX_VIEWS, "n_views out of range");
     DFB_REQUIRE(views->rows >= 2 && views->cols >= 2, "depth map too small");
-    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_MIXED, "bad mode");
+    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_UPDATE, "bad mode");
     DFB_REQUIRE(wf->k > 0, "projective update needs k >= 1 (use dfb_fuse_depth_rigid for the rigid path)");
     DFB_REQUIRE(tdist != 0, "truncation distance must be non-zero");
     memset(&P, 0, sizeof(P));
@@ -156,7 +156,7 @@ inline int build_rigid(ProjParams& P, const dfb_volume* vol, int tsdf_res, const
     if (int r = validate_ws(ws)) return r;
     DFB_REQUIRE(depth && lw34 && K && Kinv && center, "null pointer");
     DFB_REQUIRE(rows >= 2 && cols >= 2, "depth map too small");
-    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_MIXED, "bad mode");
+    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_UPDATE, "bad mode");
     DFB_REQUIRE(scale > 0, "scale must be positive");
     DFB_REQUIRE(tdist != 0, "truncation distance must be non-zero");
     memset(&P, 0, sizeof(P));
@@ -189,7 +189,7 @@ inline int build_volume(VolParams& P, const dfb_volume* vol, const dfb_warpfield
     if (int r = validate_warpfield(wf, true)) return r;
     if (int r = validate_ws(ws)) return r;
     DFB_REQUIRE(curr && cx > 0 && cy > 0 && cz > 0, "tsdf of live frame has not been loaded");
-    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_MIXED, "bad mode");
+    DFB_REQUIRE(mode >= DFB_MODE_HYBRID && mode <= DFB_MODE_BRICK_UPDATE, "bad mode");
     DFB_REQUIRE(tdist != 0, "truncation distance must be non-zero");
     memset(&P, 0, sizeof(P));
     P.tsdf = vol->tsdf; P.weight = vol->weight;

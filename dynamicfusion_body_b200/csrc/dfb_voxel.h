@@ -194,7 +194,7 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
         int ids[8];
         for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
         warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
-                 nullptr, nullptr);
+                 nullptr, nullptr, true);
     }
     double v = (double)*v_io, w = (double)*w_io;
     int m = 0, f = 0;
@@ -256,7 +256,7 @@ DFB_HDN bool voxel_volume_exact(const VolParams& P, int x, int y, int z, const u
     for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
     double pw[3];
     float wi = 0.f;
-    warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, pw, nullptr, &wi);
+    warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, pw, nullptr, &wi, true);
     double tl = 0.0;
     const bool valid = interpolate_tsdf_ref(pw, P.curr, P.cx, P.cy, P.cz, &tl);
     double v = (double)*v_io, w = (double)*w_io;

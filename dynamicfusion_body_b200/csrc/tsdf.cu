@@ -190,90 +190,112 @@ __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_consta
 }
 
 // CLAMP bricks: v' = (scale*v*w + tdist)/(scale*(w+1)), w' = min(w+1, wmax) once per view bit -- no warp, no kNN read.
-__global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
-                                                           const uint8_t* cls, const uint32_t* list) {
-    const uint32_t count = P.counters[2];
-    const int nb = nbx * nby * nbz;
-    int dx, dy, dz;
-    brick_lane(threadIdx.x, dx, dy, dz);
-    const float sc = (float)P.scale;
-    const bool vec = (P.rz & 3) == 0;
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
-        const int b = (int)list[t];
-        int bxs, by, bz;
-        brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int m = cls[b], fr = cls[nb + b];
-        const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z = bz * BRICK_Z + dz;
-        if (xs >= P.x1 - P.x0 || y >= P.ry || z >= P.rz) continue;
-        const size_t i = ((size_t)xs * P.ry + y) * P.rz + z;
-        if (vec) {
-            if (m) {
-                float4 v = *reinterpret_cast<const float4*>(P.tsdf + i);
-                float4 w = *reinterpret_cast<const float4*>(P.weight + i);
-                for (int vi = 0; vi < P.n_views; ++vi)
-                    if (m & (1 << vi)) {
-                        clamp_update(v.x, w.x, P.tdist_f, P.wmax_f, sc);
-                        clamp_update(v.y, w.y, P.tdist_f, P.wmax_f, sc);
-                        clamp_update(v.z, w.z, P.tdist_f, P.wmax_f, sc);
-                        clamp_update(v.w, w.w, P.tdist_f, P.wmax_f, sc);
-                    }
-                *reinterpret_cast<float4*>(P.tsdf + i) = v;
-                *reinterpret_cast<float4*>(P.weight + i) = w;
-            }
-            if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i) = make_uchar4(m, m, m, m);
-            if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i) = make_uchar4(fr, fr, fr, fr);
-        } else {
-            for (int q = 0; q < 4 && z + q < P.rz; ++q) {
-                if (m) {
-                    float v = P.tsdf[i + q], w = P.weight[i + q];
-                    for (int vi = 0; vi < P.n_views; ++vi)
-                        if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
-                    P.tsdf[i + q] = v;
-                    P.weight[i + q] = w;
+__device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nby, int nbz, const uint8_t* cls, int b, int dx, int dy, int dz,
+                                             float sc, bool vec) {
+    int bxs, by, bz;
+    brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    const int m = cls[b], fr = cls[nb + b];
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z = bz * BRICK_Z + dz;
+    if (xs >= P.x1 - P.x0 || y >= P.ry || z >= P.rz) return;
+    const size_t i = ((size_t)xs * P.ry + y) * P.rz + z;
+    if (vec) {
+        if (m) {
+            float4 v = *reinterpret_cast<const float4*>(P.tsdf + i);
+            float4 w = *reinterpret_cast<const float4*>(P.weight + i);
+            for (int vi = 0; vi < P.n_views; ++vi)
+                if (m & (1 << vi)) {
+                    clamp_update(v.x, w.x, P.tdist_f, P.wmax_f, sc);
+                    clamp_update(v.y, w.y, P.tdist_f, P.wmax_f, sc);
+                    clamp_update(v.z, w.z, P.tdist_f, P.wmax_f, sc);
+                    clamp_update(v.w, w.w, P.tdist_f, P.wmax_f, sc);
                 }
-                if (P.mask_out) P.mask_out[i + q] = (uint8_t)m;
-                if (P.frustum_out) P.frustum_out[i + q] = (uint8_t)fr;
+            *reinterpret_cast<float4*>(P.tsdf + i) = v;
+            *reinterpret_cast<float4*>(P.weight + i) = w;
+        }
+        if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i) = make_uchar4(m, m, m, m);
+        if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i) = make_uchar4(fr, fr, fr, fr);
+    } else {
+        for (int q = 0; q < 4 && z + q < P.rz; ++q) {
+            if (m) {
+                float v = P.tsdf[i + q], w = P.weight[i + q];
+                for (int vi = 0; vi < P.n_views; ++vi)
+                    if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
+                P.tsdf[i + q] = v;
+                P.weight[i + q] = w;
             }
+            if (P.mask_out) P.mask_out[i + q] = (uint8_t)m;
+            if (P.frustum_out) P.frustum_out[i + q] = (uint8_t)fr;
         }
     }
 }
 
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
 template <int KMAX, bool EXACTK>
+__device__ __forceinline__ void mixed_brick(const ProjParams& P, int nby, int nbz, int b, int dx, int dy, int dz, float sc) {
+    int bxs, by, bz;
+    brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
+    const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
+    for (int q = 0; q < 4; ++q) {
+        const int z = z0 + q;
+        const bool in = row_in && z < P.rz;
+        const size_t i = in ? ((size_t)xs * P.ry + y) * P.rz + z : 0;
+        int cls = CLS_SKIP, m = 0, f = 0;
+        if (in) {
+            uint16_t ids[KMAX];
+            if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
+            cls = voxel_projective_classify<KMAX, EXACTK>(P, xs + P.x0, y, z, ids, &m, &f);
+        }
+        push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+        if (!in || cls == CLS_UNCERTAIN) continue;
+        if (m) {
+            float v = P.tsdf[i], w = P.weight[i];
+            for (int vi = 0; vi < P.n_views; ++vi)
+                if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
+            P.tsdf[i] = v;
+            P.weight[i] = w;
+        }
+        if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+        if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+    }
+}
+
+__global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                           const uint8_t* cls, const uint32_t* list) {
+    const uint32_t count = P.counters[2];
+    int dx, dy, dz;
+    brick_lane(threadIdx.x, dx, dy, dz);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x)
+        stream_brick(P, nbx * nby * nbz, nby, nbz, cls, (int)list[t], dx, dy, dz, (float)P.scale, (P.rz & 3) == 0);
+}
+
+template <int KMAX, bool EXACTK>
 __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
                                                           const uint32_t* list) {
     const uint32_t count = P.counters[3];
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)list[t], dx, dy, dz, (float)P.scale);
+}
+
+// Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
+// (issue-bound per-voxel tier) and its share of CLAMP bricks (HBM-bound streaming), so both kinds of work are resident
+// on every SM at the same time and the streaming traffic hides under the arithmetic.
+template <int KMAX, bool EXACTK>
+__global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                           const uint8_t* cls, const uint32_t* stream_list, const uint32_t* mixed_list) {
+    const uint32_t cnt_s = P.counters[2], cnt_m = P.counters[3];
+    const uint32_t n_t = cnt_m > gridDim.x ? cnt_m : gridDim.x;
+    const uint32_t share = (cnt_s + n_t - 1) / n_t;
+    const int nb = nbx * nby * nbz;
+    int dx, dy, dz;
+    brick_lane(threadIdx.x, dx, dy, dz);
     const float sc = (float)P.scale;
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) {
-        const int b = (int)list[t];
-        int bxs, by, bz;
-        brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
-        const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
-        for (int q = 0; q < 4; ++q) {
-            const int z = z0 + q;
-            const bool in = row_in && z < P.rz;
-            const size_t i = in ? ((size_t)xs * P.ry + y) * P.rz + z : 0;
-            int cls = CLS_SKIP, m = 0, f = 0;
-            if (in) {
-                uint16_t ids[KMAX];
-                if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
-                cls = voxel_projective_classify<KMAX, EXACTK>(P, xs + P.x0, y, z, ids, &m, &f);
-            }
-            push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
-            if (!in || cls == CLS_UNCERTAIN) continue;
-            if (m) {
-                float v = P.tsdf[i], w = P.weight[i];
-                for (int vi = 0; vi < P.n_views; ++vi)
-                    if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
-                P.tsdf[i] = v;
-                P.weight[i] = w;
-            }
-            if (P.mask_out) P.mask_out[i] = (uint8_t)m;
-            if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
-        }
+    const bool vec = (P.rz & 3) == 0;
+    for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
+        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)mixed_list[t], dx, dy, dz, sc);
+        const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
+        for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, (int)stream_list[s], dx, dy, dz, sc, vec);
     }
 }
 
@@ -444,8 +466,8 @@ struct BrickArgs {
 int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vol, const BrickArgs& B) {
     const bool bricks = B.cls != nullptr && B.lists != nullptr && (P.rigid || (B.nodes != nullptr && B.count != nullptr));
     const bool do_classify = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_CLASSIFY;
-    const bool do_stream = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_STREAM;
-    const bool do_mixed = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_MIXED;
+    const bool do_stream = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_STREAM || mode == DFB_MODE_BRICK_UPDATE;
+    const bool do_mixed = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_MIXED || mode == DFB_MODE_BRICK_UPDATE;
     if (mode >= DFB_MODE_BRICK_CLASSIFY) DFB_REQUIRE(bricks, "brick modes need the brick workspace / candidate sets");
     if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_EXACT || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_CLASSIFY)
         DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
@@ -461,11 +483,16 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
-            if (do_stream) {
+            if (do_stream && do_mixed) {
+                if (P.k == 4 && !P.rigid) brick_update_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (P.k == 8 && !P.rigid) brick_update_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (P.k <= 4) brick_update_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else brick_update_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                DFB_LAUNCH_CHECK("brick_update_kernel");
+            } else if (do_stream) {
                 brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
                 DFB_LAUNCH_CHECK("brick_stream_kernel");
-            }
-            if (do_mixed) {
+            } else if (do_mixed) {
                 if (P.k == 4 && !P.rigid) brick_mixed_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
                 else if (P.k == 8 && !P.rigid) brick_mixed_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
                 else if (P.k <= 4) brick_mixed_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);

@@ -39,6 +39,7 @@ extern "C" {
 #define DFB_MODE_BRICK_CLASSIFY 4 /* profiling: brick classification only (fills the brick lists) */
 #define DFB_MODE_BRICK_STREAM 5   /* profiling: streaming pass over the CLAMP bricks of the last classification */
 #define DFB_MODE_BRICK_MIXED 6    /* profiling: per-voxel pass over the MIXED bricks of the last classification */
+#define DFB_MODE_BRICK_UPDATE 7   /* profiling: the production fused CLAMP+MIXED pass after a DFB_MODE_BRICK_CLASSIFY call */
 
 typedef void* dfb_stream_t; /* cudaStream_t */
 
