@@ -123,19 +123,26 @@ struct SerialCtx {
     DFB_HD bool any(bool b) const { return b; }
 };
 #if defined(__CUDACC__)
-struct WarpCtx {
-    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
-    __device__ __forceinline__ int nlanes() const { return 32; }
+// G consecutive lanes cooperate on one brick (G = 8: four bricks per warp; the per-brick work that is uniform across
+// lanes -- intervals, projection -- is then amortised over four bricks instead of one).
+template <int G>
+struct GroupCtx {
+    __device__ __forceinline__ unsigned mask() const { return (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1))); }
+    __device__ __forceinline__ int lane() const { return threadIdx.x & (G - 1); }
+    __device__ __forceinline__ int nlanes() const { return G; }
     __device__ __forceinline__ float rmin(float v) const {
-        for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const unsigned m = mask();
+        for (int o = G / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(m, v, o));
         return v;
     }
     __device__ __forceinline__ float rmax(float v) const {
-        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        const unsigned m = mask();
+        for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, o));
         return v;
     }
-    __device__ __forceinline__ bool any(bool b) const { return __any_sync(0xffffffffu, b) != 0; }
+    __device__ __forceinline__ bool any(bool b) const { return (__ballot_sync(mask(), b) & mask()) != 0u; }
 };
+typedef GroupCtx<32> WarpCtx;
 #endif
 
 // Classify brick (bxs,by,bz) (bxs slab-local).  Returns BRICK_CLS_MIXED or the per-view CLAMP bit mask (0 = SKIP);

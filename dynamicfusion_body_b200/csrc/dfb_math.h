@@ -146,18 +146,36 @@ DFB_HD float norm3_f32_ref(float ax, float ay, float az, float bx, float by, flo
 // core/fusion.py:527-551 dq_blend (dmax=None) for a float32 point and float32 node data.
 // ids: k node indices; node_pos [n][3], node_dq [n][8], node_w [n] (float32 storage of dg_w).
 // Also returns the Q4 mean node distance (core/fusion.py:180-183) when wi_out != nullptr.
-DFB_HDN void dq_blend_ref(const float* p, const int* ids, int k, const float* node_pos, const float* node_dq,
+template <int KT = 0>   // KT > 0: compile-time neighbour count (loop unrolled: the k exp() chains overlap)
+DFB_HDN void dq_blend_ref(const float* p, const int* ids, int k_rt, const float* node_pos, const float* node_dq,
                           const float* node_w, double* se3, float* wi_out) {
     double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float wi = 0.f;
+    const int k = KT > 0 ? KT : k_rt;
+    double wts[KT > 0 ? KT : 1];
+    if (KT > 0) {
+#pragma unroll
+        for (int i = 0; i < (KT > 0 ? KT : 1); ++i) {
+            const float* np_ = node_pos + 3 * (size_t)ids[i];
+            const float nrm = norm3_f32_ref(p[0], p[1], p[2], np_[0], np_[1], np_[2]);
+            const float q = fdiv(nrm, fmul(2.0f, node_w[ids[i]]));
+            wts[i] = exp((double)fmul(-1.0f, fmul(q, q)));
+        }
+    }
+#pragma unroll
     for (int i = 0; i < k; ++i) {
         const int id = ids[i];
         const float* np_ = node_pos + 3 * (size_t)id;
-        const float nrm = norm3_f32_ref(p[0], p[1], p[2], np_[0], np_[1], np_[2]);
-        const float two_w = fmul(2.0f, node_w[id]);
-        const float q = fdiv(nrm, two_w);
-        const float arg = fmul(-1.0f, fmul(q, q));
-        const double w = exp((double)arg);
+        double w;
+        if (KT > 0) {
+            w = wts[KT > 0 ? i : 0];
+        } else {
+            const float nrm = norm3_f32_ref(p[0], p[1], p[2], np_[0], np_[1], np_[2]);
+            const float two_w = fmul(2.0f, node_w[id]);
+            const float q = fdiv(nrm, two_w);
+            const float arg = fmul(-1.0f, fmul(q, q));
+            w = exp((double)arg);
+        }
         const float wf = (float)w;  // `w * dg_dq`: python float is weak -> product in float32
         const float* dqi = node_dq + 8 * (size_t)id;
         for (int c = 0; c < 8; ++c) b[c] = dadd(b[c], (double)fmul(wf, dqi[c]));
@@ -181,13 +199,14 @@ DFB_HDN void dq_blend_ref(const float* p, const int* ids, int k, const float* no
 }
 
 // core/fusion.py:502-520 warp(pos, dqs, locations, normal, m_lw) for a float32 point.
+template <int KT = 0>
 DFB_HDN void warp_ref(const float* p, const float* nrm_in, const int* ids, int k, const float* node_pos,
                       const float* node_dq, const float* node_w, const double* lw, bool has_lw, bool lw_is_f32,
                       double* out_p, double* out_n, float* wi_out, bool closed_form = false) {
     double pd[3] = {(double)p[0], (double)p[1], (double)p[2]};
     double se3[8];
     if (k > 0) {
-        dq_blend_ref(p, ids, k, node_pos, node_dq, node_w, se3, wi_out);
+        dq_blend_ref<KT>(p, ids, k, node_pos, node_dq, node_w, se3, wi_out);
         if (closed_form) dqb_warp_closed(se3, pd, out_p);
         else dqb_warp_ref(se3, false, pd, out_p);
     } else {

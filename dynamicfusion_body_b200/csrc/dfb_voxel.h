@@ -182,6 +182,7 @@ DFB_HD void clamp_update(float& v, float& w, float tdist, float wmax, float scal
 // ---- exact tier: whole-voxel functions --------------------------------------------------------
 // a3 / a2 for one voxel; v,w in/out (float32 storage, float64 arithmetic).  Returns mask bits in
 // *mask, frustum bits in *frus.
+template <int KT = 0>
 DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, const uint16_t* ids16, float* v_io,
                                     float* w_io, int* mask, int* frus) {
     double base[3];
@@ -192,9 +193,14 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
     } else {
         const float p[3] = {(float)x, (float)y, (float)z};
         int ids[8];
-        for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
-        warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
-                 nullptr, nullptr, true);
+        if (KT > 0) {
+#pragma unroll
+            for (int i = 0; i < (KT > 0 ? KT : 1); ++i) ids[i] = ids16[i];
+        } else {
+            for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
+        }
+        warp_ref<KT>(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
+                     nullptr, nullptr, true);
     }
     double v = (double)*v_io, w = (double)*w_io;
     int m = 0, f = 0;

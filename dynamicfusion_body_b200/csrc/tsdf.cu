@@ -169,18 +169,19 @@ __global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, i
     if (threadIdx.x < BRICK_PAIR_WORDS) brick_pairs[(size_t)b * BRICK_PAIR_WORDS + threadIdx.x] = pairs[threadIdx.x];
 }
 
-// one warp per brick (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h WarpCtx)
+// 8 lanes per brick, four bricks per warp (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h)
+constexpr int CLASSIFY_G = 8;
 __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
                                                              const uint8_t* brick_count, const uint32_t* brick_pairs, int nbx, int nby, int nbz,
                                                              uint8_t* cls_out, uint32_t* stream_list, uint32_t* mixed_list) {
     const int nb = nbx * nby * nbz;
-    const int lane = threadIdx.x & 31;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < nb; b += nwarps) {
+    const int gl = threadIdx.x & (CLASSIFY_G - 1);
+    const int ngroups = (gridDim.x * blockDim.x) / CLASSIFY_G;
+    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) / CLASSIFY_G; b < nb; b += ngroups) {
         int bxs, by, bz, fr = 0;
         brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, nby, nbz, bxs, by, bz, &fr, WarpCtx());
-        if (lane == 0) {
+        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, nby, nbz, bxs, by, bz, &fr, GroupCtx<CLASSIFY_G>());
+        if (gl == 0) {
             cls_out[b] = (uint8_t)cls;
             cls_out[nb + b] = (uint8_t)fr;
             if (cls == BRICK_CLS_MIXED) mixed_list[atomicAdd(P.counters + 3, 1u)] = (uint32_t)b;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant
 }
 
 // mode: 0 = work list (or re-scan on overflow), 1 = every voxel
-template <int KMAX>
+template <int KMAX, int KT>
 __global__ void __launch_bounds__(128, 5) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(128, 5) proj_exact_kernel(const __grid_constan
         }
         float v = P.tsdf[i], w = P.weight[i];
         int m, f;
-        voxel_projective_exact(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
+        voxel_projective_exact<KT>(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
         if (m) {
             P.tsdf[i] = v;
             P.weight[i] = w;
@@ -480,7 +481,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
             uint32_t* mixed_list = B.lists + nb;
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
             if (do_classify) {
-                brick_classify_kernel<<<(nb + 3) / 4 < 148 * 32 ? (nb + 3) / 4 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                brick_classify_kernel<<<(nb + 15) / 16 < 148 * 32 ? (nb + 15) / 16 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream && do_mixed) {
@@ -509,8 +510,10 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
         if (mode != DFB_MODE_HYBRID) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
-    if (P.k <= 4) proj_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
-    else proj_exact_kernel<8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    if (P.k == 4 && !P.rigid) proj_exact_kernel<4, 4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else if (P.k == 8 && !P.rigid) proj_exact_kernel<8, 8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else if (P.k <= 4) proj_exact_kernel<4, 0><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else proj_exact_kernel<8, 0><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
     DFB_LAUNCH_CHECK("proj_exact_kernel");
     return DFB_OK;
 }
