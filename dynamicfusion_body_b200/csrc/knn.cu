@@ -8,6 +8,8 @@
 // LDS.128 per node per warp); whenever two of the k+1 best squared distances are closer than the fp32
 // rounding bound the voxel is re-ranked in float64 with the oracle's operation order and the "lower id
 // wins" tie rule.
+#include <stdlib.h>
+
 #include "common.h"
 #include "dfb_math.h"
 
@@ -118,6 +120,145 @@ __global__ void __launch_bounds__(256) knn_volume_kernel(const float* node_pos, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Brick-accelerated exact build.  One CTA per 8x8x8 brick: (1) d_k of the brick centre c by a block-wide selection,
+// (2) candidate nodes = { n : |n - c| <= d_k(c) + 2 * halfdiag } staged in shared memory -- every node among the k
+// nearest of ANY voxel of the brick is in there (d_k(v) <= d_k(c) + h and |n - c| <= |n - v| + h) -- (3) per-voxel
+// ranking over the candidates only, with the same fp32-then-float64 tie discipline as the brute-force kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KB = 8;            // brick edge
+constexpr int KCAP = 1024;       // candidate capacity (16 KB); bricks that overflow fall back to the full node list
+
+template <int KMAX>
+__device__ __noinline__ void knn_exact_f64_list(float qx, float qy, float qz, const float4* cand, int nc, int k, int* out) {
+    double bd[KMAX];
+    int bi[KMAX];
+    for (int j = 0; j < KMAX; ++j) { bd[j] = 1.0e300; bi[j] = 0x7fffffff; }
+    for (int t = 0; t < nc; ++t) {
+        const float4 p = cand[t];
+        const int id = __float_as_int(p.w);
+        const double dx = dfb::dsub((double)qx, (double)p.x), dy = dfb::dsub((double)qy, (double)p.y), dz = dfb::dsub((double)qz, (double)p.z);
+        const double d2 = dfb::dadd(dfb::dadd(dfb::dmul(dx, dx), dfb::dmul(dy, dy)), dfb::dmul(dz, dz));
+        if (!(d2 < bd[k - 1] || (d2 == bd[k - 1] && id < bi[k - 1]))) continue;
+        int j = k - 1;
+        while (j > 0 && (d2 < bd[j - 1] || (d2 == bd[j - 1] && id < bi[j - 1]))) { bd[j] = bd[j - 1]; bi[j] = bi[j - 1]; --j; }
+        bd[j] = d2; bi[j] = id;
+    }
+    for (int j = 0; j < k; ++j) out[j] = bi[j];
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, int n, int k, int sx, int ry, int rz, int x0, int nby, int nbz,
+                                                        uint16_t* knn) {
+    __shared__ float4 cand[KCAP];
+    __shared__ float wtop[4][KMAX];
+    __shared__ int ncand;
+    __shared__ float T2s;
+    const int b = blockIdx.x;
+    const int bz = b % nbz, by = (b / nbz) % nby, bxs = b / (nbz * nby);
+    const int xlo = bxs * KB, ylo = by * KB, zlo = bz * KB;
+    const int xhi = min(xlo + KB, sx) - 1, yhi = min(ylo + KB, ry) - 1, zhi = min(zlo + KB, rz) - 1;
+    const float cx = 0.5f * (xlo + xhi) + (float)x0, cy = 0.5f * (ylo + yhi), cz = 0.5f * (zlo + zhi);
+    const float hx = 0.5f * (xhi - xlo), hy = 0.5f * (yhi - ylo), hz = 0.5f * (zhi - zlo);
+    const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // (1) k smallest squared distances to the centre: per-thread sorted list, warp merge, then 4-way merge
+    float lt[KMAX];
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) lt[j] = 3.0e38f;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const float dx = node_pos[3 * t] - cx, dy = node_pos[3 * t + 1] - cy, dz = node_pos[3 * t + 2] - cz;
+        float v = dx * dx + dy * dy + dz * dz;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j)
+            if (j < k && v < lt[j]) { const float tmp = lt[j]; lt[j] = v; v = tmp; }
+    }
+    for (int j = 0; j < k; ++j) {
+        float m = lt[0];
+        for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const unsigned who = __ballot_sync(0xffffffffu, lt[0] == m);
+        if (lane == __ffs(who) - 1) {   // pop the winner's head
+#pragma unroll
+            for (int q = 0; q < KMAX - 1; ++q) lt[q] = lt[q + 1];
+            lt[KMAX - 1] = 3.0e38f;
+        }
+        if (lane == 0) wtop[wid][j] = m;
+    }
+    if (threadIdx.x == 0) ncand = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float all[4 * KMAX];
+        int m = 0;
+        for (int w = 0; w < 4; ++w)
+            for (int j = 0; j < k; ++j) all[m++] = wtop[w][j];
+        for (int a = 1; a < m; ++a) {   // insertion sort of <= 32 values
+            const float v = all[a];
+            int q = a - 1;
+            while (q >= 0 && all[q] > v) { all[q + 1] = all[q]; --q; }
+            all[q + 1] = v;
+        }
+        const float T = sqrtf(all[k - 1]) * 1.00001f + 2.f * hd + 1e-3f;
+        T2s = T * T * 1.00001f;
+    }
+    __syncthreads();
+    const float T2 = T2s;
+    // (2) candidates
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const float px = node_pos[3 * t], py = node_pos[3 * t + 1], pz = node_pos[3 * t + 2];
+        const float dx = px - cx, dy = py - cy, dz = pz - cz;
+        if (dx * dx + dy * dy + dz * dz <= T2) {
+            const int pos = atomicAdd(&ncand, 1);
+            if (pos < KCAP) cand[pos] = make_float4(px, py, pz, __int_as_float(t));
+        }
+    }
+    __syncthreads();
+    const int nc = ncand;
+    const bool overflow = nc > KCAP;
+    // (3) per-voxel ranking: thread t owns voxels j = 4t .. 4t+3 of the brick (z fastest)
+    for (int q = 0; q < 4; ++q) {
+        const int j = threadIdx.x * 4 + q;
+        const int z = zlo + (j & 7), y = ylo + ((j >> 3) & 7), xs = xlo + (j >> 6);
+        if (xs >= sx || y >= ry || z >= rz) continue;
+        const float qx = (float)(xs + x0), qy = (float)y, qz = (float)z;
+        int out[KMAX];
+        if (overflow) {
+            knn_exact_f64<KMAX>(qx, qy, qz, node_pos, n, k, out);
+        } else {
+            TopK<KMAX> top;
+            top.init();
+            const int kk = (nc > k) ? k : k - 1;
+            for (int t = 0; t < nc; ++t) {
+                const float4 p = cand[t];
+                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
+                top.insert(dx * dx + dy * dy + dz * dz, __float_as_int(p.w), kk);
+            }
+            bool ambiguous = false;
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a)
+                if (a < kk && top.d[a + 1] - top.d[a] <= 4.0e-6f * top.d[a + 1]) ambiguous = true;
+            if (ambiguous) {
+                knn_exact_f64_list<KMAX>(qx, qy, qz, cand, nc, k, out);
+            } else {
+#pragma unroll
+                for (int a = 0; a < KMAX; ++a)
+                    if (a < k) out[a] = top.id[a];
+            }
+        }
+        const size_t i = ((size_t)xs * ry + y) * rz + z;
+        if (KMAX == 4 && k == 4) {
+            uint2 r;
+            r.x = (uint32_t)out[0] | ((uint32_t)out[1] << 16);
+            r.y = (uint32_t)out[2] | ((uint32_t)out[3] << 16);
+            reinterpret_cast<uint2*>(knn)[i] = r;
+        } else {
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a)
+                if (a < k) knn[i * (size_t)k + a] = (uint16_t)out[a];
+        }
+    }
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(256) knn_points_kernel(const float* pts, int64_t m, const float* node_pos, int n, int k,
                                                          int32_t* idx) {
@@ -142,12 +283,23 @@ extern "C" int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, i
     DFB_REQUIRE(n_nodes >= k && n_nodes <= 65535, "n_nodes=%d must be in [k,65535]", n_nodes);
     DFB_REQUIRE(rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad grid / slab");
     DFB_REQUIRE(ry <= 65535 && (x1 - x0) <= 65535, "ry and slab thickness must be <= 65535");
-    const int threads = rz >= 256 ? 256 : ((rz + 31) / 32) * 32;
-    const dim3 grid((rz + threads - 1) / threads, ry, x1 - x0);
     cudaStream_t s = (cudaStream_t)stream;
-    if (k <= 4) knn_volume_kernel<4><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
-    else knn_volume_kernel<8><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
-    DFB_LAUNCH_CHECK("knn_volume_kernel");
+    // DFB_KNN_BRUTE=1 selects the O(voxels * nodes) reference kernel (validation of the brick build)
+    const char* env = getenv("DFB_KNN_BRUTE");
+    const int brute = (env && atoi(env)) ? 1 : 0;
+    const int64_t nbx = (x1 - x0 + KB - 1) / KB, nby = (ry + KB - 1) / KB, nbz = (rz + KB - 1) / KB;
+    if (brute || nbx * nby * nbz >= ((int64_t)1 << 31)) {
+        const int threads = rz >= 256 ? 256 : ((rz + 31) / 32) * 32;
+        const dim3 grid((rz + threads - 1) / threads, ry, x1 - x0);
+        if (k <= 4) knn_volume_kernel<4><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
+        else knn_volume_kernel<8><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
+        DFB_LAUNCH_CHECK("knn_volume_kernel");
+        return DFB_OK;
+    }
+    const unsigned nb = (unsigned)(nbx * nby * nbz);
+    if (k <= 4) knn_brick_kernel<4><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn);
+    else knn_brick_kernel<8><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn);
+    DFB_LAUNCH_CHECK("knn_brick_kernel");
     return DFB_OK;
 }
 

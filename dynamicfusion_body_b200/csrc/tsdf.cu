@@ -8,6 +8,8 @@
 //   near a pixel-rounding boundary, ...) -> appended to a work list with one warp-aggregated atomic.
 // Pass 2 (`*_exact_kernel`): a grid-stride kernel over the work list that evaluates the reference's
 //   own arithmetic (dfb_math.h exact tier).  If the list overflowed it re-scans the volume instead.
+#include <stdlib.h>
+
 #include "common.h"
 #include "dfb_params.h"
 #include "dfb_brick.h"
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, i
 }
 
 // 8 lanes per brick, four bricks per warp (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h)
-constexpr int CLASSIFY_G = 8;
+template <int CLASSIFY_G>
 __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
                                                              const uint8_t* brick_count, const uint32_t* brick_pairs, int nbx, int nby, int nbz,
                                                              uint8_t* cls_out, uint32_t* stream_list, uint32_t* mixed_list) {
@@ -481,7 +483,14 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
             uint32_t* mixed_list = B.lists + nb;
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
             if (do_classify) {
-                brick_classify_kernel<<<(nb + 15) / 16 < 148 * 32 ? (nb + 15) / 16 : 148 * 32, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                static int G = 0;
+                if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : 8; }
+                const int per_cta = 128 / G;
+                const int cgrid = (nb + per_cta - 1) / per_cta < 148 * 32 ? (nb + per_cta - 1) / per_cta : 148 * 32;
+                if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 16) brick_classify_kernel<16><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 32) brick_classify_kernel<32><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else brick_classify_kernel<8><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream && do_mixed) {

@@ -40,6 +40,29 @@ def test_knn_volume_bit_exact(k, n_nodes):
     assert np.array_equal(np.sort(t[tie], 1), np.sort(idx[tie], 1))
 
 
+def test_knn_brick_build_equals_bruteforce_kernel():
+    """The brick-accelerated build (candidate lists per 8^3 brick) against the O(voxels*nodes) kernel on a grid large
+    enough to have far-away bricks with long candidate lists, odd sizes and a slab offset."""
+    import os
+    torch, engine, _ = _engine()
+    from dynamicfusion_body_b200 import synth
+    sc = synth.make_scene(res=160, k=4, n_nodes=1500, seed=1, rows=48, cols=64)
+    res = (160, 150, 141)
+    out = []
+    for brute in ("1", "0"):
+        os.environ["DFB_KNN_BRUTE"] = brute
+        wf = _wf(engine, sc)
+        torch.cuda.synchronize()
+        import time
+        t = time.time()
+        tab = wf.knn_table(res, 5, 133)
+        torch.cuda.synchronize()
+        print("knn build brute=%s: %.1f ms" % (brute, 1e3 * (time.time() - t)))
+        out.append(tab.cpu().numpy())
+    os.environ.pop("DFB_KNN_BRUTE")
+    assert np.array_equal(out[0], out[1])
+
+
 def test_knn_points_matches_oracle():
     torch, engine, _ = _engine()
     from dynamicfusion_body_b200 import synth
