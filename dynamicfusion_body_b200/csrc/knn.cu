@@ -214,37 +214,66 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
     }
     __syncthreads();
     const int nc = ncand;
-    const bool overflow = nc > KCAP;
+    const bool overflow = nc > KCAP;   // block-uniform
     // (3) per-voxel ranking: thread t owns voxels j = 4t .. 4t+3 of the brick (z fastest)
+    TopK<KMAX> top[4];
+    float qx[4], qy[4], qz[4];
+    bool in[4];
+#pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int j = threadIdx.x * 4 + q;
         const int z = zlo + (j & 7), y = ylo + ((j >> 3) & 7), xs = xlo + (j >> 6);
-        if (xs >= sx || y >= ry || z >= rz) continue;
-        const float qx = (float)(xs + x0), qy = (float)y, qz = (float)z;
-        int out[KMAX];
-        if (overflow) {
-            knn_exact_f64<KMAX>(qx, qy, qz, node_pos, n, k, out);
-        } else {
-            TopK<KMAX> top;
-            top.init();
-            const int kk = (nc > k) ? k : k - 1;
-            for (int t = 0; t < nc; ++t) {
-                const float4 p = cand[t];
-                const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-                top.insert(dx * dx + dy * dy + dz * dz, __float_as_int(p.w), kk);
-            }
-            bool ambiguous = false;
+        in[q] = xs < sx && y < ry && z < rz;
+        qx[q] = (float)(xs + x0); qy[q] = (float)y; qz[q] = (float)z;
+        top[q].init();
+    }
+    const int ntot = overflow ? n : nc;
+    const int kk = (ntot > k) ? k : k - 1;
+    if (!overflow) {
+        for (int t = 0; t < nc; ++t) {
+            const float4 p = cand[t];
 #pragma unroll
-            for (int a = 0; a < KMAX; ++a)
-                if (a < kk && top.d[a + 1] - top.d[a] <= 4.0e-6f * top.d[a + 1]) ambiguous = true;
-            if (ambiguous) {
-                knn_exact_f64_list<KMAX>(qx, qy, qz, cand, nc, k, out);
-            } else {
-#pragma unroll
-                for (int a = 0; a < KMAX; ++a)
-                    if (a < k) out[a] = top.id[a];
+            for (int q = 0; q < 4; ++q) {
+                const float dx = qx[q] - p.x, dy = qy[q] - p.y, dz = qz[q] - p.z;
+                top[q].insert(dx * dx + dy * dy + dz * dz, __float_as_int(p.w), kk);
             }
         }
+    } else {
+        // too many candidates for shared memory (bricks far from every node): stream the whole node list through it
+        for (int base = 0; base < n; base += KCAP) {
+            const int cnt = min(KCAP, n - base);
+            __syncthreads();
+            for (int t = threadIdx.x; t < cnt; t += blockDim.x)
+                cand[t] = make_float4(node_pos[3 * (base + t)], node_pos[3 * (base + t) + 1], node_pos[3 * (base + t) + 2], __int_as_float(base + t));
+            __syncthreads();
+            for (int t = 0; t < cnt; ++t) {
+                const float4 p = cand[t];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float dx = qx[q] - p.x, dy = qy[q] - p.y, dz = qz[q] - p.z;
+                    top[q].insert(dx * dx + dy * dy + dz * dz, base + t, kk);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!in[q]) continue;
+        int out[KMAX];
+        bool ambiguous = false;
+#pragma unroll
+        for (int a = 0; a < KMAX; ++a)
+            if (a < kk && top[q].d[a + 1] - top[q].d[a] <= 4.0e-6f * top[q].d[a + 1]) ambiguous = true;
+        if (ambiguous) {
+            if (overflow) knn_exact_f64<KMAX>(qx[q], qy[q], qz[q], node_pos, n, k, out);
+            else knn_exact_f64_list<KMAX>(qx[q], qy[q], qz[q], cand, nc, k, out);
+        } else {
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a)
+                if (a < k) out[a] = top[q].id[a];
+        }
+        const int j = threadIdx.x * 4 + q;
+        const int z = zlo + (j & 7), y = ylo + ((j >> 3) & 7), xs = xlo + (j >> 6);
         const size_t i = ((size_t)xs * ry + y) * rz + z;
         if (KMAX == 4 && k == 4) {
             uint2 r;
