@@ -199,10 +199,11 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
             for (int t = 0; t < 8; ++t) nii += qi[t] * qi[t];
             float Ap[12];
             if (j == i) {
-                // every blend weight must be positive in the reference's float64 exp: farthest voxel of the brick
+                // every blend weight must be a normal float32 in the reference (`w * dg_dq` rounds to float32; weights that
+                // vanish can make the blend fall back to the identity): test the farthest voxel of the brick
                 const float4 r0 = P.node_rec[3 * (size_t)ids[i]];
                 const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
-                if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -900.f) || !(nii > 1e-20f)) { bad = true; continue; }
+                if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f) || !(nii > 1e-20f)) { bad = true; continue; }
                 dq_affine_polar2(qi, qi, Ap);
                 box_extend_affine(Ap, 0.5f / nii, c, h, bx);
             } else {

@@ -101,7 +101,11 @@ DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, fl
         }
     }
     *amin_out = amin * 0.69314718f;
-    if (!(amax > -1000.f)) return false;  // reference exp() near/below its float64 underflow: exact tier
+    // The reference multiplies each weight into the float32 node dq as a float32 (`w * dg_dq`, python float is weak):
+    // weights below the float32 normal range (exp arg < -87.3, i.e. < -126 in log2 units) lose precision or vanish, and
+    // a blend whose weights all vanish falls back to the identity (core/fusion.py:544-549).  The fp32 tier only handles
+    // voxels whose LARGEST weight is a normal float32; the rest is decided by the exact tier.
+    if (!(amax > -125.f)) return false;
     float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {

@@ -164,3 +164,35 @@ def test_brick_culling_is_conservative():
     assert (cv != 255).mean() > 0.3                      # a sizeable part of the volume never needs the per-voxel tier
     assert not (om[0] & (cv == 0)).any()                 # SKIP bricks contain no updated voxel
     assert om[0][(cv != 0) & (cv != 255)].all()          # CLAMP bricks contain only updated voxels
+
+
+@pytest.mark.parametrize("case", ["zero_dq", "w_tiny", "w_small", "q5_lw32"])
+def test_degenerate_blends(case):
+    """Blend weights that vanish in the reference: `w * dg_dq` is a float32 product (numpy weak scalar), so weights below the
+    float32 range drop out and an all-zero blend becomes the identity (core/fusion.py:544-549).  The fp32 tier must hand
+    exactly those voxels to the exact tier."""
+    s = synth.make_scene(res=32, k=4, n_nodes=100, seed=6, rows=64, cols=80, background=True)
+    R = 32
+    t0, w0 = scenes.initial_state(R ** 3, tdist=s.tdist)
+    vox, idx, tie = scenes.oracle_knn((R, R, R), s.node_pos, 4)
+    dq, node_w, lw = s.node_dq, s.node_w, s.lw
+    if case == "zero_dq":
+        dq = np.zeros_like(s.node_dq)
+    elif case == "w_tiny":
+        node_w = 0.05
+    elif case == "w_small":
+        node_w = 0.3
+    else:
+        dq = np.tile(np.array([1, 0, 0, 0, 0, 0.01, 0.01, 0], np.float32), (s.n_nodes, 1))
+        lw = s.lw.astype(np.float32)
+    nw = np.full(s.n_nodes, np.float32(node_w))
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, s.node_pos, dq, nw, lw, s.depths, s.K,
+                                           s.Kinv, s.tdist)
+    wf = hs.HostWarpField(s.node_pos, dq, np.float32(node_w), 4, knn=idx, lw=lw)
+    for mode, bricks in ((0, False), (0, True), (1, False)):
+        hs.set_bricks(idx, 4, (R, R, R), enable=bricks)
+        tv, tw = t0.copy(), w0.copy()
+        mask, frus, cls, nunc = hs.update_projective(tv, tw, (R, R, R), wf, s.depths, s.K, s.Kinv, s.tdist, mode=mode)
+        assert np.array_equal(scenes.bits(mask, 0), om[0]) and np.array_equal(scenes.bits(frus, 0), ofr[0])
+        assert np.abs(tv - ov).max() <= 1e-5 * s.tdist
+    hs.set_bricks(enable=False)
