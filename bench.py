@@ -21,12 +21,10 @@ x-slab of 512^3 voxels of it; rank 0 broadcasts the frame (depth + node transfor
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -156,8 +154,8 @@ def run_ours(args):
     n_frames = 15
     dqs = frame_dqs(sc, n_frames)
     dq_dev = [torch.from_numpy(d).to(dev) for d in dqs]
-    depth_dev = torch.from_numpy(sc.depths).to(dev)
-    depth_host = torch.from_numpy(sc.depths).pin_memory()
+    depth_dev = torch.from_numpy(sc.depths.copy()).to(dev)
+    depth_host = torch.from_numpy(sc.depths.copy()).pin_memory()
     dq_host = [torch.from_numpy(d).pin_memory() for d in dqs]
     fus.build_knn()                                                  # once per graph revision, outside the timed region
     torch.cuda.synchronize()

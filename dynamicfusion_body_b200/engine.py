@@ -29,7 +29,10 @@ def _require_cuda(device):
 def _to_dev(a, dtype, device):
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(a)).to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()            # torch.from_numpy refuses to alias read-only buffers silently
+    return torch.from_numpy(a).to(device=device, dtype=dtype).contiguous()
 
 
 class Workspace:
