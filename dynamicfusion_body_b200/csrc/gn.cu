@@ -304,7 +304,7 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
         }
     }
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0 && part != 0.0) { atomicAdd(S + 1, part); atomicAdd(S + 4, part); }
+    if ((threadIdx.x & 31) == 0 && part != 0.0) { atomicAdd(S + 8, part); atomicAdd(S + 4, part); }
     if (i == 0) S[0] = mu;
 }
 
@@ -313,14 +313,21 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
 __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv, int n,
                                                         int max_iter, double tol2, double* delta, double* r, double* z, double* p, double* q,
                                                         double* S) {
+    // scalars: S[0]=mu  S[4]=rz0  S[5]=converged  S[6]=iterations;  RZ = S+8 (2 slots), PQ = S+10 (2 slots), double-buffered by
+    // iteration parity so that no "rotate the scalars" phase (and its grid-wide barrier) is needed: 3 barriers per iteration.
     cg::grid_group grid = cg::this_grid();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    for (int it = 0; it < max_iter; ++it) {
+    double* RZ = S + 8;
+    double* PQ = S + 10;
+    const double mu = S[0];
+    int it = 0;
+    for (; it < max_iter; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        if (tid == 0) { RZ[nxt] = 0.0; PQ[nxt] = 0.0; }
         // A: q = (H + mu I) p, pq = p.q.  One warp per block row: lane = (column group cgp = lane>>3, row a = lane&7);
         //    the 8 lanes of a group read one 512-byte block row-by-row (coalesced), groups stride over the row's blocks.
-        const double mu = S[0];
         double part = 0.0;
         {
             const int warp = tid >> 5, nwarps = nthreads >> 5;
@@ -344,10 +351,10 @@ __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, 
             }
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && part != 0.0) atomicAdd(S + 2, part);
+        if (lane == 0 && part != 0.0) atomicAdd(PQ + cur, part);
         grid.sync();
         // B: delta += alpha p, r -= alpha q, z = Minv r, rz_new = r.z.  8 lanes per node (lane a owns component a).
-        const double pq = S[2], rz = S[1];
+        const double pq = PQ[cur], rz = RZ[cur];
         const double alpha = (pq != 0.0) ? rz / pq : 0.0;
         part = 0.0;
         {
@@ -376,23 +383,17 @@ __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, 
             }
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && part != 0.0) atomicAdd(S + 3, part);
+        if (lane == 0 && part != 0.0) atomicAdd(RZ + nxt, part);
         grid.sync();
-        // C: p = z + beta p; rotate the scalars
-        const double rzn = S[3];
+        // C: p = z + beta p; convergence is evaluated identically by every thread (no broadcast needed)
+        const double rzn = RZ[nxt];
         const double beta = (rz != 0.0) ? rzn / rz : 0.0;
         for (int t = tid; t < 8 * n; t += nthreads) p[t] = z[t] + beta * p[t];
-        grid.sync();   // every thread has read S[1], S[2], S[3]
-        if (tid == 0) {
-            S[1] = rzn;
-            S[2] = 0.0;
-            S[3] = 0.0;
-            S[6] += 1.0;
-            if (!(rzn > tol2 * S[4])) S[5] = 1.0;
-        }
+        const bool done = !(rzn > tol2 * S[4]);
         grid.sync();
-        if (S[5] != 0.0) break;
+        if (done) { ++it; break; }
     }
+    if (tid == 0) { S[6] = (double)it; S[1] = RZ[it & 1]; }
 }
 
 __global__ void apply_delta_kernel(const double* x, const double* delta, int n8, double* x_new) {
@@ -493,7 +494,7 @@ extern "C" int dfb_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* nod
     return DFB_OK;
 }
 
-extern "C" int64_t dfb_gn_solve_workspace_doubles(int n_nodes) { return (int64_t)n_nodes * (64 + 8 * 4) + 8; }
+extern "C" int64_t dfb_gn_solve_workspace_doubles(int n_nodes) { return (int64_t)n_nodes * (64 + 8 * 4) + 16; }
 
 extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, double lambda,
                             int max_iter, double tol, const double* x, double* x_new, double* delta, double* workspace,
@@ -503,12 +504,12 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
     cudaStream_t s = (cudaStream_t)stream;
     const int n = n_nodes;
     double* S = workspace;
-    double* Minv = workspace + 8;
+    double* Minv = workspace + 16;
     double* r = Minv + (size_t)n * 64;
     double* z = r + (size_t)n * 8;
     double* p = z + (size_t)n * 8;
     double* q = p + (size_t)n * 8;
-    DFB_CUDA(cudaMemsetAsync(S, 0, 8 * sizeof(double), s));
+    DFB_CUDA(cudaMemsetAsync(S, 0, 16 * sizeof(double), s));
     const int nb_node = (n + 127) / 128, nb_row = (8 * n + 127) / 128;
     trace_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, n, S);
     pcg_init_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, g, n, lambda, Minv, delta, r, p, S);

@@ -167,7 +167,7 @@ class Problem:
         return x_new, delta, self._ws[:8]
 
     def gauss_newton(self, x0, lw, rw, max_iter=15, huber=True, f_scale=1.0, lam0=1e-3, lam_min=1e-5, pcg_iters=400,
-                     pcg_tol=1e-9, ftol=1e-9, verbose=False, allreduce=None):
+                     pcg_tol=1e-7, ftol=1e-9, verbose=False, allreduce=None):
         """Damped Gauss-Newton (Levenberg-Marquardt accept/reject).  `allreduce(H, g, cost)` is called after every
         assembly when the residuals are sharded over ranks (dist.py)."""
         x = _to_dev(x0, torch.float64, self.device).reshape(-1).clone()
