@@ -195,6 +195,11 @@ class _FusionBase:
             loc = np.arange(loc.size, dtype=np.int32).reshape(loc.shape)
         return _gn.dq_blend_points(wf, p, loc)[0]
 
+    def write_warp_field(self, path, filename):
+        """core/fusion.py:571-573."""
+        from . import io
+        io.write_warp_field(self._nodes, path, filename, self._itercounter)
+
     # ---- out-of-scope graph / mesh maintenance ---------------------------------------------------
     def marching_cubes(self, tsdf=None, step_size=0):
         raise NotImplementedError("surface extraction is outside the accelerated hot path (SURVEY 8f rank 3)")
