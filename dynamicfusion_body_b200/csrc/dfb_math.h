@@ -148,7 +148,7 @@ DFB_HD float norm3_f32_ref(float ax, float ay, float az, float bx, float by, flo
 // Also returns the Q4 mean node distance (core/fusion.py:180-183) when wi_out != nullptr.
 template <int KT = 0>   // KT > 0: compile-time neighbour count (loop unrolled: the k exp() chains overlap)
 DFB_HDN void dq_blend_ref(const float* p, const int* ids, int k_rt, const float* node_pos, const float* node_dq,
-                          const float* node_w, double* se3, float* wi_out) {
+                          const float* node_w, double* se3, float* wi_out, double* n2_out = nullptr) {
     double b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float wi = 0.f;
     const int k = KT > 0 ? KT : k_rt;
@@ -189,6 +189,19 @@ DFB_HDN void dq_blend_ref(const float* p, const int* ids, int k_rt, const float*
     if (wi_out) *wi_out = wi;
     double s = 0.0;
     for (int c = 0; c < 8; ++c) s = dadd(s, dmul(b[c], b[c]));
+    if (n2_out) {
+        // caller applies the closed form W(b,p)/|b|^2 (== W(b/|b|, p), W being quadratic in the dq): one division instead
+        // of a square root and eight; same value up to float64 rounding order
+        *n2_out = s;
+        if (s == 0.0) {
+            se3[0] = 1.0;
+            for (int c = 1; c < 8; ++c) se3[c] = 0.0;
+            *n2_out = 1.0;
+        } else {
+            for (int c = 0; c < 8; ++c) se3[c] = b[c];
+        }
+        return;
+    }
     const double nrm8 = dsqrt(s);
     if (nrm8 == 0.0) {
         se3[0] = 1.0;
@@ -206,9 +219,17 @@ DFB_HDN void warp_ref(const float* p, const float* nrm_in, const int* ids, int k
     double pd[3] = {(double)p[0], (double)p[1], (double)p[2]};
     double se3[8];
     if (k > 0) {
-        dq_blend_ref<KT>(p, ids, k, node_pos, node_dq, node_w, se3, wi_out);
-        if (closed_form) dqb_warp_closed(se3, pd, out_p);
-        else dqb_warp_ref(se3, false, pd, out_p);
+        if (closed_form && !(nrm_in && out_n)) {
+            double n2;
+            dq_blend_ref<KT>(p, ids, k, node_pos, node_dq, node_w, se3, wi_out, &n2);
+            dqb_warp_closed(se3, pd, out_p);
+            const double inv = 1.0 / n2;
+            out_p[0] *= inv; out_p[1] *= inv; out_p[2] *= inv;
+        } else {
+            dq_blend_ref<KT>(p, ids, k, node_pos, node_dq, node_w, se3, wi_out);
+            if (closed_form) dqb_warp_closed(se3, pd, out_p);
+            else dqb_warp_ref(se3, false, pd, out_p);
+        }
     } else {
         out_p[0] = pd[0]; out_p[1] = pd[1]; out_p[2] = pd[2];
     }

@@ -79,6 +79,24 @@ struct VolParams {
     uint8_t* mask_out;
 };
 
+// fast-tier transcendental / reciprocal: raw MUFU ops on the device (2 ulp; the error margins have > 30 ulp head-room)
+DFB_HD float fast_exp2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+DFB_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    return __frcp_rn(x);
+#else
+    return 1.0f / x;
+#endif
+}
+
 // ---- fast tier: DQB of k nodes in fp32 --------------------------------------------------------
 // rec layout: [pos.xyz, coef][dq0..3][dq4..7], coef = -log2(e)/(4 w^2)  (exp(-(d/2w)^2) = exp2(coef*d^2))
 // Returns false when the fp32 chain cannot be trusted at all (all weights underflow in the reference's
@@ -110,7 +128,7 @@ DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, fl
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
         if (i < k) {
-            const float w = exp2f(a[i] - amax);
+            const float w = fast_exp2(a[i] - amax);
             const float4 r1 = rec[3 * (size_t)ids[i] + 1];
             const float4 r2 = rec[3 * (size_t)ids[i] + 2];
             b[0] += w * r1.x; b[1] += w * r1.y; b[2] += w * r1.z; b[3] += w * r1.w;
@@ -123,7 +141,7 @@ DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, fl
     if (!(n2 > 1e-30f)) return false;
     float o[3];
     dq_apply_unnormalised(b, px, py, pz, o);
-    const float inv = 1.0f / n2;
+    const float inv = fast_rcp(n2);
     out[0] = o[0] * inv; out[1] = o[1] * inv; out[2] = o[2] * inv;
     return true;
 }
@@ -142,10 +160,11 @@ DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const 
     const float apz = fabsf(pz);
     const float ez = e * 4.f;  // |K row 2| is (0,0,1) for a pinhole; 4x head-room for general K
     if (!(apz > 8.f * ez)) return CLS_UNCERTAIN;  // also catches NaN
-    const float inv = 1.0f / pz;
+    const float inv = fast_rcp(pz);
     const float u = pu * inv, v = pv * inv;
-    const float eu = (knorm * e + fabsf(u) * ez) / apz + 4.8e-7f * fabsf(u) + 1e-6f;
-    const float ev = (knorm * e + fabsf(v) * ez) / apz + 4.8e-7f * fabsf(v) + 1e-6f;
+    const float ainv = fabsf(inv) * 1.000001f;
+    const float eu = (knorm * e + fabsf(u) * ez) * ainv + 4.8e-7f * fabsf(u) + 1e-6f;
+    const float ev = (knorm * e + fabsf(v) * ez) * ainv + 4.8e-7f * fabsf(v) + 1e-6f;
     const float umax = (float)(cols - 1), vmax = (float)(rows - 1);
     // certainly outside?
     if (u < -eu || u >= umax + eu || v < -ev || v >= vmax + ev) return CLS_SKIP;
