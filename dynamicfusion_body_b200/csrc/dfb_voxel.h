@@ -175,6 +175,17 @@ DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const 
     const int u0 = (int)rintf(u - eu), u1 = (int)rintf(u + eu);
     const int v0 = (int)rintf(v - ev), v1 = (int)rintf(v + ev);
     const float kz = kin[0] * u + kin[1] * v + kin[2];
+    const float et0 = kin_uv * (eu + ev) + 4.8e-7f * fabsf(kz);
+    const float et1 = e + 2.4e-7f * fabsf(lz);
+    if (u0 == u1 && v0 == v1) {   // the common case: the rounding of (u,v) is unambiguous -> one depth sample, no loops
+        const float z = -depth[(size_t)v0 * cols + u0];
+        if (!(z > 0.f)) return CLS_SKIP;
+        const float tl = z * kz - lz;
+        const float et = fabsf(z) * et0 + et1;
+        if (tl > tdist + et) return CLS_CLAMP;
+        if (tl < -tdist - et) return CLS_SKIP;
+        return CLS_UNCERTAIN;
+    }
     int cls = -1;
     for (int vi = v0; vi <= v1; ++vi) {
         for (int ui = u0; ui <= u1; ++ui) {
@@ -184,7 +195,7 @@ DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const 
                 c = CLS_SKIP;
             } else {
                 const float tl = z * kz - lz;
-                const float et = fabsf(z) * (kin_uv * (eu + ev) + 4.8e-7f * fabsf(kz)) + e + 2.4e-7f * fabsf(lz);
+                const float et = fabsf(z) * et0 + et1;
                 if (tl > tdist + et) c = CLS_CLAMP;
                 else if (tl < -tdist - et) c = CLS_SKIP;
                 else return CLS_UNCERTAIN;
