@@ -40,7 +40,9 @@ class WarpField(C.Structure):
     _fields_ = [("node_rec", C.c_void_p), ("node_pos", C.c_void_p), ("node_dq", C.c_void_p),
                 ("node_w", C.c_void_p), ("n_nodes", C.c_int), ("k", C.c_int), ("knn", C.c_void_p),
                 ("has_lw", C.c_int), ("lw_is_f32", C.c_int), ("lw", C.c_double * 8),
-                ("brick_nodes", C.c_void_p), ("brick_count", C.c_void_p), ("brick_pairs", C.c_void_p)]
+                ("brick_nodes", C.c_void_p), ("brick_count", C.c_void_p), ("brick_pairs", C.c_void_p),
+                ("region_nodes", C.c_void_p), ("region_count", C.c_void_p), ("region_pairs", C.c_void_p),
+                ("region_rec", C.c_void_p)]
 
 
 class Views(C.Structure):
@@ -72,6 +74,8 @@ def declare(lib, prefix="dfb_", device=True):
         "knn_build_volume": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
         "brick_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
         "brick_nodes_build": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp], C.c_int),
+        "region_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
+        "region_build": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp], C.c_int),
         "knn_points": ([vp, C.c_int64, vp, C.c_int, C.c_int, vp, vp], C.c_int),
         "tsdf_update_projective": ([C.POINTER(Volume), C.POINTER(WarpField), C.POINTER(Views), C.c_double, C.c_double,
                                     C.c_int, C.POINTER(Workspace), vp, vp, vp], C.c_int),
@@ -125,7 +129,7 @@ def check(rc):
 
 
 EXPORTS = [
-    "dfb_version", "dfb_last_error", "dfb_nodes_pack", "dfb_knn_build_volume", "dfb_knn_points", "dfb_brick_count", "dfb_brick_nodes_build",
+    "dfb_version", "dfb_last_error", "dfb_nodes_pack", "dfb_knn_build_volume", "dfb_knn_points", "dfb_brick_count", "dfb_brick_nodes_build", "dfb_region_count", "dfb_region_build",
     "dfb_tsdf_update_projective", "dfb_tsdf_update_volume", "dfb_fuse_depth_rigid", "dfb_warp_points", "dfb_dq_blend_points",
     "dfb_gn_residuals", "dfb_gn_residuals_lw", "dfb_gn_pattern_rows", "dfb_gn_pattern_cols", "dfb_gn_normal_eq",
     "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",

@@ -25,6 +25,10 @@ namespace dfb {
 
 constexpr int BRICK_X = 4, BRICK_Y = 4, BRICK_Z = 32;
 constexpr int BRICK_MAXC = 24;        // cached candidate nodes per brick (more -> always MIXED)
+constexpr int REGION_X = 16, REGION_Y = 16, REGION_Z = 32;   // 4 x 4 x 1 bricks
+constexpr int REGION_MAXC = 64;                              // distinct nodes cached per region (more -> region unusable)
+constexpr int REGION_PAIR_WORDS = 65;                        // 64*65/2 = 2080 pair bits
+constexpr int REGION_REC_FLOATS = 16;                        // P_ref (row-major 3x4), D[3], valid
 constexpr int BRICK_PAIR_WORDS = 10;   // bit p = i*(i+1)/2 + j (j <= i) of the 24*25/2 = 300 candidate pairs
 constexpr int BRICK_CLS_MIXED = 0xFF;
 constexpr int BRICK_MAX_RECT = 512;   // depth pixels scanned per brick and view before giving up
@@ -113,6 +117,38 @@ DFB_HD int popc32(uint32_t w) {
 #endif
 }
 
+// ---- regions: one reference affine map + a rigorous deviation bound per 16x16x32 block of voxels ---------------------
+// For every voxel x of region R the warped point is a convex combination of P_ij(x) over the node pairs (i,j) that share
+// x's kNN set, hence  |p'(x) - P_ref(x)|_inf <= D_R := max over the region's co-occurring pairs of sup_{x in R} |P_ij(x) - P_ref(x)|_inf
+// for ANY fixed affine P_ref (the diagonal map of the region's first node is used).  P_ij - P_ref is affine, so the sup over
+// the region box is |dA c + dt| + |dA| h per axis: exact interval arithmetic, no dependency problem.  With (P_ref, D_R) the
+// brick classifier needs one affine map per brick instead of a loop over its candidate pairs.  (D_R is the genuine spread
+// of the pair maps -- up to a few voxels where distant nodes blend -- so it is only used to sort bricks into SKIP / CLAMP /
+// MIXED; voxels of MIXED bricks are still classified by the pointwise DQB tier.)
+// region_pair_bound: contribution of one pair (local indices i >= j into `q`, the region's node dq list) to D_R.
+DFB_HD bool region_pair_bound(const float* qi, const float* qj, bool diag, const float* Pref, const float* c, const float* h, float* dev) {
+    float ni = 0.f, nj = 0.f, ip = 0.f;
+    for (int t = 0; t < 8; ++t) { ni += qi[t] * qi[t]; nj += qj[t] * qj[t]; ip += qi[t] * qj[t]; }
+    if (!(ni > 1e-20f) || !(nj > 1e-20f)) return false;
+    if (!diag && !(ip > 0.25f * sqrtf(ni * nj))) return false;
+    float Ap[12];
+    dq_affine_polar2(qi, qj, Ap);
+    const float inv = 0.5f / ip;
+    for (int r = 0; r < 3; ++r) {
+        float mid = 0.f, rad = 0.f, mag = 0.f;
+        for (int t = 0; t < 3; ++t) {
+            const float d = Ap[4 * r + t] * inv - Pref[4 * r + t];
+            mid += d * c[t];
+            rad += fabsf(d) * h[t];
+            mag += fabsf(Ap[4 * r + t] * inv * c[t]) + fabsf(Pref[4 * r + t] * c[t]);
+        }
+        const float dt = Ap[4 * r + 3] * inv - Pref[4 * r + 3];
+        mag += fabsf(Ap[4 * r + 3] * inv) + fabsf(Pref[4 * r + 3]);
+        dev[r] = fmaxf(dev[r], fabsf(mid + dt) + rad + 4e-6f * (mag + rad) + 1e-6f);
+    }
+    return true;
+}
+
 // Execution context: the same code runs with one warp per brick on the GPU (lanes split the node pairs and the depth
 // pixels, reductions by shuffle) and with a single "lane" on the host (tests/hostshim).
 struct SerialCtx {
@@ -150,7 +186,7 @@ typedef GroupCtx<32> WarpCtx;
 // All control flow is uniform across the lanes of `ctx`.
 template <class Ctx>
 DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, const uint32_t* brick_pairs,
-                           int nby, int nbz, int bxs, int by, int bz, int* frus, const Ctx ctx) {
+                           const float* region_rec, int nby, int nbz, int bxs, int by, int bz, int* frus, const Ctx ctx) {
     *frus = 0;
     const int xlo = P.x0 + bxs * BRICK_X, ylo = by * BRICK_Y, zlo = bz * BRICK_Z;
     const int xhi = (xlo + BRICK_X - 1 < P.x1 - 1) ? xlo + BRICK_X - 1 : P.x1 - 1;
@@ -159,7 +195,24 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
     const float c[3] = {0.5f * (xlo + xhi), 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
     const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
     Box3 bx;
-    if (P.rigid) {
+    bool have_box = false;
+    if (!P.rigid && region_rec) {
+        // O(1) path: the region's reference affine map applied to the brick, inflated by the region's deviation bound
+        const int nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
+        const float* rr = region_rec + (((size_t)(bxs * BRICK_X / REGION_X) * nry + by * BRICK_Y / REGION_Y) * nrz + bz * BRICK_Z / REGION_Z) * REGION_REC_FLOATS;
+        if (rr[15] > 0.5f) {
+            for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
+            box_extend_affine(rr, 1.0f, c, h, bx);
+            for (int r = 0; r < 3; ++r) {
+                const float m = rr[12 + r] + 2e-3f + 2e-6f * P.coord_mag;
+                bx.lo[r] -= m;
+                bx.hi[r] += m;
+            }
+            have_box = true;
+        }
+    }
+    if (have_box) {
+    } else if (P.rigid) {
         for (int r = 0; r < 3; ++r) { bx.lo[r] = c[r] - h[r]; bx.hi[r] = c[r] + h[r]; }
     } else {
         const size_t b = ((size_t)bxs * nby + by) * nbz + bz;

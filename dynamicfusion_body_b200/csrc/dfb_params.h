@@ -128,6 +128,7 @@ inline int build_projective(ProjParams& P, const dfb_volume* vol, const dfb_warp
     else memcpy(A, kIdent34, sizeof(A));
     double mag = fmax(fmax(vol->rx, vol->ry), vol->rz);
     mag = fmax(mag, affine_corner_mag(A, vol->rx, vol->ry, vol->rz));
+    double tnorm = 0.0;
     for (int v = 0; v < views->n_views; ++v) {
         DFB_REQUIRE(views->depth[v], "depth[%d] is null", v);
         P.depth[v] = views->depth[v];
@@ -143,7 +144,9 @@ inline int build_projective(ProjParams& P, const dfb_volume* vol, const dfb_warp
         for (int i = 0; i < 12; ++i) P.vf[v].P[i] = (float)PK[i];
         for (int i = 0; i < 4; ++i) P.vf[v].L[i] = (float)T[8 + i];
         for (int i = 0; i < 12; ++i) P.vf[v].T[i] = (float)T[i];
+        for (int r = 0; r < 3; ++r) tnorm = fmax(tnorm, fabs(T[4 * r]) + fabs(T[4 * r + 1]) + fabs(T[4 * r + 2]));
     }
+    P.tnorm = (float)(tnorm * 1.000001);
     P.coord_mag = (float)(2.0 * mag + 8.0);
     return DFB_OK;
 }

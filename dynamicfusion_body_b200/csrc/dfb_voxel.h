@@ -42,6 +42,7 @@ struct ProjParams {
     float kf[6];     // K rows 0,1 in fp32
     int k_pinhole;   // K row 2 == (0,0,1): u = K00*X/Z + K01*Y/Z + K02 (brick classifier requirement)
     float kin[3];    // Kinv row 2, fp32
+    float tnorm;     // max abs row sum of the view transforms E_v * A_lw (3x3 parts): lpos error per unit p' error
     float knorm;     // max abs row sum of K rows 0,1 (error propagation to pixels)
     float kin_uv;    // |Kinv20| + |Kinv21|
     float coord_mag; // bound on |coordinates| entering the fp32 chain (error scale)

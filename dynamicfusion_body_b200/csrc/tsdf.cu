@@ -171,18 +171,152 @@ __global__ void __launch_bounds__(128) brick_nodes_kernel(const uint16_t* knn, i
     if (threadIdx.x < BRICK_PAIR_WORDS) brick_pairs[(size_t)b * BRICK_PAIR_WORDS + threadIdx.x] = pairs[threadIdx.x];
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// regions (dfb_brick.h): per-graph node/pair sets, per-frame reference map + deviation bound
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) region_build_kernel(const uint16_t* knn, int k, int sx, int ry, int rz, int nry, int nrz,
+                                                           uint16_t* region_nodes, uint8_t* region_count, uint32_t* region_pairs) {
+    __shared__ unsigned int hkey[256];
+    __shared__ int hval[256];
+    __shared__ unsigned int pairs[REGION_PAIR_WORDS];
+    __shared__ int n_out, overflow;
+    const int reg = blockIdx.x;
+    const int rzi = reg % nrz, ryi = (reg / nrz) % nry, rxi = reg / (nrz * nry);
+    for (int t = threadIdx.x; t < 256; t += blockDim.x) { hkey[t] = 0xffffffffu; hval[t] = -1; }
+    for (int t = threadIdx.x; t < REGION_PAIR_WORDS; t += blockDim.x) pairs[t] = 0u;
+    if (threadIdx.x == 0) { n_out = 0; overflow = 0; }
+    __syncthreads();
+    constexpr int NV = REGION_X * REGION_Y * REGION_Z;
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+        const int z = rzi * REGION_Z + (v % REGION_Z), y = ryi * REGION_Y + (v / REGION_Z) % REGION_Y, xs = rxi * REGION_X + v / (REGION_Z * REGION_Y);
+        if (xs >= sx || y >= ry || z >= rz) continue;
+        const size_t i = ((size_t)xs * ry + y) * rz + z;
+        for (int j = 0; j < k; ++j) {
+            const unsigned int id = knn[i * (size_t)k + j];
+            unsigned int slot = (id * 2654435761u) >> 24;
+            int probes = 0;
+            while (true) {
+                const unsigned int old = atomicCAS(&hkey[slot], 0xffffffffu, id);
+                if (old == 0xffffffffu || old == id) break;
+                slot = (slot + 1) & 255;
+                if (++probes >= 256) { overflow = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (hkey[threadIdx.x] != 0xffffffffu) {
+        const int pos = atomicAdd(&n_out, 1);
+        hval[threadIdx.x] = pos;
+        if (pos < REGION_MAXC) region_nodes[(size_t)reg * REGION_MAXC + pos] = (uint16_t)hkey[threadIdx.x];
+    }
+    __syncthreads();
+    const bool ok = !overflow && n_out <= REGION_MAXC;
+    if (threadIdx.x == 0) region_count[reg] = ok ? (uint8_t)n_out : 255;
+    if (!ok) return;
+    for (int v = threadIdx.x; v < NV; v += blockDim.x) {
+        const int z = rzi * REGION_Z + (v % REGION_Z), y = ryi * REGION_Y + (v / REGION_Z) % REGION_Y, xs = rxi * REGION_X + v / (REGION_Z * REGION_Y);
+        if (xs >= sx || y >= ry || z >= rz) continue;
+        const size_t i = ((size_t)xs * ry + y) * rz + z;
+        int loc[DFB_MAX_K];
+        for (int j = 0; j < k; ++j) {
+            const unsigned int id = knn[i * (size_t)k + j];
+            unsigned int slot = (id * 2654435761u) >> 24;
+            while (hkey[slot] != id) slot = (slot + 1) & 255;
+            loc[j] = hval[slot];
+        }
+        for (int a = 0; a < k; ++a)
+            for (int c2 = 0; c2 <= a; ++c2) {
+                const int hi = loc[a] > loc[c2] ? loc[a] : loc[c2], lo = loc[a] > loc[c2] ? loc[c2] : loc[a];
+                const int p = hi * (hi + 1) / 2 + lo;
+                const unsigned int bit = 1u << (p & 31);
+                if (!(pairs[p >> 5] & bit)) atomicOr(&pairs[p >> 5], bit);
+            }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < REGION_PAIR_WORDS; t += blockDim.x) region_pairs[(size_t)reg * REGION_PAIR_WORDS + t] = pairs[t];
+}
+
+__global__ void __launch_bounds__(128) region_bounds_kernel(const float4* node_rec, const uint16_t* region_nodes, const uint8_t* region_count,
+                                                            const uint32_t* region_pairs, int x0, int sx, int ry, int rz, int nry, int nrz,
+                                                            float* region_rec) {
+    __shared__ float q[REGION_MAXC][8];
+    __shared__ float red[4][3];
+    __shared__ int bad_s;
+    const int reg = blockIdx.x;
+    float* out = region_rec + (size_t)reg * REGION_REC_FLOATS;
+    const int cnt = region_count[reg];
+    if (cnt == 0 || cnt > REGION_MAXC) {
+        if (threadIdx.x < REGION_REC_FLOATS) out[threadIdx.x] = 0.f;
+        return;
+    }
+    const int rzi = reg % nrz, ryi = (reg / nrz) % nry, rxi = reg / (nrz * nry);
+    const int xlo = rxi * REGION_X, ylo = ryi * REGION_Y, zlo = rzi * REGION_Z;
+    const int xhi = min(xlo + REGION_X, sx) - 1, yhi = min(ylo + REGION_Y, ry) - 1, zhi = min(zlo + REGION_Z, rz) - 1;
+    const float c[3] = {0.5f * (xlo + xhi) + (float)x0, 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
+    const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
+    if (threadIdx.x == 0) bad_s = 0;
+    __syncthreads();
+    bool bad = false;
+    const uint16_t* ids = region_nodes + (size_t)reg * REGION_MAXC;
+    if (threadIdx.x < cnt) {
+        const int id = ids[threadIdx.x];
+        const float4 r0 = node_rec[3 * (size_t)id], r1 = node_rec[3 * (size_t)id + 1], r2 = node_rec[3 * (size_t)id + 2];
+        q[threadIdx.x][0] = r1.x; q[threadIdx.x][1] = r1.y; q[threadIdx.x][2] = r1.z; q[threadIdx.x][3] = r1.w;
+        q[threadIdx.x][4] = r2.x; q[threadIdx.x][5] = r2.y; q[threadIdx.x][6] = r2.z; q[threadIdx.x][7] = r2.w;
+        // every blend weight of every voxel must be a normal float32 in the reference (see dfb_voxel.h blend_warp_fast)
+        const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
+        if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f)) bad = true;
+    }
+    __syncthreads();
+    float Pref[12], n0 = 0.f;
+    {
+        float q0[8];
+        for (int t = 0; t < 8; ++t) { q0[t] = q[0][t]; n0 += q0[t] * q0[t]; }
+        dq_affine_f(q0, Pref);
+        const float inv = n0 > 1e-20f ? 1.0f / n0 : 0.f;
+        for (int t = 0; t < 12; ++t) Pref[t] *= inv;
+        if (!(n0 > 1e-20f)) bad = true;
+    }
+    float dev[3] = {0.f, 0.f, 0.f};
+    const int npairs = cnt * (cnt + 1) / 2;
+    const uint32_t* pm = region_pairs + (size_t)reg * REGION_PAIR_WORDS;
+    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
+        if (!((pm[p >> 5] >> (p & 31)) & 1u)) continue;
+        int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
+        while (i * (i + 1) / 2 > p) --i;
+        while ((i + 1) * (i + 2) / 2 <= p) ++i;
+        const int j = p - i * (i + 1) / 2;
+        float qi[8], qj[8];
+        for (int t = 0; t < 8; ++t) { qi[t] = q[i][t]; qj[t] = q[j][t]; }
+        if (!region_pair_bound(qi, qj, i == j, Pref, c, h, dev)) bad = true;
+    }
+    if (bad) atomicOr(&bad_s, 1);
+    for (int r = 0; r < 3; ++r)
+        for (int o = 16; o > 0; o >>= 1) dev[r] = fmaxf(dev[r], __shfl_xor_sync(0xffffffffu, dev[r], o));
+    if ((threadIdx.x & 31) == 0)
+        for (int r = 0; r < 3; ++r) red[threadIdx.x >> 5][r] = dev[r];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 0; t < 12; ++t) out[t] = Pref[t];
+        for (int r = 0; r < 3; ++r) out[12 + r] = fmaxf(fmaxf(red[0][r], red[1][r]), fmaxf(red[2][r], red[3][r]));
+        out[15] = bad_s ? 0.f : 1.f;
+    }
+}
+
 // 8 lanes per brick, four bricks per warp (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h)
 template <int CLASSIFY_G>
 __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
-                                                             const uint8_t* brick_count, const uint32_t* brick_pairs, int nbx, int nby, int nbz,
-                                                             uint8_t* cls_out, uint32_t* stream_list, uint32_t* mixed_list) {
+                                                             const uint8_t* brick_count, const uint32_t* brick_pairs, const float* region_rec,
+                                                             int nbx, int nby, int nbz, uint8_t* cls_out, uint32_t* stream_list,
+                                                             uint32_t* mixed_list) {
     const int nb = nbx * nby * nbz;
     const int gl = threadIdx.x & (CLASSIFY_G - 1);
     const int ngroups = (gridDim.x * blockDim.x) / CLASSIFY_G;
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) / CLASSIFY_G; b < nb; b += ngroups) {
         int bxs, by, bz, fr = 0;
         brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, nby, nbz, bxs, by, bz, &fr, GroupCtx<CLASSIFY_G>());
+        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, region_rec, nby, nbz, bxs, by, bz, &fr, GroupCtx<CLASSIFY_G>());
         if (gl == 0) {
             cls_out[b] = (uint8_t)cls;
             cls_out[nb + b] = (uint8_t)fr;
@@ -462,6 +596,10 @@ struct BrickArgs {
     const uint16_t* nodes;
     const uint8_t* count;
     const uint32_t* pairs;
+    const uint16_t* rnodes;
+    const uint8_t* rcount;
+    const uint32_t* rpairs;
+    float* rrec;
     uint8_t* cls;
     uint32_t* lists;
 };
@@ -479,18 +617,28 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
         if (bricks) {
             const int nbx = (P.x1 - P.x0 + BRICK_X - 1) / BRICK_X, nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
             const int nb = nbx * nby * nbz;
+            const float* rrec = nullptr;
+            if (!P.rigid && B.rnodes && B.rcount && B.rpairs && B.rrec) {
+                rrec = B.rrec;
+                if (do_classify) {
+                    const int nrx = (P.x1 - P.x0 + REGION_X - 1) / REGION_X, nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
+                    region_bounds_kernel<<<nrx * nry * nrz, 128, 0, s>>>(P.node_rec, B.rnodes, B.rcount, B.rpairs, P.x0, P.x1 - P.x0, P.ry, P.rz,
+                                                                         nry, nrz, B.rrec);
+                    DFB_LAUNCH_CHECK("region_bounds_kernel");
+                }
+            }
             uint32_t* stream_list = B.lists;
             uint32_t* mixed_list = B.lists + nb;
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
             if (do_classify) {
                 static int G = 0;
-                if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : 8; }
+                if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : (rrec ? 4 : 8); }
                 const int per_cta = 128 / G;
                 const int cgrid = (nb + per_cta - 1) / per_cta < 148 * 32 ? (nb + per_cta - 1) / per_cta : 148 * 32;
-                if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (G == 16) brick_classify_kernel<16><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (G == 32) brick_classify_kernel<32><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else brick_classify_kernel<8><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 16) brick_classify_kernel<16><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 32) brick_classify_kernel<32><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else brick_classify_kernel<8><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream && do_mixed) {
@@ -546,7 +694,8 @@ extern "C" int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpf
                                           uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream) {
     ProjParams P;
     if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
-    const BrickArgs B = {wf->brick_nodes, wf->brick_count, wf->brick_pairs, ws->brick_cls, ws->brick_lists};
+    const BrickArgs B = {wf->brick_nodes, wf->brick_count, wf->brick_pairs, wf->region_nodes, wf->region_count, wf->region_pairs, wf->region_rec,
+                         ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
@@ -559,7 +708,7 @@ extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const f
     if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
                             mask_out, frustum_out))
         return r;
-    const BrickArgs B = {nullptr, nullptr, nullptr, ws->brick_cls, ws->brick_lists};
+    const BrickArgs B = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
@@ -624,5 +773,22 @@ extern "C" int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry,
     DFB_REQUIRE(nb < ((int64_t)1 << 31), "too many bricks");
     brick_nodes_kernel<<<(unsigned)nb, 128, 0, (cudaStream_t)stream>>>(knn, k, sx, ry, rz, nby, nbz, brick_nodes, brick_count, brick_pairs);
     DFB_LAUNCH_CHECK("brick_nodes_kernel");
+    return DFB_OK;
+}
+
+extern "C" int64_t dfb_region_count(int sx, int ry, int rz) {
+    return (int64_t)((sx + REGION_X - 1) / REGION_X) * ((ry + REGION_Y - 1) / REGION_Y) * ((rz + REGION_Z - 1) / REGION_Z);
+}
+
+extern "C" int dfb_region_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* region_nodes,
+                                uint8_t* region_count, uint32_t* region_pairs, dfb_stream_t stream) {
+    DFB_REQUIRE(knn && region_nodes && region_count && region_pairs, "null pointer");
+    DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K && rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad arguments");
+    const int sx = x1 - x0;
+    const int nry = (ry + REGION_Y - 1) / REGION_Y, nrz = (rz + REGION_Z - 1) / REGION_Z;
+    const int64_t nr = dfb_region_count(sx, ry, rz);
+    DFB_REQUIRE(nr < ((int64_t)1 << 31), "too many regions");
+    region_build_kernel<<<(unsigned)nr, 256, 0, (cudaStream_t)stream>>>(knn, k, sx, ry, rz, nry, nrz, region_nodes, region_count, region_pairs);
+    DFB_LAUNCH_CHECK("region_build_kernel");
     return DFB_OK;
 }

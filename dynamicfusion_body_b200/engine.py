@@ -12,6 +12,9 @@ import torch
 from . import _capi
 
 
+USE_REGIONS = True   # region reference maps (dfb_brick.h); False = per-brick pairwise hull + per-voxel DQB tier (validation)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -152,7 +155,14 @@ class DeviceWarpField:
             pairs = torch.zeros((nb, 10), dtype=torch.int32, device=self.device)
             _capi.check(_capi.lib().dfb_brick_nodes_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(nodes), _ptr(count),
                                                           _ptr(pairs), _stream()))
-            t = (nodes, count, pairs)
+            nr = int(_capi.lib().dfb_region_count(x1 - x0, res[1], res[2]))
+            rnodes = torch.zeros((nr, 64), dtype=torch.int16, device=self.device)
+            rcount = torch.zeros(nr, dtype=torch.uint8, device=self.device)
+            rpairs = torch.zeros((nr, 65), dtype=torch.int32, device=self.device)
+            rrec = torch.zeros((nr, 16), dtype=torch.float32, device=self.device)
+            _capi.check(_capi.lib().dfb_region_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(rnodes), _ptr(rcount),
+                                                     _ptr(rpairs), _stream()))
+            t = (nodes, count, pairs, rnodes, rcount, rpairs, rrec)
             self._bricks[key] = t
         return t
 
@@ -169,6 +179,11 @@ class DeviceWarpField:
             s.brick_nodes = bricks[0].data_ptr()
             s.brick_count = bricks[1].data_ptr()
             s.brick_pairs = bricks[2].data_ptr()
+            if USE_REGIONS:
+                s.region_nodes = bricks[3].data_ptr()
+                s.region_count = bricks[4].data_ptr()
+                s.region_pairs = bricks[5].data_ptr()
+                s.region_rec = bricks[6].data_ptr()
         k = self.k if k is None else k
         if k > 0:
             s.node_rec = self.node_rec.data_ptr()

@@ -66,6 +66,11 @@ typedef struct dfb_warpfield {
     const uint16_t* brick_nodes; /* [n_bricks][24] */
     const uint8_t* brick_count;  /* [n_bricks], 255 = more than 24 */
     const uint32_t* brick_pairs; /* [n_bricks][10]: bit i*(i+1)/2+j set when candidates i>=j share a voxel's kNN set (NULL = all pairs) */
+    /* optional (NULL = per-brick pairwise hull + per-voxel DQB tier): 16x16x32-voxel regions from dfb_region_build */
+    const uint16_t* region_nodes; /* [n_regions][64] */
+    const uint8_t* region_count;  /* [n_regions], 255 = more than 64 distinct nodes */
+    const uint32_t* region_pairs; /* [n_regions][65] pair bit masks */
+    float* region_rec;            /* [n_regions][16] scratch: reference map + deviation bound, rewritten by every update call */
 } dfb_warpfield;
 
 typedef struct dfb_views {
@@ -105,6 +110,10 @@ int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int 
 int64_t dfb_brick_count(int slab_x, int ry, int rz);
 int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* brick_nodes,
                           uint8_t* brick_count, uint32_t* brick_pairs, dfb_stream_t stream);
+/* Regions (16x16x32 voxels): distinct nodes and co-occurring node pairs of each region (once per graph revision). */
+int64_t dfb_region_count(int slab_x, int ry, int rz);
+int dfb_region_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* region_nodes,
+                     uint8_t* region_count, uint32_t* region_pairs, dfb_stream_t stream);
 /* KDTree.query(vert, k) for arbitrary float32 points (core/fusion.py:122,232). */
 int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
                    dfb_stream_t stream);

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <algorithm>
+#include <array>
 #include <vector>
 
 #include "../../dynamicfusion_body_b200/csrc/dfb_params.h"
@@ -79,8 +80,73 @@ static const uint16_t* g_brick_nodes = nullptr;
 static const uint8_t* g_brick_count = nullptr;
 static const uint32_t* g_brick_pairs = nullptr;
 static uint8_t* g_brick_cls_vox = nullptr;
-extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox) {
-    g_brick_nodes = nodes; g_brick_count = count; g_brick_pairs = pairs; g_brick_cls_vox = cls_vox;
+static int g_use_regions = 0;
+static float g_region_dmax = 0.f;   // largest deviation bound among valid regions of the last call (diagnostic)
+static float g_region_valid = 0.f;  // fraction of valid regions
+extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox, int use_regions) {
+    g_brick_nodes = nodes; g_brick_count = count; g_brick_pairs = pairs; g_brick_cls_vox = cls_vox; g_use_regions = use_regions;
+}
+extern "C" float hs_region_dmax() { return g_region_dmax; }
+extern "C" float hs_region_valid() { return g_region_valid; }
+
+// host mirror of region_build_kernel + region_bounds_kernel (tsdf.cu)
+static std::vector<float> build_region_records(const ProjParams& P) {
+    const int sx = P.x1 - P.x0;
+    const int nrx = (sx + REGION_X - 1) / REGION_X, nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
+    std::vector<float> rec((size_t)nrx * nry * nrz * REGION_REC_FLOATS, 0.f);
+    g_region_dmax = 0.f;
+    int nvalid = 0;
+    for (int rx = 0; rx < nrx; ++rx)
+        for (int ry_ = 0; ry_ < nry; ++ry_)
+            for (int rz_ = 0; rz_ < nrz; ++rz_) {
+                float* out = rec.data() + (((size_t)rx * nry + ry_) * nrz + rz_) * REGION_REC_FLOATS;
+                const int xlo = rx * REGION_X, ylo = ry_ * REGION_Y, zlo = rz_ * REGION_Z;
+                const int xhi = std::min(xlo + REGION_X, sx) - 1, yhi = std::min(ylo + REGION_Y, P.ry) - 1, zhi = std::min(zlo + REGION_Z, P.rz) - 1;
+                std::vector<int> nodes;
+                std::vector<std::pair<int, int>> pairs;
+                for (int x = xlo; x <= xhi; ++x)
+                    for (int y = ylo; y <= yhi; ++y)
+                        for (int z = zlo; z <= zhi; ++z) {
+                            const size_t i = ((size_t)x * P.ry + y) * P.rz + z;
+                            int loc[DFB_MAX_K];
+                            for (int j = 0; j < P.k; ++j) {
+                                const int id = P.knn[i * P.k + j];
+                                auto it = std::find(nodes.begin(), nodes.end(), id);
+                                if (it == nodes.end()) { nodes.push_back(id); loc[j] = (int)nodes.size() - 1; }
+                                else loc[j] = (int)(it - nodes.begin());
+                            }
+                            for (int a = 0; a < P.k; ++a)
+                                for (int c2 = 0; c2 <= a; ++c2) {
+                                    const std::pair<int, int> pr(std::max(loc[a], loc[c2]), std::min(loc[a], loc[c2]));
+                                    if (std::find(pairs.begin(), pairs.end(), pr) == pairs.end()) pairs.push_back(pr);
+                                }
+                        }
+                if (nodes.empty() || nodes.size() > (size_t)REGION_MAXC) continue;
+                const float c[3] = {0.5f * (xlo + xhi) + (float)P.x0, 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
+                const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
+                bool bad = false;
+                std::vector<std::array<float, 8>> q(nodes.size());
+                for (size_t t = 0; t < nodes.size(); ++t) {
+                    const float4 r0 = P.node_rec[3 * (size_t)nodes[t]], r1 = P.node_rec[3 * (size_t)nodes[t] + 1], r2 = P.node_rec[3 * (size_t)nodes[t] + 2];
+                    q[t] = {r1.x, r1.y, r1.z, r1.w, r2.x, r2.y, r2.z, r2.w};
+                    const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
+                    if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f)) bad = true;
+                }
+                float Pref[12], n0 = 0.f;
+                for (int t = 0; t < 8; ++t) n0 += q[0][t] * q[0][t];
+                dq_affine_f(q[0].data(), Pref);
+                if (!(n0 > 1e-20f)) bad = true;
+                for (int t = 0; t < 12; ++t) Pref[t] *= (n0 > 1e-20f ? 1.0f / n0 : 0.f);
+                float dev[3] = {0.f, 0.f, 0.f};
+                for (auto& pr : pairs)
+                    if (!region_pair_bound(q[pr.first].data(), q[pr.second].data(), pr.first == pr.second, Pref, c, h, dev)) bad = true;
+                for (int t = 0; t < 12; ++t) out[t] = Pref[t];
+                for (int r = 0; r < 3; ++r) out[12 + r] = dev[r];
+                out[15] = bad ? 0.f : 1.f;
+                if (!bad) { ++nvalid; g_region_dmax = std::max(g_region_dmax, std::max(dev[0], std::max(dev[1], dev[2]))); }
+            }
+    g_region_valid = (float)nvalid / (float)((size_t)nrx * nry * nrz);
+    return rec;
 }
 
 template <int KMAX>
@@ -90,6 +156,9 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
     const bool bricks = mode == DFB_MODE_HYBRID && (P.rigid || (g_brick_nodes && g_brick_count)) && g_brick_cls_vox;
     const int nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
     std::vector<int> brick_cache((size_t)((P.x1 - P.x0 + BRICK_X - 1) / BRICK_X) * nby * nbz, -1);
+    std::vector<float> region_rec;
+    if (bricks && !P.rigid && g_use_regions) region_rec = build_region_records(P);
+    const float* rrec = region_rec.empty() ? nullptr : region_rec.data();
     for (int xs = 0; xs < P.x1 - P.x0; ++xs)
         for (int y = 0; y < P.ry; ++y)
             for (int z = 0; z < P.rz; ++z) {
@@ -98,7 +167,7 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                     const size_t bid = ((size_t)(xs / BRICK_X) * nby + y / BRICK_Y) * nbz + z / BRICK_Z;
                     if (brick_cache[bid] < 0) {
                         int fr0 = 0;
-                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, g_brick_pairs, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
+                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, g_brick_pairs, rrec, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
                         brick_cache[bid] = c0 | (fr0 << 8);
                     }
                     const int bc = brick_cache[bid] & 0xff, fr = brick_cache[bid] >> 8;

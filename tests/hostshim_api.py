@@ -43,14 +43,16 @@ def lib():
     return _lib
 
 
-def set_bricks(knn=None, k=4, slab_shape=None, enable=True, use_pairs=True):
+def set_bricks(knn=None, k=4, slab_shape=None, enable=True, use_pairs=True, regions=True):
     """Enable/disable the brick-culling emulation.  Returns the per-voxel brick-class array (0xFF = mixed) that the next
     update_projective / fuse_depth_rigid call fills."""
     L = lib()
     L.hs_brick_nodes_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.hs_set_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hs_set_bricks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.hs_region_dmax.restype = C.c_float
+    L.hs_region_valid.restype = C.c_float
     if not enable:
-        L.hs_set_bricks(None, None, None, None)
+        L.hs_set_bricks(None, None, None, None, 0)
         return None
     sx, ry, rz = slab_shape
     nb = ((sx + 3) // 4) * ((ry + 3) // 4) * ((rz + 31) // 32)
@@ -60,12 +62,17 @@ def set_bricks(knn=None, k=4, slab_shape=None, enable=True, use_pairs=True):
         knn = np.ascontiguousarray(knn, dtype=np.uint16)
         nodes = np.zeros((nb, 24), np.uint16); count = np.zeros(nb, np.uint8); pairs = np.zeros((nb, 10), np.uint32)
         L.hs_brick_nodes_build(_p(knn), k, sx, ry, rz, _p(nodes), _p(count), _p(pairs))
-        L.hs_set_bricks(_p(nodes), _p(count), _p(pairs) if use_pairs else None, _p(cls_vox))
+        L.hs_set_bricks(_p(nodes), _p(count), _p(pairs) if use_pairs else None, _p(cls_vox), 1 if regions else 0)
         keep += [knn, nodes, count, pairs]
     else:
-        L.hs_set_bricks(None, None, None, _p(cls_vox))
+        L.hs_set_bricks(None, None, None, _p(cls_vox), 0)
     set_bricks._keep = keep
     return cls_vox
+
+
+def region_stats():
+    """(largest deviation bound among valid regions, fraction of valid regions) of the last region-enabled call."""
+    return float(lib().hs_region_dmax()), float(lib().hs_region_valid())
 
 
 def _p(a):
