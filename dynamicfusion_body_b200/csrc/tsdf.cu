@@ -271,8 +271,12 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const float4* node_r
     __syncthreads();
     float Pref[12], n0 = 0.f;
     {
+        // reference map = diagonal map of the region's lowest node id (the cached list order depends on atomics)
+        int ref = 0;
+        for (int t = 1; t < cnt; ++t)
+            if (ids[t] < ids[ref]) ref = t;
         float q0[8];
-        for (int t = 0; t < 8; ++t) { q0[t] = q[0][t]; n0 += q0[t] * q0[t]; }
+        for (int t = 0; t < 8; ++t) { q0[t] = q[ref][t]; n0 += q0[t] * q0[t]; }
         dq_affine_f(q0, Pref);
         const float inv = n0 > 1e-20f ? 1.0f / n0 : 0.f;
         for (int t = 0; t < 12; ++t) Pref[t] *= inv;
@@ -635,7 +639,9 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : (rrec ? 4 : 8); }
                 const int per_cta = 128 / G;
                 const int cgrid = (nb + per_cta - 1) / per_cta < 148 * 32 ? (nb + per_cta - 1) / per_cta : 148 * 32;
-                if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                if (G == 1) brick_classify_kernel<1><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 2) brick_classify_kernel<2><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 else if (G == 16) brick_classify_kernel<16><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 else if (G == 32) brick_classify_kernel<32><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 else brick_classify_kernel<8><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);

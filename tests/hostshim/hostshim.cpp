@@ -133,8 +133,9 @@ static std::vector<float> build_region_records(const ProjParams& P) {
                     if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f)) bad = true;
                 }
                 float Pref[12], n0 = 0.f;
-                for (int t = 0; t < 8; ++t) n0 += q[0][t] * q[0][t];
-                dq_affine_f(q[0].data(), Pref);
+                const size_t ref = (size_t)(std::min_element(nodes.begin(), nodes.end()) - nodes.begin());
+                for (int t = 0; t < 8; ++t) n0 += q[ref][t] * q[ref][t];
+                dq_affine_f(q[ref].data(), Pref);
                 if (!(n0 > 1e-20f)) bad = true;
                 for (int t = 0; t < 12; ++t) Pref[t] *= (n0 > 1e-20f ? 1.0f / n0 : 0.f);
                 float dev[3] = {0.f, 0.f, 0.f};
