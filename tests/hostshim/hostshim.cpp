@@ -81,6 +81,8 @@ static const uint8_t* g_brick_count = nullptr;
 static const uint32_t* g_brick_pairs = nullptr;
 static uint8_t* g_brick_cls_vox = nullptr;
 static int g_use_regions = 0;
+static long g_seg_resolved = 0;
+extern "C" long hs_seg_resolved() { long v = g_seg_resolved; g_seg_resolved = 0; return v; }
 static float g_region_dmax = 0.f;   // largest deviation bound among valid regions of the last call (diagnostic)
 static float g_region_valid = 0.f;  // fraction of valid regions
 extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox, int use_regions) {
@@ -193,6 +195,27 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                 uint16_t ids[KMAX] = {0};
                 for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
                 int m = 0, f = 0, cls = CLS_UNCERTAIN;
+                if (mode == DFB_MODE_HYBRID && bricks && rrec) {
+                    // the thread's 4-voxel run (z aligned to 4) settled by the region bound, as mixed_brick does
+                    const int nry_ = (P.ry + REGION_Y - 1) / REGION_Y, nrz_ = (P.rz + REGION_Z - 1) / REGION_Z;
+                    const float* rr = rrec + (((size_t)(xs / REGION_X) * nry_ + y / REGION_Y) * nrz_ + z / REGION_Z) * REGION_REC_FLOATS;
+                    if (rr[15] > 0.5f) {
+                        const int z0 = z & ~3, z1 = std::min(z0 + 3, P.rz - 1);
+                        int fr = 0;
+                        const int sm = segment_classify(P, rr, xs + P.x0, y, z0, z1, &fr, SerialCtx());
+                        if (sm != BRICK_CLS_MIXED) {
+                            float v = P.tsdf[i], w = P.weight[i];
+                            for (int vi = 0; vi < P.n_views; ++vi)
+                                if (sm & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, (float)P.scale);
+                            if (sm) { P.tsdf[i] = v; P.weight[i] = w; }
+                            if (P.mask_out) P.mask_out[i] = (uint8_t)sm;
+                            if (P.frustum_out) P.frustum_out[i] = (uint8_t)fr;
+                            if (cls_out) cls_out[i] = sm ? CLS_CLAMP : CLS_SKIP;
+                            ++g_seg_resolved;
+                            continue;
+                        }
+                    }
+                }
                 if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
                 if (cls_out) cls_out[i] = (uint8_t)cls;
                 float v = P.tsdf[i], w = P.weight[i];
