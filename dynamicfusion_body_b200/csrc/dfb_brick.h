@@ -346,12 +346,14 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
     return box_views_classify(P, bx, frus, ctx);
 }
 
-// Region-bound classification of an arbitrary run of voxels (x, y, z0..z1) -- used by the per-voxel kernel to settle a
-// thread's 4-voxel segment with one affine map before falling back to the pointwise DQB tier.  rr: valid region record.
+// Region-bound classification of an arbitrary box of voxels [xlo..xhi] x [ylo..yhi] x [zlo..zhi] (global indices) -- used by
+// the per-voxel kernel to settle a warp's 4x4x8 sub-brick with one affine map before falling back to the pointwise DQB
+// tier.  rr: valid region record.
 template <class Ctx>
-DFB_HDN int segment_classify(const ProjParams& P, const float* rr, int x, int y, int z0, int z1, int* frus, const Ctx ctx) {
-    const float c[3] = {(float)x, (float)y, 0.5f * (z0 + z1)};
-    const float h[3] = {0.f, 0.f, 0.5f * (z1 - z0)};
+DFB_HDN int subbox_classify(const ProjParams& P, const float* rr, int xlo, int xhi, int ylo, int yhi, int zlo, int zhi, int* frus,
+                            const Ctx ctx) {
+    const float c[3] = {0.5f * (xlo + xhi), 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
+    const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
     Box3 bx;
     for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
     box_extend_affine(rr, 1.0f, c, h, bx);
