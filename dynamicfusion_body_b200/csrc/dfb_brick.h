@@ -181,70 +181,6 @@ struct GroupCtx {
 typedef GroupCtx<32> WarpCtx;
 #endif
 
-// Classify a box of warped points p' (bounds bx) against every view: push it through lw / extrinsics / intrinsics with
-// interval arithmetic, scan the depth image over the pixel rectangle.  Returns BRICK_CLS_MIXED or the per-view CLAMP mask.
-template <class Ctx>
-DFB_HDN int box_views_classify(const ProjParams& P, const Box3& bx, int* frus, const Ctx ctx) {
-    const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
-    const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
-    int mask = 0, fr = 0;
-    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
-    for (int v = 0; v < P.n_views; ++v) {
-        const ViewFast& V = P.vf[v];
-        // camera-space box, then a = X/Z, b = Y/Z, (u,v) = K[0:2] * (a, b, 1): dividing X by Z (not K*lpos rows by each
-        // other) keeps the interval dependency problem away from the principal-point term
-        float xl, xh, yl, yh, lzl, lzh;
-        row_interval(V.T, c3, h3, xl, xh);
-        row_interval(V.T + 4, c3, h3, yl, yh);
-        row_interval(V.T + 8, c3, h3, lzl, lzh);
-        if (!P.k_pinhole) return DFB_MIXED(9);
-        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
-        float al, ah, bl, bh;
-        div_interval(xl, xh, lzl, lzh, al, ah);
-        div_interval(yl, yh, lzl, lzh, bl, bh);
-        float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-        float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-        float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
-        float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
-        {
-            const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
-            ul -= su; uh += su; vl -= sv; vh += sv;
-        }
-        const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
-        if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
-        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
-        fr |= 1 << v;
-        const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
-        const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
-        if (npx > BRICK_MAX_RECT) return DFB_MIXED(5);
-        float zmin = 3.0e38f, zmax = -3.0e38f;
-        bool nan = false;
-        for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
-            const int iv = iv0 + t / nu, iu = iu0 + t % nu;
-            const float z = -P.depth[v][(size_t)iv * P.cols + iu];
-            nan |= !(z == z);
-            zmin = fminf(zmin, z);
-            zmax = fmaxf(zmax, z);
-        }
-        if (ctx.any(nan)) return DFB_MIXED(6);
-        zmin = ctx.rmin(zmin);
-        zmax = ctx.rmax(zmax);
-        // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
-        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
-        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
-        const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
-        const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
-        if (!(kzl > 0.f)) return DFB_MIXED(7);
-        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
-        const float zs = 1e-6f * fabsf(zmax) * kzh;
-        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
-        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
-        return DFB_MIXED(8);
-    }
-    *frus = fr;
-    return mask;
-}
-
 // Classify brick (bxs,by,bz) (bxs slab-local).  Returns BRICK_CLS_MIXED or the per-view CLAMP bit mask (0 = SKIP);
 // *frus = per-view "certainly inside the image" bits (meaningful when the result is not MIXED).
 // All control flow is uniform across the lanes of `ctx`.
@@ -343,26 +279,64 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
             bx.hi[r] = ctx.rmax(bx.hi[r]) + m;
         }
     }
-    return box_views_classify(P, bx, frus, ctx);
-}
-
-// Region-bound classification of an arbitrary box of voxels [xlo..xhi] x [ylo..yhi] x [zlo..zhi] (global indices) -- used by
-// the per-voxel kernel to settle a warp's 4x4x8 sub-brick with one affine map before falling back to the pointwise DQB
-// tier.  rr: valid region record.
-template <class Ctx>
-DFB_HDN int subbox_classify(const ProjParams& P, const float* rr, int xlo, int xhi, int ylo, int yhi, int zlo, int zhi, int* frus,
-                            const Ctx ctx) {
-    const float c[3] = {0.5f * (xlo + xhi), 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
-    const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
-    Box3 bx;
-    for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
-    box_extend_affine(rr, 1.0f, c, h, bx);
-    for (int r = 0; r < 3; ++r) {
-        const float m = rr[12 + r] + 2e-3f + 2e-6f * P.coord_mag;
-        bx.lo[r] -= m;
-        bx.hi[r] += m;
+    const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
+    const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
+    int mask = 0, fr = 0;
+    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
+    for (int v = 0; v < P.n_views; ++v) {
+        const ViewFast& V = P.vf[v];
+        // camera-space box, then a = X/Z, b = Y/Z, (u,v) = K[0:2] * (a, b, 1): dividing X by Z (not K*lpos rows by each
+        // other) keeps the interval dependency problem away from the principal-point term
+        float xl, xh, yl, yh, lzl, lzh;
+        row_interval(V.T, c3, h3, xl, xh);
+        row_interval(V.T + 4, c3, h3, yl, yh);
+        row_interval(V.T + 8, c3, h3, lzl, lzh);
+        if (!P.k_pinhole) return DFB_MIXED(9);
+        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
+        float al, ah, bl, bh;
+        div_interval(xl, xh, lzl, lzh, al, ah);
+        div_interval(yl, yh, lzl, lzh, bl, bh);
+        float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        {
+            const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
+            ul -= su; uh += su; vl -= sv; vh += sv;
+        }
+        const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
+        if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
+        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
+        fr |= 1 << v;
+        const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
+        const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
+        if (npx > BRICK_MAX_RECT) return DFB_MIXED(5);
+        float zmin = 3.0e38f, zmax = -3.0e38f;
+        bool nan = false;
+        for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
+            const int iv = iv0 + t / nu, iu = iu0 + t % nu;
+            const float z = -P.depth[v][(size_t)iv * P.cols + iu];
+            nan |= !(z == z);
+            zmin = fminf(zmin, z);
+            zmax = fmaxf(zmax, z);
+        }
+        if (ctx.any(nan)) return DFB_MIXED(6);
+        zmin = ctx.rmin(zmin);
+        zmax = ctx.rmax(zmax);
+        // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
+        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
+        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
+        const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
+        const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+        if (!(kzl > 0.f)) return DFB_MIXED(7);
+        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
+        const float zs = 1e-6f * fabsf(zmax) * kzh;
+        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
+        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
+        return DFB_MIXED(8);
     }
-    return box_views_classify(P, bx, frus, ctx);
+    *frus = fr;
+    return mask;
 }
 
 }  // namespace dfb

@@ -371,48 +371,12 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
 }
 
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
-// MIXED bricks.  Warp w of the CTA owns the z-quarter [8w, 8w+8) of the brick (4x4x8 voxels, 4 consecutive z per lane).
-// The warp first tries to settle its whole sub-brick with the region bound (one affine map, depth-rectangle scan shared by
-// the lanes; no kNN gather, no blend); only sub-bricks it cannot settle -- inside the band widened by the region's
-// deviation, at silhouettes -- run the pointwise DQB tier (classify, clamped update, defer the rest to the exact pass).
 template <int KMAX, bool EXACTK>
-__device__ __forceinline__ void mixed_brick(const ProjParams& P, const float* region_rec, int nby, int nbz, int b, float sc) {
+__device__ __forceinline__ void mixed_brick(const ProjParams& P, int nby, int nbz, int b, int dx, int dy, int dz, float sc) {
     int bxs, by, bz;
     brick_thread_coords(b, nby, nbz, bxs, by, bz);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = lane >> 1, dx = row >> 2, dy = row & 3;
-    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + warp * 8 + (lane & 1) * 4;
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
-    bool resolved = false;
-    const int zlo = bz * BRICK_Z + warp * 8;
-    if (region_rec && !P.rigid && zlo < P.rz) {      // warp-uniform
-        const int nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
-        const float* rr = region_rec + (((size_t)(bxs * BRICK_X / REGION_X) * nry + by * BRICK_Y / REGION_Y) * nrz + bz * BRICK_Z / REGION_Z) * REGION_REC_FLOATS;
-        if (rr[15] > 0.5f) {
-            const int xlo = P.x0 + bxs * BRICK_X, ylo = by * BRICK_Y;
-            const int xhi = min(xlo + BRICK_X, P.x1) - 1, yhi = min(ylo + BRICK_Y, P.ry) - 1, zhi = min(zlo + 8, P.rz) - 1;
-            int fr = 0;
-            const int m = subbox_classify(P, rr, xlo, xhi, ylo, yhi, zlo, zhi, &fr, GroupCtx<32>());
-            if (m != BRICK_CLS_MIXED) {
-                resolved = true;
-                if (row_in) {
-                    const size_t i = ((size_t)xs * P.ry + y) * P.rz + z0;
-                    for (int q = 0; q < 4 && z0 + q < P.rz; ++q) {
-                        if (m) {
-                            float v = P.tsdf[i + q], w = P.weight[i + q];
-                            for (int vi = 0; vi < P.n_views; ++vi)
-                                if (m & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
-                            P.tsdf[i + q] = v;
-                            P.weight[i + q] = w;
-                        }
-                        if (P.mask_out) P.mask_out[i + q] = (uint8_t)m;
-                        if (P.frustum_out) P.frustum_out[i + q] = (uint8_t)fr;
-                    }
-                }
-            }
-        }
-    }
-    if (resolved) return;                            // warp-uniform
     for (int q = 0; q < 4; ++q) {
         const int z = z0 + q;
         const bool in = row_in && z < P.rz;
@@ -447,21 +411,20 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
 }
 
 template <int KMAX, bool EXACTK>
-__global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, const float* region_rec, int nbx, int nby,
-                                                          int nbz, const uint32_t* list) {
+__global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                          const uint32_t* list) {
     const uint32_t count = P.counters[3];
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, region_rec, nby, nbz, (int)list[t], (float)P.scale);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)list[t], dx, dy, dz, (float)P.scale);
 }
 
 // Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
 // (issue-bound per-voxel tier) and its share of CLAMP bricks (HBM-bound streaming), so both kinds of work are resident
 // on every SM at the same time and the streaming traffic hides under the arithmetic.
 template <int KMAX, bool EXACTK>
-__global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant__ ProjParams P, const float* region_rec, int nbx, int nby,
-                                                           int nbz, const uint8_t* cls, const uint32_t* stream_list,
-                                                           const uint32_t* mixed_list) {
+__global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+                                                           const uint8_t* cls, const uint32_t* stream_list, const uint32_t* mixed_list) {
     const uint32_t cnt_s = P.counters[2], cnt_m = P.counters[3];
     const uint32_t n_t = cnt_m > gridDim.x ? cnt_m : gridDim.x;
     const uint32_t share = (cnt_s + n_t - 1) / n_t;
@@ -471,7 +434,7 @@ __global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant
     const float sc = (float)P.scale;
     const bool vec = (P.rz & 3) == 0;
     for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
-        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, region_rec, nby, nbz, (int)mixed_list[t], sc);
+        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)mixed_list[t], dx, dy, dz, sc);
         const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
         for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, (int)stream_list[s], dx, dy, dz, sc, vec);
     }
@@ -685,19 +648,19 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream && do_mixed) {
-                if (P.k == 4 && !P.rigid) brick_update_kernel<4, true><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (P.k == 8 && !P.rigid) brick_update_kernel<8, true><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (P.k <= 4) brick_update_kernel<4, false><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else brick_update_kernel<8, false><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                if (P.k == 4 && !P.rigid) brick_update_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (P.k == 8 && !P.rigid) brick_update_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else if (P.k <= 4) brick_update_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+                else brick_update_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_update_kernel");
             } else if (do_stream) {
                 brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
                 DFB_LAUNCH_CHECK("brick_stream_kernel");
             } else if (do_mixed) {
-                if (P.k == 4 && !P.rigid) brick_mixed_kernel<4, true><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, mixed_list);
-                else if (P.k == 8 && !P.rigid) brick_mixed_kernel<8, true><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, mixed_list);
-                else if (P.k <= 4) brick_mixed_kernel<4, false><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, mixed_list);
-                else brick_mixed_kernel<8, false><<<grid, 128, 0, s>>>(P, rrec, nbx, nby, nbz, mixed_list);
+                if (P.k == 4 && !P.rigid) brick_mixed_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else if (P.k == 8 && !P.rigid) brick_mixed_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else if (P.k <= 4) brick_mixed_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                else brick_mixed_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
                 DFB_LAUNCH_CHECK("brick_mixed_kernel");
             }
         } else {

@@ -7,7 +7,6 @@
 #include <stdio.h>
 #include <algorithm>
 #include <array>
-#include <unordered_map>
 #include <vector>
 
 #include "../../dynamicfusion_body_b200/csrc/dfb_params.h"
@@ -82,8 +81,6 @@ static const uint8_t* g_brick_count = nullptr;
 static const uint32_t* g_brick_pairs = nullptr;
 static uint8_t* g_brick_cls_vox = nullptr;
 static int g_use_regions = 0;
-static long g_seg_resolved = 0;
-extern "C" long hs_seg_resolved() { long v = g_seg_resolved; g_seg_resolved = 0; return v; }
 static float g_region_dmax = 0.f;   // largest deviation bound among valid regions of the last call (diagnostic)
 static float g_region_valid = 0.f;  // fraction of valid regions
 extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox, int use_regions) {
@@ -160,7 +157,6 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
     const bool bricks = mode == DFB_MODE_HYBRID && (P.rigid || (g_brick_nodes && g_brick_count)) && g_brick_cls_vox;
     const int nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
     std::vector<int> brick_cache((size_t)((P.x1 - P.x0 + BRICK_X - 1) / BRICK_X) * nby * nbz, -1);
-    std::unordered_map<size_t, int> sub_cache;
     std::vector<float> region_rec;
     if (bricks && !P.rigid && g_use_regions) region_rec = build_region_records(P);
     const float* rrec = region_rec.empty() ? nullptr : region_rec.data();
@@ -197,34 +193,6 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                 uint16_t ids[KMAX] = {0};
                 for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
                 int m = 0, f = 0, cls = CLS_UNCERTAIN;
-                if (mode == DFB_MODE_HYBRID && bricks && rrec) {
-                    // the warp's 4x4x8 sub-brick settled by the region bound, as mixed_brick does (cached per sub-brick)
-                    const int nry_ = (P.ry + REGION_Y - 1) / REGION_Y, nrz_ = (P.rz + REGION_Z - 1) / REGION_Z;
-                    const float* rr = rrec + (((size_t)(xs / REGION_X) * nry_ + y / REGION_Y) * nrz_ + z / REGION_Z) * REGION_REC_FLOATS;
-                    if (rr[15] > 0.5f) {
-                        const size_t sid = ((((size_t)(xs / BRICK_X) * nby + y / BRICK_Y) * nbz + z / BRICK_Z) << 2) | (size_t)((z % BRICK_Z) / 8);
-                        auto it = sub_cache.find(sid);
-                        if (it == sub_cache.end()) {
-                            const int xlo = P.x0 + (xs / BRICK_X) * BRICK_X, ylo = (y / BRICK_Y) * BRICK_Y, zlo = (z / 8) * 8;
-                            const int xhi = std::min(xlo + BRICK_X, P.x1) - 1, yhi = std::min(ylo + BRICK_Y, P.ry) - 1, zhi = std::min(zlo + 8, P.rz) - 1;
-                            int fr0 = 0;
-                            const int sm0 = subbox_classify(P, rr, xlo, xhi, ylo, yhi, zlo, zhi, &fr0, SerialCtx());
-                            it = sub_cache.emplace(sid, sm0 | (fr0 << 8)).first;
-                        }
-                        const int sm = it->second & 0xff, fr = it->second >> 8;
-                        if (sm != BRICK_CLS_MIXED) {
-                            float v = P.tsdf[i], w = P.weight[i];
-                            for (int vi = 0; vi < P.n_views; ++vi)
-                                if (sm & (1 << vi)) clamp_update(v, w, P.tdist_f, P.wmax_f, (float)P.scale);
-                            if (sm) { P.tsdf[i] = v; P.weight[i] = w; }
-                            if (P.mask_out) P.mask_out[i] = (uint8_t)sm;
-                            if (P.frustum_out) P.frustum_out[i] = (uint8_t)fr;
-                            if (cls_out) cls_out[i] = sm ? CLS_CLAMP : CLS_SKIP;
-                            ++g_seg_resolved;
-                            continue;
-                        }
-                    }
-                }
                 if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
                 if (cls_out) cls_out[i] = (uint8_t)cls;
                 float v = P.tsdf[i], w = P.weight[i];

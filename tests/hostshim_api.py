@@ -71,10 +71,8 @@ def set_bricks(knn=None, k=4, slab_shape=None, enable=True, use_pairs=True, regi
 
 
 def region_stats():
-    """(largest deviation bound among valid regions, fraction of valid regions, voxels of MIXED bricks settled by the
-    4-voxel run test) of the last region-enabled call."""
-    lib().hs_seg_resolved.restype = C.c_long
-    return float(lib().hs_region_dmax()), float(lib().hs_region_valid()), int(lib().hs_seg_resolved())
+    """(largest deviation bound among valid regions, fraction of valid regions) of the last region-enabled call."""
+    return float(lib().hs_region_dmax()), float(lib().hs_region_valid())
 
 
 def _p(a):
