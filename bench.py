@@ -214,11 +214,11 @@ def run_ours(args):
 
     # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----
     kk = 4 if args.k <= 4 else 8
-    # production launches per step: nodes_pack, brick_classify_kernel, brick_update_kernel (CLAMP + MIXED bricks fused),
-    # proj_exact_kernel.  The two halves of the fused pass are also timed alone (profiling modes) for the breakdown.
-    prod = [("brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
+    # production launches per step: nodes_pack, region_bounds_kernel, brick_classify_kernel, brick_update_kernel (CLAMP + MIXED
+    # bricks fused), proj_exact_kernel.  The two halves of the fused pass are also timed alone (profiling modes) for the breakdown.
+    prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
             ("proj_exact_kernel<%d>" % kk, _capi.MODE_LIST_ONLY)]
-    parts = [("brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
+    parts = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
              ("brick_mixed_kernel<%d>" % kk, _capi.MODE_BRICK_MIXED)]
 
     def time_modes(seq, reps):
@@ -270,7 +270,7 @@ def run_ours(args):
                    "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
         "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(sc.depths.nbytes + dqs[0].nbytes),
                 "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": 4 * args.steps,
+        "gpu_launches": 5 * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": TRAFFIC_PER_LAUNCH.get(dominant.split("<")[0]),
