@@ -140,33 +140,67 @@ __device__ __forceinline__ int find_slot(const int32_t* row_ptr, const int32_t* 
 }
 
 // ---- normal equations -------------------------------------------------------------------------------------------
-// data term: one warp per vertex; every lane evaluates (r, g, wts) redundantly (a few hundred float64 flops) and owns
-// two of the 64 entries of each 8x8 block, so the k*k block updates are 2 coalesced 256-byte atomic bursts each.
+// data term: each lane evaluates the (r, g, wts) of its OWN residual (a few hundred float64 flops), then the warp walks its 32
+// residuals, broadcasting one residual's values by shuffle so that every lane scatters two of the 64 entries of each 8x8
+// block: the k*k block updates are coalesced 256-byte atomic bursts and nothing is computed 32 times.
 __global__ void __launch_bounds__(256) normal_eq_data_kernel(const __grid_constant__ GNParams P, const double* x, const int32_t* row_ptr,
                                                             const int32_t* col_idx, double* H, double* g, double* cost) {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int r0 = lane >> 3, c0 = lane & 7;
     double c_rob = 0.0, c_l2 = 0.0;
-    for (int64_t i = warp; i < P.n_vert; i += nwarps) {
-        double r, gv[8], wts[DFB_MAX_K];
-        data_residual_jac(P, x, i, &r, gv, wts);
-        const double om = huber_weight(r, P.huber, P.f_scale);
-        const int32_t* ids = P.vert_knn + i * P.k;
-        const int r0 = lane >> 3, c0 = lane & 7;
-        const double e0 = gv[r0] * gv[c0], e1 = gv[r0 + 4] * gv[c0];
-        for (int a = 0; a < P.k; ++a) {
-            const int ia = ids[a];
-            for (int b = 0; b < P.k; ++b) {
-                const int slot = find_slot(row_ptr, col_idx, ia, ids[b]);
-                const double cf = om * wts[a] * wts[b];
-                atomicAdd(H + (size_t)slot * 64 + lane, cf * e0);
-                atomicAdd(H + (size_t)slot * 64 + 32 + lane, cf * e1);
-            }
-            if (lane < 8) atomicAdd(g + 8 * (size_t)ia + lane, om * wts[a] * r * gv[lane]);
+    for (int64_t base = warp * 32; base < P.n_vert; base += nwarps * 32) {
+        const int64_t mine = base + lane;
+        double r = 0.0, gv[8], wts[DFB_MAX_K], om = 0.0;
+        int ids[DFB_MAX_K];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) gv[t] = 0.0;
+#pragma unroll
+        for (int a = 0; a < DFB_MAX_K; ++a) { wts[a] = 0.0; ids[a] = 0; }
+        if (mine < P.n_vert) {
+            data_residual_jac(P, x, mine, &r, gv, wts);
+            om = huber_weight(r, P.huber, P.f_scale);
+            for (int a = 0; a < P.k; ++a) ids[a] = P.vert_knn[mine * P.k + a];
+            c_rob += huber_rho(r, P.huber, P.f_scale);
+            c_l2 += 0.5 * r * r;
         }
-        if (lane == 0) { c_rob += huber_rho(r, P.huber, P.f_scale); c_l2 += 0.5 * r * r; }
+        const int cnt = (int)((P.n_vert - base < 32) ? (P.n_vert - base) : 32);
+        for (int src = 0; src < cnt; ++src) {
+            const double s_r = __shfl_sync(0xffffffffu, r, src), s_om = __shfl_sync(0xffffffffu, om, src);
+            double sg[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) sg[t] = __shfl_sync(0xffffffffu, gv[t], src);
+            // this lane's two entries of g g^T: (r0, c0) and (r0 + 4, c0); select without dynamic register indexing
+            double ga = 0.0, gb = 0.0, gc = 0.0, gl = 0.0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (t == r0) ga = sg[t];
+                if (t == r0 + 4) gb = sg[t];
+                if (t == c0) gc = sg[t];
+                if (t == (lane & 7)) gl = sg[t];
+            }
+            const double e0 = ga * gc, e1 = gb * gc;
+#pragma unroll
+            for (int a = 0; a < DFB_MAX_K; ++a) {
+                if (a >= P.k) break;
+                const int ia = __shfl_sync(0xffffffffu, ids[a], src);
+                const double wa = __shfl_sync(0xffffffffu, wts[a], src);
+#pragma unroll
+                for (int b = 0; b < DFB_MAX_K; ++b) {
+                    if (b >= P.k) break;
+                    const int ib = __shfl_sync(0xffffffffu, ids[b], src);
+                    const double wb = __shfl_sync(0xffffffffu, wts[b], src);
+                    const int slot = find_slot(row_ptr, col_idx, ia, ib);
+                    const double cf = s_om * wa * wb;
+                    atomicAdd(H + (size_t)slot * 64 + lane, cf * e0);
+                    atomicAdd(H + (size_t)slot * 64 + 32 + lane, cf * e1);
+                }
+                if (lane < 8) atomicAdd(g + 8 * (size_t)ia + lane, s_om * wa * s_r * gl);
+            }
+        }
     }
+    for (int o = 16; o > 0; o >>= 1) { c_rob += __shfl_xor_sync(0xffffffffu, c_rob, o); c_l2 += __shfl_xor_sync(0xffffffffu, c_l2, o); }
     if (lane == 0 && (c_rob != 0.0 || c_l2 != 0.0)) { atomicAdd(cost, c_rob); atomicAdd(cost + 1, c_l2); }
 }
 
@@ -468,7 +502,7 @@ extern "C" int dfb_gn_normal_eq(const dfb_gn_problem* prob, const double* x, con
     DFB_CUDA(cudaMemsetAsync(g, 0, (size_t)P.n_nodes * 8 * sizeof(double), s));
     DFB_CUDA(cudaMemsetAsync(cost, 0, 2 * sizeof(double), s));
     if (P.n_vert > 0) {
-        normal_eq_data_kernel<<<blocks_for(P.n_vert * 32, 256, 148 * 16), 256, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
+        normal_eq_data_kernel<<<blocks_for(P.n_vert, 256, 148 * 16), 256, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
         DFB_LAUNCH_CHECK("normal_eq_data_kernel");
     }
     normal_eq_reg_kernel<<<blocks_for((int64_t)P.n_nodes * P.k, 64), 64, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
