@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(128, 5) proj_exact_kernel(const __grid_constan
 // a1
 // ------------------------------------------------------------------------------------------------
 template <int KMAX>
-__global__ void __launch_bounds__(256) vol_fast_kernel(const __grid_constant__ VolParams P) {
+__global__ void __launch_bounds__(256, 3) vol_fast_kernel(const __grid_constant__ VolParams P) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int xs = blockIdx.z;
