@@ -100,13 +100,28 @@ def update_volume(tsdf, tsdfw, curr_tsdf, vox, knn_idx, node_pos, node_dq, node_
             np.where(mask, w_new, w_old).astype(np.float64), mask)
 
 
+def _matvec_rows(M, cols):
+    """np.matmul(M, v) for ONE small vector v, vectorised over many v: numpy evaluates each output element as the plain
+    left-to-right sum  M[r,0]*v0 + M[r,1]*v1 + ...  (no FMA, no blocking).  A batched `V @ M.T` goes through dgemm, whose
+    different rounding flips knife-edge decisions (e.g. u == k + 0.5 exactly when the optical axis passes through voxel
+    centres) -- caught by tests/test_gpu_classes.py against the reference."""
+    M = np.asarray(M, dtype=np.float64)
+    out = []
+    for r in range(M.shape[0]):
+        acc = M[r, 0] * cols[0]
+        for c in range(1, M.shape[1]):
+            acc = acc + M[r, c] * cols[c]
+        out.append(acc)
+    return np.stack(out, axis=-1)
+
+
 def _project_and_fuse(lpos, dm, K, Kinv, v_old, w_old, tdist, scale, wmax):
     """Per-voxel body of FusionDM.fuseDepths from `project_to_pixel` on (core/fusion_dm.py:194-210,
     core/util.py:312-320).  `(dmx, dmy) = dm.shape` = (rows, cols): u is tested against cols-1 and v
     against rows-1; the pixel is `dm[int(round(v))][int(round(u))]` (round-half-even); depth is stored
     negative; `z > 0` required."""
     rows, cols = dm.shape
-    p = lpos @ np.asarray(K, dtype=np.float64).T
+    p = _matvec_rows(K, [lpos[..., 0], lpos[..., 1], lpos[..., 2]])
     nz = p[..., 2] != 0
     with np.errstate(invalid='ignore', divide='ignore'):
         u = p[..., 0] / p[..., 2]
@@ -118,7 +133,7 @@ def _project_and_fuse(lpos, dm, K, Kinv, v_old, w_old, tdist, scale, wmax):
     has_depth = frustum & (z > 0)
     uc = z[..., None] * np.stack([u, v, np.ones_like(u)], axis=-1)
     with np.errstate(invalid='ignore'):
-        cpos = uc @ np.asarray(Kinv, dtype=np.float64).T
+        cpos = _matvec_rows(Kinv, [uc[..., 0], uc[..., 1], uc[..., 2]])
         tl = cpos[..., 2] - lpos[..., 2]
         mask = has_depth & (tl > -1 * tdist)
     wi = 1
@@ -137,7 +152,7 @@ def fuse_depth_rigid(tsdf, tsdfw, vox, dm, lw34, K, Kinv, tdist, res, scale=1.0,
     sdf_center = np.zeros(3) + res / 2
     pos = scale * (vox - sdf_center) + center
     lw34 = np.asarray(lw34)
-    lpos = np.concatenate([pos, np.ones(pos.shape[:-1] + (1,))], axis=-1) @ lw34.T
+    lpos = _matvec_rows(lw34, [pos[..., 0], pos[..., 1], pos[..., 2], np.ones(pos.shape[:-1])])
     return _project_and_fuse(lpos, dm, K, Kinv, np.asarray(tsdf), np.asarray(tsdfw), tdist, scale, wmax)
 
 
@@ -155,7 +170,7 @@ def update_projective(tsdf, tsdfw, vox, knn_idx, node_pos, node_dq, node_w, lw, 
     for vi, dm in enumerate(dms):
         if extrinsics is not None:
             E = np.asarray(extrinsics[vi], dtype=np.float64)
-            lpos = np.concatenate([pw, np.ones(pw.shape[:-1] + (1,))], axis=-1) @ E.T
+            lpos = _matvec_rows(E, [pw[..., 0], pw[..., 1], pw[..., 2], np.ones(pw.shape[:-1])])
         else:
             lpos = pw
         v, w, m, fr = _project_and_fuse(lpos, dm, K, Kinv, v, w, tdist, 1.0, wmax)

@@ -70,7 +70,7 @@ def test_fuseDepths_live():
         rt, rw = fdm.fuseDepths(dm, lw34, t0.copy(), w0.copy(), scale=0.9, center=np.array([0.1, -0.1, 0.0]))
     v, w, m, fr = ot.fuse_depth_rigid(t0.ravel(), w0.ravel(), ot.voxel_grid((R, R, R)), dm, lw34, K, np.linalg.inv(K), 0.5, R, scale=0.9,
                                       center=np.array([0.1, -0.1, 0.0]))
-    assert np.abs(v - rt.ravel()).max() <= 1e-14 and np.array_equal(w, rw.ravel()) and m.sum() > 10
+    assert np.array_equal(v, rt.ravel()) and np.array_equal(w, rw.ravel()) and m.sum() > 10
 
 
 def test_computef_live():
