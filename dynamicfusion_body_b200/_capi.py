@@ -20,7 +20,7 @@ MODE_BRICK_MIXED = 6
 MODE_BRICK_UPDATE = 7
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libdfb_b200.so")
+LIB_PATH = os.environ.get("DFB_LIB") or os.path.join(_PKG_DIR, "libdfb_b200.so")   # DFB_LIB: developer override (kernel variants)
 
 c_f32p = C.POINTER(C.c_float)
 c_f64p = C.POINTER(C.c_double)

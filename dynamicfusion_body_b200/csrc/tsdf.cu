@@ -92,6 +92,15 @@ __device__ __forceinline__ void brick_thread_coords(int b, int nby, int nbz, int
     bxs = t / nby;
 }
 
+// work-list entries carry the brick coordinates packed 10/10/12 bits (x, y, z), so the per-voxel passes never divide
+constexpr int BRICK_PACK_MAX_XY = 1024, BRICK_PACK_MAX_Z = 4096;
+__device__ __forceinline__ uint32_t brick_pack(int bxs, int by, int bz) { return ((uint32_t)bxs << 22) | ((uint32_t)by << 12) | (uint32_t)bz; }
+__device__ __forceinline__ void brick_unpack(uint32_t e, int& bxs, int& by, int& bz) {
+    bxs = (int)(e >> 22);
+    by = (int)((e >> 12) & 1023u);
+    bz = (int)(e & 4095u);
+}
+
 // thread t of a 128-thread CTA owns 4 consecutive z voxels of one of the brick's 16 rows
 __device__ __forceinline__ void brick_lane(int t, int& dx, int& dy, int& dz) {
     const int row = t >> 3;
@@ -324,17 +333,18 @@ __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_consta
         if (gl == 0) {
             cls_out[b] = (uint8_t)cls;
             cls_out[nb + b] = (uint8_t)fr;
-            if (cls == BRICK_CLS_MIXED) mixed_list[atomicAdd(P.counters + 3, 1u)] = (uint32_t)b;
-            else if (cls != 0 || (P.frustum_out != nullptr && fr != 0)) stream_list[atomicAdd(P.counters + 2, 1u)] = (uint32_t)b;
+            if (cls == BRICK_CLS_MIXED) mixed_list[atomicAdd(P.counters + 3, 1u)] = brick_pack(bxs, by, bz);
+            else if (cls != 0 || (P.frustum_out != nullptr && fr != 0)) stream_list[atomicAdd(P.counters + 2, 1u)] = brick_pack(bxs, by, bz);
         }
     }
 }
 
 // CLAMP bricks: v' = (scale*v*w + tdist)/(scale*(w+1)), w' = min(w+1, wmax) once per view bit -- no warp, no kNN read.
-__device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nby, int nbz, const uint8_t* cls, int b, int dx, int dy, int dz,
-                                             float sc, bool vec) {
+__device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nby, int nbz, const uint8_t* cls, uint32_t entry, int dx, int dy,
+                                             int dz, float sc, bool vec) {
     int bxs, by, bz;
-    brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    brick_unpack(entry, bxs, by, bz);
+    const int b = (bxs * nby + by) * nbz + bz;
     const int m = cls[b], fr = cls[nb + b];
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z = bz * BRICK_Z + dz;
     if (xs >= P.x1 - P.x0 || y >= P.ry || z >= P.rz) return;
@@ -372,9 +382,10 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
 
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
 template <int KMAX, bool EXACTK>
-__device__ __forceinline__ void mixed_brick(const ProjParams& P, int nby, int nbz, int b, int dx, int dy, int dz, float sc) {
+__device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry, int dx, int dy, int dz, float sc) {
     int bxs, by, bz;
-    brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    brick_unpack(entry, bxs, by, bz);
+    const bool want_masks = P.mask_out != nullptr || P.frustum_out != nullptr;
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
     for (int q = 0; q < 4; ++q) {
@@ -396,8 +407,10 @@ __device__ __forceinline__ void mixed_brick(const ProjParams& P, int nby, int nb
             P.tsdf[i] = v;
             P.weight[i] = w;
         }
-        if (P.mask_out) P.mask_out[i] = (uint8_t)m;
-        if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+        if (want_masks) {
+            if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+            if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+        }
     }
 }
 
@@ -407,7 +420,7 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
     for (uint32_t t = blockIdx.x; t < count; t += gridDim.x)
-        stream_brick(P, nbx * nby * nbz, nby, nbz, cls, (int)list[t], dx, dy, dz, (float)P.scale, (P.rz & 3) == 0);
+        stream_brick(P, nbx * nby * nbz, nby, nbz, cls, list[t], dx, dy, dz, (float)P.scale, (P.rz & 3) == 0);
 }
 
 template <int KMAX, bool EXACTK>
@@ -416,7 +429,7 @@ __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant_
     const uint32_t count = P.counters[3];
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)list[t], dx, dy, dz, (float)P.scale);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, list[t], dx, dy, dz, (float)P.scale);
 }
 
 // Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
@@ -434,15 +447,18 @@ __global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant
     const float sc = (float)P.scale;
     const bool vec = (P.rz & 3) == 0;
     for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
-        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, nby, nbz, (int)mixed_list[t], dx, dy, dz, sc);
+        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, mixed_list[t], dx, dy, dz, sc);
         const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
-        for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, (int)stream_list[s], dx, dy, dz, sc, vec);
+        for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
     }
 }
 
 // mode: 0 = work list (or re-scan on overflow), 1 = every voxel
+#ifndef DFB_EXACT_MINB
+#define DFB_EXACT_MINB 8
+#endif
 template <int KMAX, int KT>
-__global__ void __launch_bounds__(128, 5) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
+__global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
     const bool use_list = !all_mode && count <= P.capacity;
@@ -621,6 +637,8 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
         if (bricks) {
             const int nbx = (P.x1 - P.x0 + BRICK_X - 1) / BRICK_X, nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
             const int nb = nbx * nby * nbz;
+            DFB_REQUIRE(nbx <= BRICK_PACK_MAX_XY && nby <= BRICK_PACK_MAX_XY && nbz <= BRICK_PACK_MAX_Z,
+                        "volume too large for the brick work lists (4096 x 4096 x 131072 voxels per slab)");
             const float* rrec = nullptr;
             if (!P.rigid && B.rnodes && B.rcount && B.rpairs && B.rrec) {
                 rrec = B.rrec;

@@ -63,6 +63,24 @@ def test_every_k(k):
     _run(sc, (24, 24, 24), 0, 24, t0, w0)
 
 
+@pytest.mark.parametrize("seed,max_disp,views,k", [(1, 3.0, 1, 4), (2, 10.0, 1, 4), (3, 1.0, 3, 8), (4, 30.0, 1, 4)])
+def test_wild_warp_fields_stay_conservative(seed, max_disp, views, k):
+    """Large translations and rotating nodes: the warp is far from rigid, the brick and region bounds are loose, the
+    fast tier's error margins are at their widest. Results must not change -- only the share of deferred voxels may."""
+    from dynamicfusion_body_b200 import synth
+    import scenes
+    import dataclasses
+    R = 64
+    sc = synth.make_scene(res=R, k=k, n_nodes=300, seed=seed, rows=120, cols=160, background=True, max_disp=max_disp, n_views=views)
+    rng = np.random.default_rng(seed)
+    ax = rng.normal(size=(sc.n_nodes, 3))
+    ang = np.deg2rad(rng.uniform(0, 3, sc.n_nodes))
+    extra = synth.axis_angle_dq(ax, ang, rng.normal(size=(sc.n_nodes, 3)) * max_disp * 0.2).astype(np.float32)
+    dq = (sc.node_dq * 0.7 + extra * 0.3).astype(np.float32)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    _run(sc, (R, R, R), 0, R, t0, w0, dq=dq)
+
+
 def test_n_nodes_equals_k():
     """The reference queries k+1 neighbours and drops the last (core/fusion.py:175-176), which needs N >= k+1; with
     N == k every node is a neighbour of every voxel -- the table must still be the distance-sorted permutation."""
