@@ -99,6 +99,7 @@ inline void fill_intrinsics(ProjParams& P, const double* K, const double* Kinv) 
     P.k_pinhole = (K[6] == 0.0 && K[7] == 0.0 && K[8] == 1.0) ? 1 : 0;
     P.knorm = (float)fmax(fabs(K[0]) + fabs(K[1]) + fabs(K[2]), fabs(K[3]) + fabs(K[4]) + fabs(K[5]));
     P.kin_uv = (float)(fabs(Kinv[6]) + fabs(Kinv[7]));
+    P.ezf = (float)(fmax(1.0, fabs(K[6]) + fabs(K[7]) + fabs(K[8])) * 1.000001);
 }
 
 static const double kIdent34[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};

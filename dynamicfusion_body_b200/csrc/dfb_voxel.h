@@ -44,6 +44,7 @@ struct ProjParams {
     float kin[3];    // Kinv row 2, fp32
     float tnorm;     // max abs row sum of the view transforms E_v * A_lw (3x3 parts): lpos error per unit p' error
     float knorm;     // max abs row sum of K rows 0,1 (error propagation to pixels)
+    float ezf;       // abs row sum of K row 2 (1 for a pinhole), never below 1: error propagation to the projective divisor
     float kin_uv;    // |Kinv20| + |Kinv21|
     float coord_mag; // bound on |coordinates| entering the fp32 chain (error scale)
     // update
@@ -158,14 +159,14 @@ DFB_HD float pos_err_bound(float coord_mag, float amin_nat) {
 // in: (pu,pv,pz) = K*lpos, lz = lpos_z, e = error bound on lpos components.
 // frustum_bit: 1 if certainly inside the image, 0 if certainly outside (only valid if result != UNCERTAIN)
 DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const float* depth, int rows, int cols,
-                         const float* kin, float knorm, float kin_uv, float tdist, int* frustum_bit) {
+                         const float* kin, float knorm, float ezf, float kin_uv, float tdist, int* frustum_bit) {
     *frustum_bit = 0;
     const float apz = fabsf(pz);
-    const float ez = e * 4.f;  // |K row 2| is (0,0,1) for a pinhole; 4x head-room for general K
-    if (!(apz > 8.f * ez)) return CLS_UNCERTAIN;  // also catches NaN
+    const float ez = e * ezf;  // error of the divisor K_row2 . lpos
+    if (!(apz > 64.f * ez)) return CLS_UNCERTAIN;  // also catches NaN
     const float inv = fast_rcp(pz);
     const float u = pu * inv, v = pv * inv;
-    const float ainv = fabsf(inv) * 1.000001f;
+    const float ainv = fabsf(inv) * 1.02f;         // 1/|true divisor| <= 1/(|pz| - ez) <= (1/|pz|) / (1 - 1/64)
     const float eu = (knorm * e + fabsf(u) * ez) * ainv + 4.8e-7f * fabsf(u) + 1e-6f;
     const float ev = (knorm * e + fabsf(v) * ez) * ainv + 4.8e-7f * fabsf(v) + 1e-6f;
     const float umax = (float)(cols - 1), vmax = (float)(rows - 1);
@@ -249,7 +250,8 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
 
 // fast classification of a voxel for a2/a3.  Returns CLS_UNCERTAIN, or CLS_SKIP/CLS_CLAMP-style result:
 // *mask gets the per-view clamp bits (all certain), *frus the per-view frustum bits.
-template <int KMAX, bool EXACTK = false>
+// ONEVIEW: n_views == 1 known at compile time (the view record is then addressed with immediate offsets)
+template <int KMAX, bool EXACTK = false, bool ONEVIEW = false>
 DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus) {
     float pw[3];
     float e;
@@ -262,14 +264,16 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
         e = pos_err_bound(P.coord_mag, amin);
     }
     int m = 0, f = 0;
-    for (int vi = 0; vi < P.n_views; ++vi) {
-        const ViewFast& V = P.vf[vi];
+    const int nv = ONEVIEW ? 1 : P.n_views;
+#pragma unroll 1
+    for (int vi = 0; vi < nv; ++vi) {
+        const ViewFast& V = P.vf[ONEVIEW ? 0 : vi];
         const float pu = V.P[0] * pw[0] + V.P[1] * pw[1] + V.P[2] * pw[2] + V.P[3];
         const float pv = V.P[4] * pw[0] + V.P[5] * pw[1] + V.P[6] * pw[2] + V.P[7];
         const float pz = V.P[8] * pw[0] + V.P[9] * pw[1] + V.P[10] * pw[2] + V.P[11];
         const float lz = V.L[0] * pw[0] + V.L[1] * pw[1] + V.L[2] * pw[2] + V.L[3];
         int fb;
-        const int c = classify_view(pu, pv, pz, lz, e, P.depth[vi], P.rows, P.cols, P.kin, P.knorm, P.kin_uv, P.tdist_f, &fb);
+        const int c = classify_view(pu, pv, pz, lz, e, P.depth[ONEVIEW ? 0 : vi], P.rows, P.cols, P.kin, P.knorm, P.ezf, P.kin_uv, P.tdist_f, &fb);
         if (c == CLS_UNCERTAIN) return CLS_UNCERTAIN;
         if (c == CLS_CLAMP) m |= 1 << vi;
         if (fb) f |= 1 << vi;

@@ -380,11 +380,10 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
     }
 }
 
-// MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass)
-template <int KMAX, bool EXACTK>
-__device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry, int dx, int dy, int dz, float sc) {
-    int bxs, by, bz;
-    brick_unpack(entry, bxs, by, bz);
+// MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass).
+// Edge bricks (cut by the volume boundary, or rz not a multiple of 4): one guarded voxel at a time.
+template <int KMAX, bool EXACTK, bool ONEVIEW>
+__device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc) {
     const bool want_masks = P.mask_out != nullptr || P.frustum_out != nullptr;
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
@@ -396,7 +395,7 @@ __device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry,
         if (in) {
             uint16_t ids[KMAX];
             if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
-            cls = voxel_projective_classify<KMAX, EXACTK>(P, xs + P.x0, y, z, ids, &m, &f);
+            cls = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f);
         }
         push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
         if (!in || cls == CLS_UNCERTAIN) continue;
@@ -414,6 +413,91 @@ __device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry,
     }
 }
 
+// Interior bricks: the thread's four z-consecutive voxels move as one float4 of v, one of w and (k = 4 / 8) two / four
+// 16-byte kNN loads, all issued before the arithmetic; the four classifications are independent instruction streams
+// for the scheduler, and the warp reserves its work-list slots with one atomic.
+template <int KMAX, bool EXACTK, bool ONEVIEW>
+__device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc) {
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
+    const size_t i0 = ((size_t)xs * P.ry + y) * P.rz + z0;
+    const float4 v4 = *reinterpret_cast<const float4*>(P.tsdf + i0);
+    const float4 w4 = *reinterpret_cast<const float4*>(P.weight + i0);
+    uint16_t ids[4][KMAX];
+    if (!P.rigid) {
+        if (EXACTK && KMAX == 4) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.knn + i0 * 4);
+            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                ids[q][0] = r[2 * q] & 0xffff; ids[q][1] = r[2 * q] >> 16;
+                ids[q][2] = r[2 * q + 1] & 0xffff; ids[q][3] = r[2 * q + 1] >> 16;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) load_ids<KMAX>(P.knn, i0 + q, EXACTK ? KMAX : P.k, ids[q]);
+        }
+    }
+    float v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+    int cls[4], m[4], f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        m[q] = 0; f[q] = 0;
+        cls[q] = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q]);
+    }
+    // work list: one reservation per warp for the four voxels of every lane
+    unsigned bal[4];
+    uint32_t total = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        bal[q] = __ballot_sync(0xffffffffu, cls[q] == CLS_UNCERTAIN);
+        total += __popc(bal[q]);
+    }
+    if (total) {
+        const int lane = threadIdx.x & 31;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(P.counters, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (cls[q] == CLS_UNCERTAIN) {
+                const uint32_t pos = base + __popc(bal[q] & ((1u << lane) - 1u));
+                if (pos < P.capacity) P.list[pos] = (uint32_t)(i0 + q);
+            }
+            base += __popc(bal[q]);
+        }
+    }
+    bool changed = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (cls[q] == CLS_UNCERTAIN) { m[q] = 0; f[q] = 0; continue; }
+        if (m[q]) {
+            if (ONEVIEW) {
+                clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
+            } else {
+                for (int vi = 0; vi < P.n_views; ++vi)
+                    if (m[q] & (1 << vi)) clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
+            }
+            changed = true;
+        }
+    }
+    if (changed) {   // deferred voxels get their old value back; the exact pass runs after this kernel
+        *reinterpret_cast<float4*>(P.tsdf + i0) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(P.weight + i0) = make_float4(w[0], w[1], w[2], w[3]);
+    }
+    if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i0) = make_uchar4(m[0], m[1], m[2], m[3]);
+    if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i0) = make_uchar4(f[0], f[1], f[2], f[3]);
+}
+
+template <int KMAX, bool EXACTK, bool ONEVIEW>
+__device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry, int dx, int dy, int dz, float sc) {
+    int bxs, by, bz;
+    brick_unpack(entry, bxs, by, bz);
+    const bool full = (P.rz & 3) == 0 && (bxs + 1) * BRICK_X <= P.x1 - P.x0 && (by + 1) * BRICK_Y <= P.ry && (bz + 1) * BRICK_Z <= P.rz;
+    if (full) mixed_brick_full<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc);
+    else mixed_brick_edge<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc);
+}
+
 __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
                                                            const uint8_t* cls, const uint32_t* list) {
     const uint32_t count = P.counters[2];
@@ -423,20 +507,25 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
         stream_brick(P, nbx * nby * nbz, nby, nbz, cls, list[t], dx, dy, dz, (float)P.scale, (P.rz & 3) == 0);
 }
 
-template <int KMAX, bool EXACTK>
+template <int KMAX, bool EXACTK, bool ONEVIEW>
 __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
                                                           const uint32_t* list) {
     const uint32_t count = P.counters[3];
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK>(P, list[t], dx, dy, dz, (float)P.scale);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, list[t], dx, dy, dz, (float)P.scale);
 }
 
 // Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
 // (issue-bound per-voxel tier) and its share of CLAMP bricks (HBM-bound streaming), so both kinds of work are resident
 // on every SM at the same time and the streaming traffic hides under the arithmetic.
-template <int KMAX, bool EXACTK>
-__global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
+// 8 CTAs of 128 threads per SM (64 registers): measured best against 5, 6 and 10 (profiles/r1_ncu_full_summary.md)
+#ifndef DFB_UPDATE_MINB
+#define DFB_UPDATE_MINB 8
+#endif
+#define DFB_UPDATE_BOUNDS __launch_bounds__(128, DFB_UPDATE_MINB)
+template <int KMAX, bool EXACTK, bool ONEVIEW>
+__global__ void DFB_UPDATE_BOUNDS brick_update_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
                                                            const uint8_t* cls, const uint32_t* stream_list, const uint32_t* mixed_list) {
     const uint32_t cnt_s = P.counters[2], cnt_m = P.counters[3];
     const uint32_t n_t = cnt_m > gridDim.x ? cnt_m : gridDim.x;
@@ -447,7 +536,7 @@ __global__ void __launch_bounds__(128) brick_update_kernel(const __grid_constant
     const float sc = (float)P.scale;
     const bool vec = (P.rz & 3) == 0;
     for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
-        if (t < cnt_m) mixed_brick<KMAX, EXACTK>(P, mixed_list[t], dx, dy, dz, sc);
+        if (t < cnt_m) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, mixed_list[t], dx, dy, dz, sc);
         const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
         for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
     }
@@ -666,19 +755,21 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 DFB_LAUNCH_CHECK("brick_classify_kernel");
             }
             if (do_stream && do_mixed) {
-                if (P.k == 4 && !P.rigid) brick_update_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (P.k == 8 && !P.rigid) brick_update_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else if (P.k <= 4) brick_update_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                else brick_update_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
+#define DFB_BRICK_DISPATCH(KERNEL, ...)                                                                                  \
+    do {                                                                                                                 \
+        const bool one = P.n_views == 1;                                                                                 \
+        if (P.k == 4 && !P.rigid) { if (one) KERNEL<4, true, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<4, true, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
+        else if (P.k == 8 && !P.rigid) { if (one) KERNEL<8, true, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<8, true, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
+        else if (P.k <= 4) { if (one) KERNEL<4, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<4, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
+        else { if (one) KERNEL<8, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<8, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
+    } while (0)
+                DFB_BRICK_DISPATCH(brick_update_kernel, P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 DFB_LAUNCH_CHECK("brick_update_kernel");
             } else if (do_stream) {
                 brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
                 DFB_LAUNCH_CHECK("brick_stream_kernel");
             } else if (do_mixed) {
-                if (P.k == 4 && !P.rigid) brick_mixed_kernel<4, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
-                else if (P.k == 8 && !P.rigid) brick_mixed_kernel<8, true><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
-                else if (P.k <= 4) brick_mixed_kernel<4, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
-                else brick_mixed_kernel<8, false><<<grid, 128, 0, s>>>(P, nbx, nby, nbz, mixed_list);
+                DFB_BRICK_DISPATCH(brick_mixed_kernel, P, nbx, nby, nbz, mixed_list);
                 DFB_LAUNCH_CHECK("brick_mixed_kernel");
             }
         } else {
