@@ -31,6 +31,7 @@ constexpr int REGION_PAIR_WORDS = 65;                        // 64*65/2 = 2080 p
 constexpr int REGION_REC_FLOATS = 16;                        // P_ref (row-major 3x4), D[3], valid
 constexpr int BRICK_PAIR_WORDS = 10;   // bit p = i*(i+1)/2 + j (j <= i) of the 24*25/2 = 300 candidate pairs
 constexpr int BRICK_CLS_MIXED = 0xFF;
+constexpr int REGION_MAX_RECT = 4096;   // depth pixels scanned for a whole region (one warp)
 constexpr int BRICK_MAX_RECT = 512;   // depth pixels scanned per brick and view before giving up
 
 struct Box3 { float lo[3], hi[3]; };
@@ -181,6 +182,91 @@ struct GroupCtx {
 typedef GroupCtx<32> WarpCtx;
 #endif
 
+// Second half of the classification, shared by bricks and regions: project the warped-space box `bx` into every view
+// and compare the depth rectangle it covers with the box's depth range.  Returns BRICK_CLS_MIXED or the per-view CLAMP
+// bit mask (0 = SKIP); *frus = per-view "certainly inside the image" bits.  Control flow is uniform across `ctx`.
+template <class Ctx>
+DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect, int* frus, const Ctx ctx) {
+    *frus = 0;
+    const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
+    const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
+    int mask = 0, fr = 0;
+    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
+    for (int v = 0; v < P.n_views; ++v) {
+        const ViewFast& V = P.vf[v];
+        // camera-space box, then a = X/Z, b = Y/Z, (u,v) = K[0:2] * (a, b, 1): dividing X by Z (not K*lpos rows by each
+        // other) keeps the interval dependency problem away from the principal-point term
+        float xl, xh, yl, yh, lzl, lzh;
+        row_interval(V.T, c3, h3, xl, xh);
+        row_interval(V.T + 4, c3, h3, yl, yh);
+        row_interval(V.T + 8, c3, h3, lzl, lzh);
+        if (!P.k_pinhole) return DFB_MIXED(9);
+        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
+        float al, ah, bl, bh;
+        div_interval(xl, xh, lzl, lzh, al, ah);
+        div_interval(yl, yh, lzl, lzh, bl, bh);
+        float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        {
+            const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
+            ul -= su; uh += su; vl -= sv; vh += sv;
+        }
+        const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
+        if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
+        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
+        fr |= 1 << v;
+        const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
+        const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
+        if (npx > max_rect) return DFB_MIXED(5);
+        float zmin = 3.0e38f, zmax = -3.0e38f;
+        bool nan = false;
+        for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
+            const int iv = iv0 + t / nu, iu = iu0 + t % nu;
+            const float z = -P.depth[v][(size_t)iv * P.cols + iu];
+            nan |= !(z == z);
+            zmin = fminf(zmin, z);
+            zmax = fmaxf(zmax, z);
+        }
+        if (ctx.any(nan)) return DFB_MIXED(6);
+        zmin = ctx.rmin(zmin);
+        zmax = ctx.rmax(zmax);
+        // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
+        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
+        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
+        const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
+        const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+        if (!(kzl > 0.f)) return DFB_MIXED(7);
+        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
+        const float zs = 1e-6f * fabsf(zmax) * kzh;
+        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
+        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
+        return DFB_MIXED(8);
+    }
+    *frus = fr;
+    return mask;
+}
+
+// rr[15] of a region record: 0 = no bound (fall back to the pairwise hull), 1 = (P_ref, D_R) valid, >= 2: the WHOLE region
+// is already classified, code - 2 = CLAMP mask + 256 * frustum bits (every brick of it inherits the class).
+DFB_HD float region_code(bool valid, int cls, int fr) {
+    if (!valid) return 0.f;
+    if (cls == BRICK_CLS_MIXED) return 1.f;
+    return (float)(2 + cls + 256 * fr);
+}
+
+// warped-space box of the voxel box (c, h) under the region's reference map, inflated by its deviation bound
+DFB_HD void region_box(const float* rr, const float* c, const float* h, float coord_mag, Box3& bx) {
+    for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
+    box_extend_affine(rr, 1.0f, c, h, bx);
+    for (int r = 0; r < 3; ++r) {
+        const float m = rr[12 + r] + 2e-3f + 2e-6f * coord_mag;
+        bx.lo[r] -= m;
+        bx.hi[r] += m;
+    }
+}
+
 // Classify brick (bxs,by,bz) (bxs slab-local).  Returns BRICK_CLS_MIXED or the per-view CLAMP bit mask (0 = SKIP);
 // *frus = per-view "certainly inside the image" bits (meaningful when the result is not MIXED).
 // All control flow is uniform across the lanes of `ctx`.
@@ -200,14 +286,13 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
         // O(1) path: the region's reference affine map applied to the brick, inflated by the region's deviation bound
         const int nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
         const float* rr = region_rec + (((size_t)(bxs * BRICK_X / REGION_X) * nry + by * BRICK_Y / REGION_Y) * nrz + bz * BRICK_Z / REGION_Z) * REGION_REC_FLOATS;
+        if (rr[15] > 1.5f) {           // the region as a whole is already SKIP / CLAMP
+            const int code = (int)rr[15] - 2;
+            *frus = code >> 8;
+            return code & 0xff;
+        }
         if (rr[15] > 0.5f) {
-            for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
-            box_extend_affine(rr, 1.0f, c, h, bx);
-            for (int r = 0; r < 3; ++r) {
-                const float m = rr[12 + r] + 2e-3f + 2e-6f * P.coord_mag;
-                bx.lo[r] -= m;
-                bx.hi[r] += m;
-            }
+            region_box(rr, c, h, P.coord_mag, bx);
             have_box = true;
         }
     }
@@ -279,64 +364,7 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
             bx.hi[r] = ctx.rmax(bx.hi[r]) + m;
         }
     }
-    const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
-    const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
-    int mask = 0, fr = 0;
-    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
-    for (int v = 0; v < P.n_views; ++v) {
-        const ViewFast& V = P.vf[v];
-        // camera-space box, then a = X/Z, b = Y/Z, (u,v) = K[0:2] * (a, b, 1): dividing X by Z (not K*lpos rows by each
-        // other) keeps the interval dependency problem away from the principal-point term
-        float xl, xh, yl, yh, lzl, lzh;
-        row_interval(V.T, c3, h3, xl, xh);
-        row_interval(V.T + 4, c3, h3, yl, yh);
-        row_interval(V.T + 8, c3, h3, lzl, lzh);
-        if (!P.k_pinhole) return DFB_MIXED(9);
-        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
-        float al, ah, bl, bh;
-        div_interval(xl, xh, lzl, lzh, al, ah);
-        div_interval(yl, yh, lzl, lzh, bl, bh);
-        float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-        float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-        float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
-        float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
-        {
-            const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
-            ul -= su; uh += su; vl -= sv; vh += sv;
-        }
-        const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
-        if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
-        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
-        fr |= 1 << v;
-        const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
-        const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
-        if (npx > BRICK_MAX_RECT) return DFB_MIXED(5);
-        float zmin = 3.0e38f, zmax = -3.0e38f;
-        bool nan = false;
-        for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
-            const int iv = iv0 + t / nu, iu = iu0 + t % nu;
-            const float z = -P.depth[v][(size_t)iv * P.cols + iu];
-            nan |= !(z == z);
-            zmin = fminf(zmin, z);
-            zmax = fmaxf(zmax, z);
-        }
-        if (ctx.any(nan)) return DFB_MIXED(6);
-        zmin = ctx.rmin(zmin);
-        zmax = ctx.rmax(zmax);
-        // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
-        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
-        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
-        const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
-        const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
-        if (!(kzl > 0.f)) return DFB_MIXED(7);
-        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
-        const float zs = 1e-6f * fabsf(zmax) * kzh;
-        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
-        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
-        return DFB_MIXED(8);
-    }
-    *frus = fr;
-    return mask;
+    return box_classify_views(P, bx, BRICK_MAX_RECT, frus, ctx);
 }
 
 }  // namespace dfb

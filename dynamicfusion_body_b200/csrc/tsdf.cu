@@ -246,9 +246,11 @@ __global__ void __launch_bounds__(256) region_build_kernel(const uint16_t* knn, 
     for (int t = threadIdx.x; t < REGION_PAIR_WORDS; t += blockDim.x) region_pairs[(size_t)reg * REGION_PAIR_WORDS + t] = pairs[t];
 }
 
-__global__ void __launch_bounds__(128) region_bounds_kernel(const float4* node_rec, const uint16_t* region_nodes, const uint8_t* region_count,
-                                                            const uint32_t* region_pairs, int x0, int sx, int ry, int rz, int nry, int nrz,
+__global__ void __launch_bounds__(128) region_bounds_kernel(const __grid_constant__ ProjParams P, const uint16_t* region_nodes,
+                                                            const uint8_t* region_count, const uint32_t* region_pairs, int nry, int nrz,
                                                             float* region_rec) {
+    const float4* node_rec = P.node_rec;
+    const int x0 = P.x0, sx = P.x1 - P.x0, ry = P.ry, rz = P.rz;
     __shared__ float q[REGION_MAXC][8];
     __shared__ float red[4][3];
     __shared__ int bad_s;
@@ -310,10 +312,21 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const float4* node_r
     if ((threadIdx.x & 31) == 0)
         for (int r = 0; r < 3; ++r) red[threadIdx.x >> 5][r] = dev[r];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int t = 0; t < 12; ++t) out[t] = Pref[t];
-        for (int r = 0; r < 3; ++r) out[12 + r] = fmaxf(fmaxf(red[0][r], red[1][r]), fmaxf(red[2][r], red[3][r]));
-        out[15] = bad_s ? 0.f : 1.f;
+    if (threadIdx.x < 32) {
+        // warp 0: the record, and -- with (P_ref, D_R) in hand -- one attempt to classify the region as a whole; every
+        // brick of a region that is SKIP / CLAMP in its entirety inherits that class without any work of its own
+        float rr[REGION_REC_FLOATS];
+        for (int t = 0; t < 12; ++t) rr[t] = Pref[t];
+        for (int r = 0; r < 3; ++r) rr[12 + r] = fmaxf(fmaxf(red[0][r], red[1][r]), fmaxf(red[2][r], red[3][r]));
+        const bool valid = bad_s == 0;
+        int cls = BRICK_CLS_MIXED, fr = 0;
+        if (valid) {
+            Box3 bx;
+            region_box(rr, c, h, P.coord_mag, bx);
+            cls = box_classify_views(P, bx, REGION_MAX_RECT, &fr, WarpCtx());
+        }
+        rr[15] = region_code(valid, cls, fr);
+        if (threadIdx.x < REGION_REC_FLOATS) out[threadIdx.x] = rr[threadIdx.x];
     }
 }
 
@@ -445,7 +458,9 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
         m[q] = 0; f[q] = 0;
         cls[q] = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q]);
     }
-    // work list: one reservation per warp for the four voxels of every lane
+    // work list: one reservation per warp for the four voxels of every lane.  (Measured and dropped: CTA-level
+    // aggregation through shared memory, and prefetch.global.L2 of the next brick's v / w / kNN lines -- neither the
+    // counter nor DRAM latency at the head of a brick is what the kernel waits for.)
     unsigned bal[4];
     uint32_t total = 0;
 #pragma unroll
@@ -733,8 +748,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 rrec = B.rrec;
                 if (do_classify) {
                     const int nrx = (P.x1 - P.x0 + REGION_X - 1) / REGION_X, nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
-                    region_bounds_kernel<<<nrx * nry * nrz, 128, 0, s>>>(P.node_rec, B.rnodes, B.rcount, B.rpairs, P.x0, P.x1 - P.x0, P.ry, P.rz,
-                                                                         nry, nrz, B.rrec);
+                    region_bounds_kernel<<<nrx * nry * nrz, 128, 0, s>>>(P, B.rnodes, B.rcount, B.rpairs, nry, nrz, B.rrec);
                     DFB_LAUNCH_CHECK("region_bounds_kernel");
                 }
             }

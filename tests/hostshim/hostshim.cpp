@@ -83,11 +83,13 @@ static uint8_t* g_brick_cls_vox = nullptr;
 static int g_use_regions = 0;
 static float g_region_dmax = 0.f;   // largest deviation bound among valid regions of the last call (diagnostic)
 static float g_region_valid = 0.f;  // fraction of valid regions
+static int g_region_resolved = 0;   // regions classified as a whole in the last call
 extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox, int use_regions) {
     g_brick_nodes = nodes; g_brick_count = count; g_brick_pairs = pairs; g_brick_cls_vox = cls_vox; g_use_regions = use_regions;
 }
 extern "C" float hs_region_dmax() { return g_region_dmax; }
 extern "C" float hs_region_valid() { return g_region_valid; }
+extern "C" int hs_region_resolved() { return g_region_resolved; }
 
 // host mirror of region_build_kernel + region_bounds_kernel (tsdf.cu)
 static std::vector<float> build_region_records(const ProjParams& P) {
@@ -95,6 +97,7 @@ static std::vector<float> build_region_records(const ProjParams& P) {
     const int nrx = (sx + REGION_X - 1) / REGION_X, nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
     std::vector<float> rec((size_t)nrx * nry * nrz * REGION_REC_FLOATS, 0.f);
     g_region_dmax = 0.f;
+    g_region_resolved = 0;
     int nvalid = 0;
     for (int rx = 0; rx < nrx; ++rx)
         for (int ry_ = 0; ry_ < nry; ++ry_)
@@ -143,7 +146,14 @@ static std::vector<float> build_region_records(const ProjParams& P) {
                     if (!region_pair_bound(q[pr.first].data(), q[pr.second].data(), pr.first == pr.second, Pref, c, h, dev)) bad = true;
                 for (int t = 0; t < 12; ++t) out[t] = Pref[t];
                 for (int r = 0; r < 3; ++r) out[12 + r] = dev[r];
-                out[15] = bad ? 0.f : 1.f;
+                int rcls = BRICK_CLS_MIXED, rfr = 0;
+                if (!bad) {
+                    Box3 bx;
+                    region_box(out, c, h, P.coord_mag, bx);
+                    rcls = box_classify_views(P, bx, REGION_MAX_RECT, &rfr, SerialCtx());
+                }
+                out[15] = region_code(!bad, rcls, rfr);
+                if (!bad && rcls != BRICK_CLS_MIXED) ++g_region_resolved;
                 if (!bad) { ++nvalid; g_region_dmax = std::max(g_region_dmax, std::max(dev[0], std::max(dev[1], dev[2]))); }
             }
     g_region_valid = (float)nvalid / (float)((size_t)nrx * nry * nrz);

@@ -75,6 +75,11 @@ def region_stats():
     return float(lib().hs_region_dmax()), float(lib().hs_region_valid())
 
 
+def regions_resolved():
+    """Number of regions the last region-enabled call classified as a whole (all their bricks inherit the class)."""
+    return int(lib().hs_region_resolved())
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

@@ -153,11 +153,13 @@ def test_brick_culling_is_conservative():
     wf = hs.HostWarpField(s.node_pos, s.node_dq, np.float32(s.node_w), 4, knn=idx, lw=s.lw)
     res = []
     for bricks in (False, True):
-        cv = hs.set_bricks(idx, 4, (R, R, R), enable=bricks)
+        cv = hs.set_bricks(idx, 4, (R, R, R), enable=bricks, regions=True)
         tv, tw = t0.copy(), w0.copy()
         mask, frus, cls, nunc = hs.update_projective(tv, tw, (R, R, R), wf, s.depths, s.K, s.Kinv, s.tdist)
         res.append((tv, tw, mask, frus))
         assert np.array_equal(scenes.bits(mask, 0), om[0]) and np.array_equal(scenes.bits(frus, 0), ofr[0])
+    nreg = (R // 16) * (R // 16) * (R // 32)
+    assert hs.regions_resolved() > 0.2 * nreg            # whole 16x16x32 regions are settled by one box test
     hs.set_bricks(enable=False)
     # masks and weights are identical; values may differ by an fp32 ulp where one run resolved a voxel in the fp32
     # tier and the other in the float64 tier
