@@ -295,7 +295,7 @@ __global__ void trace_kernel(const int32_t* row_ptr, const int32_t* col_idx, con
 }
 
 __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, int n, double lambda,
-                                double* Minv, double* delta, double* r, double* p, double* S) {
+                                double* Minv, double* delta, double* r, double* z_out, double* S) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const double mu = lambda * S[7] / (8.0 * n);
     double part = 0.0;
@@ -322,7 +322,7 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
                     for (int b = 0; b < 16; ++b) A[a][b] -= f * A[c][b];
             }
         }
-        double rr[8], zz[8];
+        double rr[8];
         for (int a = 0; a < 8; ++a) {
             rr[a] = -g[8 * (size_t)i + a];
             for (int b = 0; b < 8; ++b) Minv[(size_t)i * 64 + a * 8 + b] = A[a][8 + b];
@@ -330,10 +330,9 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
         for (int a = 0; a < 8; ++a) {
             double z = 0.0;
             for (int b = 0; b < 8; ++b) z += A[a][8 + b] * rr[b];
-            zz[a] = z;
             delta[8 * (size_t)i + a] = 0.0;
             r[8 * (size_t)i + a] = rr[a];
-            p[8 * (size_t)i + a] = z;
+            z_out[8 * (size_t)i + a] = z;
             part += rr[a] * z;
         }
     }
@@ -344,53 +343,66 @@ __global__ void pcg_init_kernel(const int32_t* row_ptr, const int32_t* col_idx, 
 
 // The whole PCG loop in ONE cooperative launch: the system is tiny (8N <= 32k rows, ~10 MB of L2-resident blocks), so
 // separate launches are pure launch latency (4 dependent launches ~ 37 us/iteration measured); grid.sync() costs ~2 us.
-__global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv, int n,
-                                                        int max_iter, double tol2, double* delta, double* r, double* z, double* p, double* q,
-                                                        double* S) {
-    // scalars: S[0]=mu  S[4]=rz0  S[5]=converged  S[6]=iterations;  RZ = S+8 (2 slots), PQ = S+10 (2 slots), double-buffered by
-    // iteration parity so that no "rotate the scalars" phase (and its grid-wide barrier) is needed: 3 barriers per iteration.
+// Chronopoulos-Gear arrangement of CG: with s = A z carried next to w = A p, both inner products of an iteration
+// ((r,z) and (z,s)) are available after ONE matrix product, so an iteration is
+//   phase 1 (node-local, 8 lanes per node): p = z + beta p, w = s + beta w, x += alpha p, r -= alpha w, z = Minv r, (r,z)
+//   -- barrier --
+//   phase 2 (one warp per block row):       s = (H + mu I) z, (z,s)
+//   -- barrier --
+// i.e. two grid-wide barriers per iteration instead of the three of the textbook ordering.  Every thread derives alpha and
+// beta from the same globally reduced sums, so no scalar has to be broadcast.
+__global__ void __launch_bounds__(256) pcg_global_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv, int n,
+                                                        int max_iter, double tol2, double* delta, double* r, double* z, double* p, double* sv,
+                                                        double* w, double* S) {
+    // scalars: S[0]=mu  S[1]=final (r,z)  S[4]=(r,z) at start  S[6]=iterations;  G = S+8: (r,z), D = S+10: (z,s), both
+    // double-buffered by iteration parity so that no "rotate the scalars" phase is needed.
     cg::grid_group grid = cg::this_grid();
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
-    double* RZ = S + 8;
-    double* PQ = S + 10;
+    double* G = S + 8;
+    double* D = S + 10;
     const double mu = S[0];
-    int it = 0;
-    for (; it < max_iter; ++it) {
-        const int cur = it & 1, nxt = cur ^ 1;
-        if (tid == 0) { RZ[nxt] = 0.0; PQ[nxt] = 0.0; }
-        // A: q = (H + mu I) p, pq = p.q.  One warp per block row: lane = (column group cgp = lane>>3, row a = lane&7);
-        //    the 8 lanes of a group read one 512-byte block row-by-row (coalesced), groups stride over the row's blocks.
+    const double rz0 = S[4];
+    // s = (H + mu I) z and the partial (z,s) into *acc_zs.  One warp per block row: lane = (column group cgp = lane>>3,
+    // row a = lane&7); the 8 lanes of a group read one 512-byte block row-by-row (coalesced), groups stride over the blocks.
+    auto spmv = [&](double* acc_zs) {
         double part = 0.0;
-        {
-            const int warp = tid >> 5, nwarps = nthreads >> 5;
-            const int a = lane & 7, cgp = lane >> 3;
-            for (int i = warp; i < n; i += nwarps) {
-                double acc = 0.0;
-                for (int s = row_ptr[i] + cgp; s < row_ptr[i + 1]; s += 4) {
-                    const double* Hb = H + (size_t)s * 64 + a * 8;
-                    const double* pj = p + 8 * (size_t)col_idx[s];
+        const int warp = tid >> 5, nwarps = nthreads >> 5;
+        const int a = lane & 7, cgp = lane >> 3;
+        for (int i = warp; i < n; i += nwarps) {
+            double acc = 0.0;
+            for (int t = row_ptr[i] + cgp; t < row_ptr[i + 1]; t += 4) {
+                const double* Hb = H + (size_t)t * 64 + a * 8;
+                const double* zj = z + 8 * (size_t)col_idx[t];
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) acc += Hb[b] * pj[b];
-                }
-                acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-                if (cgp == 0) {
-                    const double pa = p[8 * (size_t)i + a];
-                    acc += mu * pa;
-                    q[8 * (size_t)i + a] = acc;
-                    part += acc * pa;
-                }
+                for (int b = 0; b < 8; ++b) acc += Hb[b] * zj[b];
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (cgp == 0) {
+                const double za = z[8 * (size_t)i + a];
+                acc += mu * za;
+                sv[8 * (size_t)i + a] = acc;
+                part += acc * za;
             }
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && part != 0.0) atomicAdd(PQ + cur, part);
-        grid.sync();
-        // B: delta += alpha p, r -= alpha q, z = Minv r, rz_new = r.z.  8 lanes per node (lane a owns component a).
-        const double pq = PQ[cur], rz = RZ[cur];
-        const double alpha = (pq != 0.0) ? rz / pq : 0.0;
-        part = 0.0;
+        if (lane == 0 && part != 0.0) atomicAdd(acc_zs, part);
+    };
+    spmv(D + 0);
+    grid.sync();
+    double g_prev = 1.0, alpha_prev = 1.0;
+    int it = 0;
+    double g_last = G[0];
+    for (; it < max_iter; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const double gam = G[cur], dzs = D[cur];
+        const double beta = (it == 0 || g_prev == 0.0) ? 0.0 : gam / g_prev;
+        const double den = (it == 0) ? dzs : dzs - beta * gam / alpha_prev;
+        const double alpha = (den != 0.0) ? gam / den : 0.0;
+        if (tid == 0) D[nxt] = 0.0;
+        double part = 0.0;
         {
             const int grp = tid >> 3, ngrp = nthreads >> 3, a = lane & 7;
             const int nloop = (n + ngrp - 1) / ngrp;
@@ -400,8 +412,12 @@ __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, 
                 const size_t t = 8 * (size_t)(ok ? i : 0) + a;
                 double ra = 0.0;
                 if (ok) {
-                    delta[t] += alpha * p[t];
-                    ra = r[t] - alpha * q[t];
+                    const double pa = (it == 0) ? z[t] : z[t] + beta * p[t];
+                    const double wa = (it == 0) ? sv[t] : sv[t] + beta * w[t];
+                    p[t] = pa;
+                    w[t] = wa;
+                    delta[t] += alpha * pa;
+                    ra = r[t] - alpha * wa;
                     r[t] = ra;
                 }
                 double zz = 0.0;
@@ -417,17 +433,181 @@ __global__ void __launch_bounds__(256) pcg_fused_kernel(const int32_t* row_ptr, 
             }
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0 && part != 0.0) atomicAdd(RZ + nxt, part);
+        if (lane == 0 && part != 0.0) atomicAdd(G + nxt, part);
         grid.sync();
-        // C: p = z + beta p; convergence is evaluated identically by every thread (no broadcast needed)
-        const double rzn = RZ[nxt];
-        const double beta = (rz != 0.0) ? rzn / rz : 0.0;
-        for (int t = tid; t < 8 * n; t += nthreads) p[t] = z[t] + beta * p[t];
-        const bool done = !(rzn > tol2 * S[4]);
+        g_last = G[nxt];
+        if (!(g_last > tol2 * rz0)) { ++it; break; }   // identical on every thread
+        if (tid == 0) G[cur] = 0.0;                   // accumulated again in phase 1 of the next iteration
+        spmv(D + nxt);
+        g_prev = gam;
+        alpha_prev = alpha;
         grid.sync();
-        if (done) { ++it; break; }
     }
-    if (tid == 0) { S[6] = (double)it; S[1] = RZ[it & 1]; }
+    if (tid == 0) { S[6] = (double)it; S[1] = g_last; }
+}
+
+// Resident variant of the same iteration for systems that fit on the chip (N <= 4 rows per warp x 1184 warps): the matrix
+// never changes during a solve, so every CTA copies the 8x8 blocks (and column indices, and inverse diagonal blocks) of the
+// rows it owns into shared memory ONCE, and the node-local vectors r, p, w, delta, s, z of a row live in the registers of
+// the warp that owns it for the whole solve.  Per iteration only z (64 bytes per node) goes through L2: written in phase 1,
+// gathered by the neighbours' matrix products in phase 2.
+template <int RPW>
+__global__ void __launch_bounds__(256, 1) pcg_resident_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv,
+                                                              int n, int max_iter, double tol2, double* delta, const double* r_in, double* z,
+                                                              double* S, int cap_blocks) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int a = lane & 7, cgp = lane >> 3;
+    constexpr int ROWS_PER_CTA = 8 * RPW;
+    double* Ms = smem;                                        // [ROWS_PER_CTA][64]
+    // blocks are stored TRANSPOSED, columns swizzled by the block's parity: element (a, b) of cached block loc lives at
+    // loc*64 + (b ^ (loc & 1))*8 + a.  The 8 lanes of a group then sweep 16 consecutive banks and the groups of a warp (which
+    // read consecutive blocks) alternate between the two halves of the bank array -> the 2 wavefronts a 64-bit warp access
+    // needs anyway (row-major blocks were a 16-way bank conflict: 2.2 -> 1.6 ms per solve).
+    constexpr int HS = 64;
+    double* Hs = Ms + ROWS_PER_CTA * 64;                      // [cap_blocks][HS]
+    int32_t* cs = reinterpret_cast<int32_t*>(Hs + (size_t)cap_blocks * HS);   // [cap_blocks]
+    const int row_first = blockIdx.x * ROWS_PER_CTA;
+    const int row_end = min(row_first + ROWS_PER_CTA, n);
+    const int bs = row_first < n ? row_ptr[row_first] : 0;
+    const int be = row_first < n ? row_ptr[row_end] : 0;
+    const int ncache = min(be - bs, cap_blocks);
+    for (int t = threadIdx.x; t < ncache * 64; t += blockDim.x) Hs[(t >> 6) * HS + (((t & 7) ^ ((t >> 6) & 1)) * 8) + ((t >> 3) & 7)] = H[(size_t)bs * 64 + t];
+    for (int t = threadIdx.x; t < ncache; t += blockDim.x) cs[t] = col_idx[bs + t];
+    for (int t = threadIdx.x; t < (row_end - row_first) * 64; t += blockDim.x) Ms[t] = Minv[(size_t)row_first * 64 + t];
+    __syncthreads();
+    double* G = S + 8;
+    double* D = S + 10;
+    const double mu = S[0];
+    const double rz0 = S[4];
+    // registers of the lanes cgp == 0 (component a of each owned row)
+    double rr[RPW], pp[RPW], ww[RPW], dd[RPW], ss[RPW], zz[RPW];
+    int rs[RPW], re[RPW];
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int i = row_first + wic * RPW + j;
+        const bool ok = i < n;
+        rr[j] = ok ? r_in[8 * (size_t)i + a] : 0.0;
+        zz[j] = ok ? z[8 * (size_t)i + a] : 0.0;
+        pp[j] = 0.0; ww[j] = 0.0; dd[j] = 0.0; ss[j] = 0.0;
+        rs[j] = ok ? row_ptr[i] : 0;
+        re[j] = ok ? row_ptr[i + 1] : 0;
+    }
+    __shared__ double red[8];
+    // one global atomic per CTA and inner product (the 8 warp sums meet in shared memory first)
+    auto cta_add = [&](double part, double* target) {
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) red[wic] = part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[k];
+            if (t != 0.0) atomicAdd(target, t);
+        }
+        __syncthreads();
+    };
+    // s = (H + mu I) z for the owned rows.  Lane (a, cgp) handles row a of the blocks cgp, cgp+4, ... of the block row.
+    // Every lane gathers ONE component of the neighbour's z per block (the 8 lanes of a group cover the 8 components and
+    // exchange them by shuffle), four blocks in flight, so a row of <= 16 blocks pays a single L2 round trip.
+    auto gather = [&](int j, int t0, double* zv, const double** Hb, int* hst) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + cgp + 4 * u;
+            const bool valid = t < re[j];
+            const int loc = t - bs;
+            const bool cached = valid && loc < ncache;
+            const int col = valid ? (cached ? cs[loc] : col_idx[t]) : 0;
+            zv[u] = valid ? z[8 * (size_t)col + a] : 0.0;
+            Hb[u] = cached ? Hs + (size_t)loc * HS + a : valid ? H + (size_t)t * 64 + a * 8 : Hs;
+            hst[u] = (cached || !valid) ? 8 | ((loc & 1) << 8) : 1;   // element (a, b) is Hb[(b ^ parity) * stride]; parity in bit 8
+        }
+    };
+    auto consume = [&](const double* zv, const double* const* Hb, const int* hst, double acc) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b)   // b runs over the PHYSICAL columns; the matching z component is b ^ parity
+                acc += Hb[u][b * (hst[u] & 0xff)] * __shfl_sync(0xffffffffu, zv[u], (lane & 24) | (b ^ (hst[u] >> 8)));
+        }
+        return acc;
+    };
+    auto spmv = [&](double* acc_zs) {
+        double part = 0.0;
+        // the first 16 blocks of EVERY owned row are gathered before any arithmetic: one L2 round trip per product
+        double zv0[RPW][4];
+        const double* Hb0[RPW][4];
+        int hs0[RPW][4];
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) gather(j, rs[j], zv0[j], Hb0[j], hs0[j]);
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            double acc = consume(zv0[j], Hb0[j], hs0[j], 0.0);
+            for (int t0 = rs[j] + 16; t0 < re[j]; t0 += 16) {     // rows longer than 16 blocks; uniform across the warp
+                double zv[4];
+                const double* Hb[4];
+                int hst[4];
+                gather(j, t0, zv, Hb, hst);
+                acc = consume(zv, Hb, hst, acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            acc += mu * zz[j];
+            ss[j] = acc;
+            if (cgp == 0 && rs[j] < re[j]) part += acc * zz[j];
+        }
+        cta_add(part, acc_zs);
+    };
+    spmv(D + 0);
+    grid.sync();
+    double g_prev = 1.0, alpha_prev = 1.0;
+    int it = 0;
+    double g_last = G[0];
+    const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+    for (; it < max_iter; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const double gam = G[cur], dzs = D[cur];
+        const double beta = (it == 0 || g_prev == 0.0) ? 0.0 : gam / g_prev;
+        const double den = (it == 0) ? dzs : dzs - beta * gam / alpha_prev;
+        const double alpha = (den != 0.0) ? gam / den : 0.0;
+        if (leader) D[nxt] = 0.0;
+        double part = 0.0;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const int i = row_first + wic * RPW + j;
+            pp[j] = (it == 0) ? zz[j] : zz[j] + beta * pp[j];
+            ww[j] = (it == 0) ? ss[j] : ss[j] + beta * ww[j];
+            dd[j] += alpha * pp[j];
+            rr[j] -= alpha * ww[j];
+            // z = Minv r: lane (a, cgp) multiplies columns 2cgp, 2cgp+1 of row a; r_b comes from lane b (a group-0 lane)
+            const double* Mrow = Ms + (size_t)(wic * RPW + j) * 64 + a * 8 + 2 * cgp;
+            const double r0 = __shfl_sync(0xffffffffu, rr[j], 2 * cgp), r1 = __shfl_sync(0xffffffffu, rr[j], 2 * cgp + 1);
+            double zn = (i < n) ? Mrow[0] * r0 + Mrow[1] * r1 : 0.0;
+            zn += __shfl_xor_sync(0xffffffffu, zn, 8);
+            zn += __shfl_xor_sync(0xffffffffu, zn, 16);
+            zz[j] = zn;
+            if (cgp == 0 && i < n) {
+                z[8 * (size_t)i + a] = zn;
+                part += rr[j] * zn;
+            }
+        }
+        cta_add(part, G + nxt);
+        grid.sync();
+        g_last = G[nxt];
+        if (!(g_last > tol2 * rz0)) { ++it; break; }
+        if (leader) G[cur] = 0.0;
+        spmv(D + nxt);
+        g_prev = gam;
+        alpha_prev = alpha;
+        grid.sync();
+    }
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int i = row_first + wic * RPW + j;
+        if (cgp == 0 && i < n) delta[8 * (size_t)i + a] = dd[j];
+    }
+    if (leader) { S[6] = (double)it; S[1] = g_last; }
 }
 
 __global__ void apply_delta_kernel(const double* x, const double* delta, int n8, double* x_new) {
@@ -528,7 +708,7 @@ extern "C" int dfb_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* nod
     return DFB_OK;
 }
 
-extern "C" int64_t dfb_gn_solve_workspace_doubles(int n_nodes) { return (int64_t)n_nodes * (64 + 8 * 4) + 16; }
+extern "C" int64_t dfb_gn_solve_workspace_doubles(int n_nodes) { return (int64_t)n_nodes * (64 + 8 * 5) + 16; }
 
 extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, double lambda,
                             int max_iter, double tol, const double* x, double* x_new, double* delta, double* workspace,
@@ -542,28 +722,53 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
     double* r = Minv + (size_t)n * 64;
     double* z = r + (size_t)n * 8;
     double* p = z + (size_t)n * 8;
-    double* q = p + (size_t)n * 8;
+    double* sv = p + (size_t)n * 8;
+    double* w = sv + (size_t)n * 8;
     DFB_CUDA(cudaMemsetAsync(S, 0, 16 * sizeof(double), s));
     const int nb_node = (n + 127) / 128, nb_row = (8 * n + 127) / 128;
     trace_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, n, S);
-    pcg_init_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, g, n, lambda, Minv, delta, r, p, S);
+    pcg_init_kernel<<<nb_node, 128, 0, s>>>(row_ptr, col_idx, H, g, n, lambda, Minv, delta, r, z, S);
     DFB_LAUNCH_CHECK("pcg_init_kernel");
     const double tol2 = tol * tol;
     {
-        static int coop_blocks = -1;   // co-resident CTAs of pcg_fused_kernel on this device
-        if (coop_blocks < 0) {
-            int dev = 0, sms = 0, per_sm = 0;
+        static int sms = -1, smem_max = 0;
+        if (sms < 0) {
+            int dev = 0;
             DFB_CUDA(cudaGetDevice(&dev));
+            DFB_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
             DFB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_fused_kernel, 256, 0));
-            coop_blocks = sms * (per_sm > 0 ? 1 : 0);
         }
-        DFB_REQUIRE(coop_blocks > 0, "cooperative launch not possible on this device");
-        int blocks = (32 * n + 255) / 256;   // one warp per block row
-        if (blocks > coop_blocks) blocks = coop_blocks;
-        void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
-                        (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&q, (void*)&S};
-        DFB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_fused_kernel, dim3(blocks), dim3(256), args, 0, s));
+        static const bool force_global = getenv("DFB_PCG_GLOBAL") != nullptr;
+        const int warps = sms * 8;
+        const int rpw = (n + warps - 1) / warps;
+        if (rpw <= 4 && !force_global) {
+            // resident path: one CTA of 8 warps per SM, rpw block rows per warp, matrix blocks cached in shared memory
+            const int rows_per_cta = 8 * rpw;
+            const int blocks = (n + rows_per_cta - 1) / rows_per_cta;
+            const size_t fixed = (size_t)rows_per_cta * 64 * sizeof(double);
+            int cap_blocks = (int)(((size_t)smem_max - 1024 - fixed) / (64 * sizeof(double) + sizeof(int32_t)));
+            const size_t smem = fixed + (size_t)cap_blocks * (64 * sizeof(double) + sizeof(int32_t));
+            const double* r_in = r;
+            void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
+                            (void*)&delta, (void*)&r_in, (void*)&z, (void*)&S, (void*)&cap_blocks};
+            void* fn = rpw == 1 ? (void*)pcg_resident_kernel<1> : rpw == 2 ? (void*)pcg_resident_kernel<2>
+                     : rpw == 3 ? (void*)pcg_resident_kernel<3> : (void*)pcg_resident_kernel<4>;
+            DFB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            DFB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, s));
+        } else {
+            static int coop_blocks = -1;   // co-resident CTAs of pcg_global_kernel on this device
+            if (coop_blocks < 0) {
+                int per_sm = 0;
+                DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_global_kernel, 256, 0));
+                coop_blocks = sms * (per_sm > 0 ? 1 : 0);
+            }
+            DFB_REQUIRE(coop_blocks > 0, "cooperative launch not possible on this device");
+            int blocks = (32 * n + 255) / 256;   // one warp per block row
+            if (blocks > coop_blocks) blocks = coop_blocks;
+            void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
+                            (void*)&delta, (void*)&r, (void*)&z, (void*)&p, (void*)&sv, (void*)&w, (void*)&S};
+            DFB_CUDA(cudaLaunchCooperativeKernel((void*)pcg_global_kernel, dim3(blocks), dim3(256), args, 0, s));
+        }
     }
     apply_delta_kernel<<<nb_row, 128, 0, s>>>(x, delta, 8 * n, x_new);
     DFB_LAUNCH_CHECK("apply_delta_kernel");

@@ -185,7 +185,7 @@ int dfb_gn_normal_eq(const dfb_gn_problem* prob, const double* x, const int32_t*
 int dfb_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* node_dq, const double* lw, double* H8, double* g8, double* cost,
                         dfb_stream_t stream);
 /* Damped node-space solve (H + lambda*mean(diag H)*I) delta = -g by block-Jacobi PCG, then x_new = x + delta.
- * workspace: dfb_gn_solve_workspace_doubles(N) doubles; workspace[0..7] = {mu, rz, -, -, rz0, converged, iterations, trace}. */
+ * workspace: dfb_gn_solve_workspace_doubles(N) doubles; workspace[0..7] = {mu, final (r,z), -, -, initial (r,z), -, iterations, trace}. */
 int64_t dfb_gn_solve_workspace_doubles(int n_nodes);
 int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, double lambda,
                  int max_iter, double tol, const double* x, double* x_new, double* delta, double* workspace, dfb_stream_t stream);
