@@ -36,11 +36,18 @@ constexpr int BRICK_MAX_RECT = 512;   // depth pixels scanned per brick and view
 
 struct Box3 { float lo[3], hi[3]; };
 
-#if defined(DFB_BRICK_DEBUG)   // tests: report which condition sent a brick to the per-voxel path
-#define DFB_MIXED(n) (*frus = -(n), BRICK_CLS_MIXED)
-#else
-#define DFB_MIXED(n) BRICK_CLS_MIXED
-#endif
+// Class of a brick (or region).  Views are classified one by one: `clamp` = views in which every voxel gets the clamped
+// update, `frus` = views whose image certainly contains every voxel, `mixed` = views the box test could not settle (their
+// bits in clamp / frus are 0).  cls = BRICK_CLS_MIXED when any view is unsettled, else the clamp mask (0 = SKIP).  The
+// per-voxel tier of a MIXED brick only evaluates the unsettled views and takes the others from (clamp, frus).
+struct BrickClass {
+    int cls, clamp, frus, mixed;
+};
+DFB_HD BrickClass brick_class_all_mixed(int n_views) {
+    BrickClass r;
+    r.cls = BRICK_CLS_MIXED; r.clamp = 0; r.frus = 0; r.mixed = (1 << n_views) - 1;
+    return r;
+}
 
 // affine map (row-major 3x4) of dqb_warp(q, .) for a possibly non-unit q, fp32
 DFB_HD void dq_affine_f(const float* q, float* A) {
@@ -183,14 +190,13 @@ typedef GroupCtx<32> WarpCtx;
 #endif
 
 // Second half of the classification, shared by bricks and regions: project the warped-space box `bx` into every view
-// and compare the depth rectangle it covers with the box's depth range.  Returns BRICK_CLS_MIXED or the per-view CLAMP
-// bit mask (0 = SKIP); *frus = per-view "certainly inside the image" bits.  Control flow is uniform across `ctx`.
+// and compare the depth rectangle it covers with the box's depth range, view by view.  Control flow is uniform across `ctx`.
 template <class Ctx>
-DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect, int* frus, const Ctx ctx) {
-    *frus = 0;
+DFB_HDN BrickClass box_classify_views(const ProjParams& P, const Box3& bx, int max_rect, const Ctx ctx) {
     const float c3[3] = {0.5f * (bx.lo[0] + bx.hi[0]), 0.5f * (bx.lo[1] + bx.hi[1]), 0.5f * (bx.lo[2] + bx.hi[2])};
     const float h3[3] = {0.5f * (bx.hi[0] - bx.lo[0]), 0.5f * (bx.hi[1] - bx.lo[1]), 0.5f * (bx.hi[2] - bx.lo[2])};
-    int mask = 0, fr = 0;
+    int mask = 0, fr = 0, mixed = 0;
+    if (!P.k_pinhole) return brick_class_all_mixed(P.n_views);
     const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag;
     for (int v = 0; v < P.n_views; ++v) {
         const ViewFast& V = P.vf[v];
@@ -200,8 +206,7 @@ DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect
         row_interval(V.T, c3, h3, xl, xh);
         row_interval(V.T + 4, c3, h3, yl, yh);
         row_interval(V.T + 8, c3, h3, lzl, lzh);
-        if (!P.k_pinhole) return DFB_MIXED(9);
-        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) return DFB_MIXED(3);   // must be safely in front of the camera
+        if (!(lzl > 1e-3f * (fabsf(lzh) + 1.f))) { mixed |= 1 << v; continue; }   // must be safely in front of the camera
         float al, ah, bl, bh;
         div_interval(xl, xh, lzl, lzh, al, ah);
         div_interval(yl, yh, lzl, lzh, bl, bh);
@@ -215,11 +220,11 @@ DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect
         }
         const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
         if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) continue;        // certainly outside this image: view skipped
-        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return DFB_MIXED(4);
-        fr |= 1 << v;
+        if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) { mixed |= 1 << v; continue; }
+        const int frbit = 1 << v;
         const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
         const int nu = iu1 - iu0 + 1, npx = nu * (iv1 - iv0 + 1);
-        if (npx > max_rect) return DFB_MIXED(5);
+        if (npx > max_rect) { mixed |= 1 << v; continue; }
         float zmin = 3.0e38f, zmax = -3.0e38f;
         bool nan = false;
         for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
@@ -229,7 +234,7 @@ DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect
             zmin = fminf(zmin, z);
             zmax = fmaxf(zmax, z);
         }
-        if (ctx.any(nan)) return DFB_MIXED(6);
+        if (ctx.any(nan)) { mixed |= 1 << v; continue; }
         zmin = ctx.rmin(zmin);
         zmax = ctx.rmax(zmax);
         // kz = Kinv20*u + Kinv21*v + Kinv22 over the rectangle
@@ -237,23 +242,25 @@ DFB_HDN int box_classify_views(const ProjParams& P, const Box3& bx, int max_rect
         const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
         const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
         const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
-        if (!(kzl > 0.f)) return DFB_MIXED(7);
-        if (zmax <= 0.f) continue;                                                 // no measurement anywhere: view skipped
+        if (!(kzl > 0.f)) { mixed |= 1 << v; continue; }
+        if (zmax <= 0.f) { fr |= frbit; continue; }                                // no measurement anywhere: view skipped
         const float zs = 1e-6f * fabsf(zmax) * kzh;
-        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; continue; }
-        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) continue;                     // every measured pixel lies far in front: skipped
-        return DFB_MIXED(8);
+        if (zmin > 0.f && zmin * kzl - lzh > P.tdist_f + mt + zs) { mask |= 1 << v; fr |= frbit; continue; }
+        if (zmax * kzh - lzl < -P.tdist_f - mt - zs) { fr |= frbit; continue; }   // every measured pixel lies far in front: skipped
+        mixed |= 1 << v;
     }
-    *frus = fr;
-    return mask;
+    BrickClass r;
+    r.clamp = mask; r.frus = fr; r.mixed = mixed;
+    r.cls = mixed ? BRICK_CLS_MIXED : mask;
+    return r;
 }
 
 // rr[15] of a region record: 0 = no bound (fall back to the pairwise hull), 1 = (P_ref, D_R) valid, >= 2: the WHOLE region
 // is already classified, code - 2 = CLAMP mask + 256 * frustum bits (every brick of it inherits the class).
-DFB_HD float region_code(bool valid, int cls, int fr) {
+DFB_HD float region_code(bool valid, const BrickClass& c) {
     if (!valid) return 0.f;
-    if (cls == BRICK_CLS_MIXED) return 1.f;
-    return (float)(2 + cls + 256 * fr);
+    if (c.mixed) return 1.f;
+    return (float)(2 + c.clamp + 256 * c.frus);
 }
 
 // warped-space box of the voxel box (c, h) under the region's reference map, inflated by its deviation bound
@@ -267,13 +274,10 @@ DFB_HD void region_box(const float* rr, const float* c, const float* h, float co
     }
 }
 
-// Classify brick (bxs,by,bz) (bxs slab-local).  Returns BRICK_CLS_MIXED or the per-view CLAMP bit mask (0 = SKIP);
-// *frus = per-view "certainly inside the image" bits (meaningful when the result is not MIXED).
-// All control flow is uniform across the lanes of `ctx`.
+// Classify brick (bxs,by,bz) (bxs slab-local).  All control flow is uniform across the lanes of `ctx`.
 template <class Ctx>
-DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, const uint32_t* brick_pairs,
-                           const float* region_rec, int nby, int nbz, int bxs, int by, int bz, int* frus, const Ctx ctx) {
-    *frus = 0;
+DFB_HDN BrickClass brick_classify(const ProjParams& P, const uint16_t* brick_nodes, const uint8_t* brick_count, const uint32_t* brick_pairs,
+                                  const float* region_rec, int nby, int nbz, int bxs, int by, int bz, const Ctx ctx) {
     const int xlo = P.x0 + bxs * BRICK_X, ylo = by * BRICK_Y, zlo = bz * BRICK_Z;
     const int xhi = (xlo + BRICK_X - 1 < P.x1 - 1) ? xlo + BRICK_X - 1 : P.x1 - 1;
     const int yhi = (ylo + BRICK_Y - 1 < P.ry - 1) ? ylo + BRICK_Y - 1 : P.ry - 1;
@@ -288,8 +292,9 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
         const float* rr = region_rec + (((size_t)(bxs * BRICK_X / REGION_X) * nry + by * BRICK_Y / REGION_Y) * nrz + bz * BRICK_Z / REGION_Z) * REGION_REC_FLOATS;
         if (rr[15] > 1.5f) {           // the region as a whole is already SKIP / CLAMP
             const int code = (int)rr[15] - 2;
-            *frus = code >> 8;
-            return code & 0xff;
+            BrickClass r;
+            r.clamp = code & 0xff; r.frus = code >> 8; r.mixed = 0; r.cls = r.clamp;
+            return r;
         }
         if (rr[15] > 0.5f) {
             region_box(rr, c, h, P.coord_mag, bx);
@@ -302,7 +307,7 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
     } else {
         const size_t b = ((size_t)bxs * nby + by) * nbz + bz;
         const int cnt = brick_count[b];
-        if (cnt == 0 || cnt > BRICK_MAXC) return DFB_MIXED(1);
+        if (cnt == 0 || cnt > BRICK_MAXC) return brick_class_all_mixed(P.n_views);
         for (int r = 0; r < 3; ++r) { bx.lo[r] = 3.0e38f; bx.hi[r] = -3.0e38f; }
         const uint16_t* ids = brick_nodes + b * BRICK_MAXC;
         bool bad = false;
@@ -356,7 +361,7 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
                 box_extend_affine(Ap, 0.5f / ip, c, h, bx);
             }
         }
-        if (ctx.any(bad)) return DFB_MIXED(2);
+        if (ctx.any(bad)) return brick_class_all_mixed(P.n_views);
         // reference-side rounding of p' (Q3: float32 cast) and float64 noise; polarisation cancellation slack
         for (int r = 0; r < 3; ++r) {
             const float m = 2e-3f + 2e-6f * P.coord_mag;
@@ -364,7 +369,7 @@ DFB_HDN int brick_classify(const ProjParams& P, const uint16_t* brick_nodes, con
             bx.hi[r] = ctx.rmax(bx.hi[r]) + m;
         }
     }
-    return box_classify_views(P, bx, BRICK_MAX_RECT, frus, ctx);
+    return box_classify_views(P, bx, BRICK_MAX_RECT, ctx);
 }
 
 }  // namespace dfb

@@ -251,8 +251,11 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
 // fast classification of a voxel for a2/a3.  Returns CLS_UNCERTAIN, or CLS_SKIP/CLS_CLAMP-style result:
 // *mask gets the per-view clamp bits (all certain), *frus the per-view frustum bits.
 // ONEVIEW: n_views == 1 known at compile time (the view record is then addressed with immediate offsets)
+// views / m0 / f0: a MIXED brick hands over the views its box test left open (bit mask) and the CLAMP / frustum bits of the
+// views it settled; only the open views are evaluated here.  Defaults = every view open.
 template <int KMAX, bool EXACTK = false, bool ONEVIEW = false>
-DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus) {
+DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus,
+                                     int views = 0xff, int m0 = 0, int f0 = 0) {
     float pw[3];
     float e;
     if (P.rigid) {
@@ -263,10 +266,11 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
         if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin, EXACTK)) return CLS_UNCERTAIN;
         e = pos_err_bound(P.coord_mag, amin);
     }
-    int m = 0, f = 0;
+    int m = m0, f = f0;
     const int nv = ONEVIEW ? 1 : P.n_views;
 #pragma unroll 1
     for (int vi = 0; vi < nv; ++vi) {
+        if (!ONEVIEW && !((views >> vi) & 1)) continue;
         const ViewFast& V = P.vf[ONEVIEW ? 0 : vi];
         const float pu = V.P[0] * pw[0] + V.P[1] * pw[1] + V.P[2] * pw[2] + V.P[3];
         const float pv = V.P[4] * pw[0] + V.P[5] * pw[1] + V.P[6] * pw[2] + V.P[7];

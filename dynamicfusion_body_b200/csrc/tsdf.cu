@@ -319,13 +319,13 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const __grid_constan
         for (int t = 0; t < 12; ++t) rr[t] = Pref[t];
         for (int r = 0; r < 3; ++r) rr[12 + r] = fmaxf(fmaxf(red[0][r], red[1][r]), fmaxf(red[2][r], red[3][r]));
         const bool valid = bad_s == 0;
-        int cls = BRICK_CLS_MIXED, fr = 0;
+        BrickClass rc = brick_class_all_mixed(P.n_views);
         if (valid) {
             Box3 bx;
             region_box(rr, c, h, P.coord_mag, bx);
-            cls = box_classify_views(P, bx, REGION_MAX_RECT, &fr, WarpCtx());
+            rc = box_classify_views(P, bx, REGION_MAX_RECT, WarpCtx());
         }
-        rr[15] = region_code(valid, cls, fr);
+        rr[15] = region_code(valid, rc);
         if (threadIdx.x < REGION_REC_FLOATS) out[threadIdx.x] = rr[threadIdx.x];
     }
 }
@@ -340,14 +340,17 @@ __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_consta
     const int gl = threadIdx.x & (CLASSIFY_G - 1);
     const int ngroups = (gridDim.x * blockDim.x) / CLASSIFY_G;
     for (int b = (blockIdx.x * blockDim.x + threadIdx.x) / CLASSIFY_G; b < nb; b += ngroups) {
-        int bxs, by, bz, fr = 0;
+        int bxs, by, bz;
         brick_thread_coords(b, nby, nbz, bxs, by, bz);
-        const int cls = brick_classify(P, brick_nodes, brick_count, brick_pairs, region_rec, nby, nbz, bxs, by, bz, &fr, GroupCtx<CLASSIFY_G>());
+        const BrickClass bc = brick_classify(P, brick_nodes, brick_count, brick_pairs, region_rec, nby, nbz, bxs, by, bz, GroupCtx<CLASSIFY_G>());
         if (gl == 0) {
-            cls_out[b] = (uint8_t)cls;
-            cls_out[nb + b] = (uint8_t)fr;
-            if (cls == BRICK_CLS_MIXED) mixed_list[atomicAdd(P.counters + 3, 1u)] = brick_pack(bxs, by, bz);
-            else if (cls != 0 || (P.frustum_out != nullptr && fr != 0)) stream_list[atomicAdd(P.counters + 2, 1u)] = brick_pack(bxs, by, bz);
+            // four planes of nb bytes: class (0xFF = MIXED), frustum bits, open views, CLAMP bits of the settled views
+            cls_out[b] = (uint8_t)bc.cls;
+            cls_out[nb + b] = (uint8_t)bc.frus;
+            cls_out[2 * nb + b] = (uint8_t)bc.mixed;
+            cls_out[3 * nb + b] = (uint8_t)bc.clamp;
+            if (bc.mixed) mixed_list[atomicAdd(P.counters + 3, 1u)] = brick_pack(bxs, by, bz);
+            else if (bc.clamp != 0 || (P.frustum_out != nullptr && bc.frus != 0)) stream_list[atomicAdd(P.counters + 2, 1u)] = brick_pack(bxs, by, bz);
         }
     }
 }
@@ -396,7 +399,8 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass).
 // Edge bricks (cut by the volume boundary, or rz not a multiple of 4): one guarded voxel at a time.
 template <int KMAX, bool EXACTK, bool ONEVIEW>
-__device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc) {
+__device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc, int views, int m0,
+                                                 int f0) {
     const bool want_masks = P.mask_out != nullptr || P.frustum_out != nullptr;
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
@@ -408,7 +412,7 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
         if (in) {
             uint16_t ids[KMAX];
             if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
-            cls = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f);
+            cls = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
         }
         push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
         if (!in || cls == CLS_UNCERTAIN) continue;
@@ -430,7 +434,8 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
 // 16-byte kNN loads, all issued before the arithmetic; the four classifications are independent instruction streams
 // for the scheduler, and the warp reserves its work-list slots with one atomic.
 template <int KMAX, bool EXACTK, bool ONEVIEW>
-__device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc) {
+__device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc, int views, int m0,
+                                                 int f0) {
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const size_t i0 = ((size_t)xs * P.ry + y) * P.rz + z0;
     const float4 v4 = *reinterpret_cast<const float4*>(P.tsdf + i0);
@@ -456,7 +461,7 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         m[q] = 0; f[q] = 0;
-        cls[q] = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q]);
+        cls[q] = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q], views, m0, f0);
     }
     // work list: one reservation per warp for the four voxels of every lane.  (Measured and dropped: CTA-level
     // aggregation through shared memory, and prefetch.global.L2 of the next brick's v / w / kNN lines -- neither the
@@ -505,12 +510,18 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
 }
 
 template <int KMAX, bool EXACTK, bool ONEVIEW>
-__device__ __forceinline__ void mixed_brick(const ProjParams& P, uint32_t entry, int dx, int dy, int dz, float sc) {
+__device__ __forceinline__ void mixed_brick(const ProjParams& P, int nb, int nby, int nbz, const uint8_t* cls, uint32_t entry, int dx, int dy, int dz,
+                                            float sc) {
     int bxs, by, bz;
     brick_unpack(entry, bxs, by, bz);
+    int views = 0xff, m0 = 0, f0 = 0;
+    if (!ONEVIEW) {   // with several views the brick's box test has usually settled most of them
+        const int b = (bxs * nby + by) * nbz + bz;
+        f0 = cls[nb + b]; views = cls[2 * nb + b]; m0 = cls[3 * nb + b];
+    }
     const bool full = (P.rz & 3) == 0 && (bxs + 1) * BRICK_X <= P.x1 - P.x0 && (by + 1) * BRICK_Y <= P.ry && (bz + 1) * BRICK_Z <= P.rz;
-    if (full) mixed_brick_full<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc);
-    else mixed_brick_edge<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc);
+    if (full) mixed_brick_full<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0);
+    else mixed_brick_edge<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0);
 }
 
 __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
@@ -524,11 +535,11 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
 
 template <int KMAX, bool EXACTK, bool ONEVIEW>
 __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
-                                                          const uint32_t* list) {
+                                                          const uint8_t* cls, const uint32_t* list) {
     const uint32_t count = P.counters[3];
     int dx, dy, dz;
     brick_lane(threadIdx.x, dx, dy, dz);
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, list[t], dx, dy, dz, (float)P.scale);
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, nbx * nby * nbz, nby, nbz, cls, list[t], dx, dy, dz, (float)P.scale);
 }
 
 // Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
@@ -551,7 +562,7 @@ __global__ void DFB_UPDATE_BOUNDS brick_update_kernel(const __grid_constant__ Pr
     const float sc = (float)P.scale;
     const bool vec = (P.rz & 3) == 0;
     for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
-        if (t < cnt_m) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, mixed_list[t], dx, dy, dz, sc);
+        if (t < cnt_m) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, nb, nby, nbz, cls, mixed_list[t], dx, dy, dz, sc);
         const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
         for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
     }
@@ -783,7 +794,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
                 DFB_LAUNCH_CHECK("brick_stream_kernel");
             } else if (do_mixed) {
-                DFB_BRICK_DISPATCH(brick_mixed_kernel, P, nbx, nby, nbz, mixed_list);
+                DFB_BRICK_DISPATCH(brick_mixed_kernel, P, nbx, nby, nbz, B.cls, mixed_list);
                 DFB_LAUNCH_CHECK("brick_mixed_kernel");
             }
         } else {

@@ -46,7 +46,7 @@ class Workspace:
         self.list = torch.empty(self.capacity, dtype=torch.int32, device=device)
         self.counters = torch.zeros(8, dtype=torch.int32, device=device)
         self.n_bricks = int(n_bricks)
-        self.brick_cls = torch.zeros(2 * self.n_bricks, dtype=torch.uint8, device=device) if n_bricks else None
+        self.brick_cls = torch.zeros(4 * self.n_bricks, dtype=torch.uint8, device=device) if n_bricks else None
         self.brick_lists = torch.zeros(2 * self.n_bricks, dtype=torch.int32, device=device) if n_bricks else None
 
     def struct(self, use_bricks=True):

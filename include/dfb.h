@@ -90,7 +90,7 @@ typedef struct dfb_workspace {
                            counters[1] = voxels the exact pass processed, counters[2] = bricks streamed (CLAMP),
                            counters[3] = bricks evaluated per voxel (MIXED) */
     /* optional (NULL = no brick culling), n_bricks = dfb_brick_count(x1-x0, ry, rz): */
-    uint8_t* brick_cls;    /* device [2*n_bricks] */
+    uint8_t* brick_cls;    /* device [4*n_bricks]: class (0xFF = MIXED), frustum bits, open views, settled CLAMP bits */
     uint32_t* brick_lists; /* device [2*n_bricks] */
 } dfb_workspace;
 

@@ -146,14 +146,14 @@ static std::vector<float> build_region_records(const ProjParams& P) {
                     if (!region_pair_bound(q[pr.first].data(), q[pr.second].data(), pr.first == pr.second, Pref, c, h, dev)) bad = true;
                 for (int t = 0; t < 12; ++t) out[t] = Pref[t];
                 for (int r = 0; r < 3; ++r) out[12 + r] = dev[r];
-                int rcls = BRICK_CLS_MIXED, rfr = 0;
+                BrickClass rc = brick_class_all_mixed(P.n_views);
                 if (!bad) {
                     Box3 bx;
                     region_box(out, c, h, P.coord_mag, bx);
-                    rcls = box_classify_views(P, bx, REGION_MAX_RECT, &rfr, SerialCtx());
+                    rc = box_classify_views(P, bx, REGION_MAX_RECT, SerialCtx());
                 }
-                out[15] = region_code(!bad, rcls, rfr);
-                if (!bad && rcls != BRICK_CLS_MIXED) ++g_region_resolved;
+                out[15] = region_code(!bad, rc);
+                if (!bad && !rc.mixed) ++g_region_resolved;
                 if (!bad) { ++nvalid; g_region_dmax = std::max(g_region_dmax, std::max(dev[0], std::max(dev[1], dev[2]))); }
             }
     g_region_valid = (float)nvalid / (float)((size_t)nrx * nry * nrz);
@@ -166,7 +166,7 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
     uint32_t n_unc = 0;
     const bool bricks = mode == DFB_MODE_HYBRID && (P.rigid || (g_brick_nodes && g_brick_count)) && g_brick_cls_vox;
     const int nby = (P.ry + BRICK_Y - 1) / BRICK_Y, nbz = (P.rz + BRICK_Z - 1) / BRICK_Z;
-    std::vector<int> brick_cache((size_t)((P.x1 - P.x0 + BRICK_X - 1) / BRICK_X) * nby * nbz, -1);
+    std::vector<BrickClass> brick_cache((size_t)((P.x1 - P.x0 + BRICK_X - 1) / BRICK_X) * nby * nbz, BrickClass{-1, 0, 0, 0});
     std::vector<float> region_rec;
     if (bricks && !P.rigid && g_use_regions) region_rec = build_region_records(P);
     const float* rrec = region_rec.empty() ? nullptr : region_rec.data();
@@ -174,20 +174,15 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
         for (int y = 0; y < P.ry; ++y)
             for (int z = 0; z < P.rz; ++z) {
                 const size_t i = xs * plane + (size_t)y * P.rz + z;
+                int views = 0xff, m0 = 0, f0 = 0;   // what the brick's box test hands to the per-voxel tier
                 if (bricks) {
                     const size_t bid = ((size_t)(xs / BRICK_X) * nby + y / BRICK_Y) * nbz + z / BRICK_Z;
-                    if (brick_cache[bid] < 0) {
-                        int fr0 = 0;
-                        const int c0 = brick_classify(P, g_brick_nodes, g_brick_count, g_brick_pairs, rrec, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, &fr0, SerialCtx());
-                        brick_cache[bid] = c0 | (fr0 << 8);
-                    }
-                    const int bc = brick_cache[bid] & 0xff, fr = brick_cache[bid] >> 8;
-#if defined(DFB_BRICK_DEBUG)
-                    g_brick_cls_vox[i] = (uint8_t)(bc == BRICK_CLS_MIXED ? 200 - (int8_t)(brick_cache[bid] >> 8) : bc);
-#else
+                    if (brick_cache[bid].cls < 0)
+                        brick_cache[bid] = brick_classify(P, g_brick_nodes, g_brick_count, g_brick_pairs, rrec, nby, nbz, xs / BRICK_X, y / BRICK_Y, z / BRICK_Z, SerialCtx());
+                    const BrickClass& B = brick_cache[bid];
+                    const int bc = B.cls, fr = B.frus;
                     g_brick_cls_vox[i] = (uint8_t)bc;
-#endif
-                    if (bc != BRICK_CLS_MIXED) {
+                    if (!B.mixed) {
                         if (bc) {
                             float v = P.tsdf[i], w = P.weight[i];
                             for (int vi = 0; vi < P.n_views; ++vi)
@@ -199,11 +194,12 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                         if (cls_out) cls_out[i] = bc ? CLS_CLAMP : CLS_SKIP;
                         continue;
                     }
+                    views = B.mixed; m0 = B.clamp; f0 = B.frus;
                 }
                 uint16_t ids[KMAX] = {0};
                 for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
                 int m = 0, f = 0, cls = CLS_UNCERTAIN;
-                if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
+                if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
                 if (cls_out) cls_out[i] = (uint8_t)cls;
                 float v = P.tsdf[i], w = P.weight[i];
                 if (cls == CLS_UNCERTAIN) {
