@@ -186,13 +186,16 @@ __global__ void __launch_bounds__(256) normal_eq_data_kernel(const __grid_consta
                 if (a >= P.k) break;
                 const int ia = __shfl_sync(0xffffffffu, ids[a], src);
                 const double wa = __shfl_sync(0xffffffffu, wts[a], src);
+                // block (a,b) and block (b,a) receive the SAME 8x8 matrix w_a w_b om g g^T: only the block in the upper
+                // triangle of the node graph is accumulated here (10 of the 16 bursts at k = 4), mirror_lower_kernel copies it
 #pragma unroll
                 for (int b = 0; b < DFB_MAX_K; ++b) {
                     if (b >= P.k) break;
+                    if (b < a) continue;
                     const int ib = __shfl_sync(0xffffffffu, ids[b], src);
                     const double wb = __shfl_sync(0xffffffffu, wts[b], src);
-                    const int slot = find_slot(row_ptr, col_idx, ia, ib);
-                    const double cf = s_om * wa * wb;
+                    const int slot = find_slot(row_ptr, col_idx, ia < ib ? ia : ib, ia < ib ? ib : ia);
+                    const double cf = s_om * wa * wb * ((b != a && ia == ib) ? 2.0 : 1.0);
                     atomicAdd(H + (size_t)slot * 64 + lane, cf * e0);
                     atomicAdd(H + (size_t)slot * 64 + 32 + lane, cf * e1);
                 }
@@ -202,6 +205,24 @@ __global__ void __launch_bounds__(256) normal_eq_data_kernel(const __grid_consta
     }
     for (int o = 16; o > 0; o >>= 1) { c_rob += __shfl_xor_sync(0xffffffffu, c_rob, o); c_l2 += __shfl_xor_sync(0xffffffffu, c_l2, o); }
     if (lane == 0 && (c_rob != 0.0 || c_l2 != 0.0)) { atomicAdd(cost, c_rob); atomicAdd(cost + 1, c_l2); }
+}
+
+// lower-triangle blocks of the data term = their upper-triangle twins (see normal_eq_data_kernel); 64 threads per block
+__global__ void mirror_lower_kernel(const int32_t* row_ptr, const int32_t* col_idx, int n, double* H) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = t >> 6;
+    const int e = (int)(t & 63);
+    if (s >= row_ptr[n]) return;
+    const int j = col_idx[s];
+    // row of slot s: largest i with row_ptr[i] <= s
+    int lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row_ptr[mid] <= s) lo = mid; else hi = mid;
+    }
+    const int i = lo;
+    if (j >= i) return;
+    H[(size_t)s * 64 + e] = H[(size_t)find_slot(row_ptr, col_idx, j, i) * 64 + e];
 }
 
 __device__ __forceinline__ void add_block(double* Hb, const double A[3][8], const double B[3][8], const double* om) {
@@ -684,6 +705,8 @@ extern "C" int dfb_gn_normal_eq(const dfb_gn_problem* prob, const double* x, con
     if (P.n_vert > 0) {
         normal_eq_data_kernel<<<blocks_for(P.n_vert, 256, 148 * 16), 256, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
         DFB_LAUNCH_CHECK("normal_eq_data_kernel");
+        mirror_lower_kernel<<<(unsigned)((nnzb * 64 + 255) / 256), 256, 0, s>>>(row_ptr, col_idx, P.n_nodes, H);
+        DFB_LAUNCH_CHECK("mirror_lower_kernel");
     }
     normal_eq_reg_kernel<<<blocks_for((int64_t)P.n_nodes * P.k, 64), 64, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
     DFB_LAUNCH_CHECK("normal_eq_reg_kernel");

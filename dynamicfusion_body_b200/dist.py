@@ -42,6 +42,24 @@ def broadcast_frame(depths, node_dq, lw=None, src=0, group=None):
     return depths, node_dq, lw
 
 
+class FramePacket:
+    """One frame (global rigid dq, depth views, node transforms) in ONE contiguous float32 device buffer, so that the
+    per-frame broadcast root -> all is a single collective (two or three small NCCL launches cost more than the
+    1.3 MB they move).  `lw` (8,) float64, `depths` (V, rows, cols) float32 and `node_dq` (N, 8) float32 are views."""
+
+    def __init__(self, n_views, rows, cols, n_nodes, device):
+        nd = n_views * rows * cols
+        self.flat = torch.zeros(16 + nd + 8 * n_nodes, dtype=torch.float32, device=device)
+        self.lw = self.flat[:16].view(torch.float64)
+        self.depths = self.flat[16:16 + nd].view(n_views, rows, cols)
+        self.node_dq = self.flat[16 + nd:].view(n_nodes, 8)
+
+    def broadcast(self, src=0, group=None):
+        if is_dist():
+            dist.broadcast(self.flat, src, group=group)
+        return self
+
+
 def allreduce_normal_equations(H, g, cost, group=None):
     """Sum the block-sparse normal equations over ranks (one flat buffer -> one collective)."""
     if not is_dist():

@@ -134,3 +134,23 @@ def _gn_job(rank, world):
 def test_sharded_normal_equations_allreduce():
     out = _run(_gn_job)
     assert out[0] is True and out[1] is True
+
+
+def _packet_job(rank, world):
+    """FramePacket: one collective carries lw (float64), the depth views and the node transforms."""
+    from dynamicfusion_body_b200 import dist as ddist
+    rng = np.random.default_rng(7)
+    lw = rng.normal(size=8)
+    depths = rng.normal(size=(3, 12, 16)).astype(np.float32)
+    dq = rng.normal(size=(37, 8)).astype(np.float32)
+    pk = ddist.FramePacket(3, 12, 16, 37, torch.device("cpu"))
+    assert pk.depths.is_contiguous() and pk.node_dq.is_contiguous() and pk.lw.dtype == torch.float64
+    if rank == 0:
+        pk.lw.copy_(torch.from_numpy(lw)); pk.depths.copy_(torch.from_numpy(depths)); pk.node_dq.copy_(torch.from_numpy(dq))
+    pk.broadcast()
+    return bool(np.array_equal(pk.lw.numpy(), lw) and np.array_equal(pk.depths.numpy(), depths) and np.array_equal(pk.node_dq.numpy(), dq))
+
+
+def test_frame_packet_broadcast():
+    out = _run(_packet_job)
+    assert out[0] and out[1]
