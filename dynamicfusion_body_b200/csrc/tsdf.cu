@@ -254,22 +254,28 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const __grid_constan
     __shared__ float q[REGION_MAXC][8];
     __shared__ float red[4][3];
     __shared__ int bad_s;
-    const int reg = blockIdx.x;
+    __shared__ unsigned ref_key;
+    __shared__ int pre[REGION_PAIR_WORDS + 1];
+    __shared__ uint16_t plist[REGION_MAXC * (REGION_MAXC + 1) / 2];
+    // grid = (nrz, nry, nrx): no index division
+    const int rzi = blockIdx.x, ryi = blockIdx.y, rxi = blockIdx.z;
+    const int reg = (rxi * nry + ryi) * nrz + rzi;
     float* out = region_rec + (size_t)reg * REGION_REC_FLOATS;
     const int cnt = region_count[reg];
     if (cnt == 0 || cnt > REGION_MAXC) {
         if (threadIdx.x < REGION_REC_FLOATS) out[threadIdx.x] = 0.f;
         return;
     }
-    const int rzi = reg % nrz, ryi = (reg / nrz) % nry, rxi = reg / (nrz * nry);
     const int xlo = rxi * REGION_X, ylo = ryi * REGION_Y, zlo = rzi * REGION_Z;
     const int xhi = min(xlo + REGION_X, sx) - 1, yhi = min(ylo + REGION_Y, ry) - 1, zhi = min(zlo + REGION_Z, rz) - 1;
     const float c[3] = {0.5f * (xlo + xhi) + (float)x0, 0.5f * (ylo + yhi), 0.5f * (zlo + zhi)};
     const float h[3] = {0.5f * (xhi - xlo), 0.5f * (yhi - ylo), 0.5f * (zhi - zlo)};
-    if (threadIdx.x == 0) bad_s = 0;
+    if (threadIdx.x == 0) { bad_s = 0; ref_key = 0xffffffffu; }
     __syncthreads();
     bool bad = false;
     const uint16_t* ids = region_nodes + (size_t)reg * REGION_MAXC;
+    const int npairs = cnt * (cnt + 1) / 2, nwords = (npairs + 31) >> 5;
+    const uint32_t* pm = region_pairs + (size_t)reg * REGION_PAIR_WORDS;
     if (threadIdx.x < cnt) {
         const int id = ids[threadIdx.x];
         const float4 r0 = node_rec[3 * (size_t)id], r1 = node_rec[3 * (size_t)id + 1], r2 = node_rec[3 * (size_t)id + 2];
@@ -278,14 +284,43 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const __grid_constan
         // every blend weight of every voxel must be a normal float32 in the reference (see dfb_voxel.h blend_warp_fast)
         const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
         if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f)) bad = true;
+        // reference map = diagonal map of the region's lowest node id (the cached list order depends on atomics)
+        atomicMin(&ref_key, ((unsigned)id << 8) | threadIdx.x);
+    }
+    if (threadIdx.x >= 96) {
+        // warp 3: exclusive prefix of the pair mask's popcounts, so that the pairs that do co-occur can be dealt out densely
+        const int lane = threadIdx.x & 31;
+        int carry = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int w = w0 + lane;
+            uint32_t m = w < nwords ? pm[w] : 0u;
+            if (w == nwords - 1 && (npairs & 31)) m &= (1u << (npairs & 31)) - 1u;
+            const int cntw = __popc(m);
+            int inc = cntw;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (w < nwords) pre[w] = carry + inc - cntw;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) pre[nwords] = carry;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < nwords; w += blockDim.x) {
+        uint32_t m = pm[w];
+        if (w == nwords - 1 && (npairs & 31)) m &= (1u << (npairs & 31)) - 1u;
+        int o = pre[w];
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            plist[o++] = (uint16_t)(32 * w + bit);
+        }
     }
     __syncthreads();
     float Pref[12], n0 = 0.f;
     {
-        // reference map = diagonal map of the region's lowest node id (the cached list order depends on atomics)
-        int ref = 0;
-        for (int t = 1; t < cnt; ++t)
-            if (ids[t] < ids[ref]) ref = t;
+        const int ref = (int)(ref_key & 0xffu);
         float q0[8];
         for (int t = 0; t < 8; ++t) { q0[t] = q[ref][t]; n0 += q0[t] * q0[t]; }
         dq_affine_f(q0, Pref);
@@ -294,16 +329,15 @@ __global__ void __launch_bounds__(128) region_bounds_kernel(const __grid_constan
         if (!(n0 > 1e-20f)) bad = true;
     }
     float dev[3] = {0.f, 0.f, 0.f};
-    const int npairs = cnt * (cnt + 1) / 2;
-    const uint32_t* pm = region_pairs + (size_t)reg * REGION_PAIR_WORDS;
-    for (int p = threadIdx.x; p < npairs; p += blockDim.x) {
-        if (!((pm[p >> 5] >> (p & 31)) & 1u)) continue;
+    const int nset = pre[nwords];
+    for (int t = threadIdx.x; t < nset; t += blockDim.x) {
+        const int p = plist[t];
         int i = (int)((sqrtf(8.f * (float)p + 1.f) - 1.f) * 0.5f);
         while (i * (i + 1) / 2 > p) --i;
         while ((i + 1) * (i + 2) / 2 <= p) ++i;
         const int j = p - i * (i + 1) / 2;
         float qi[8], qj[8];
-        for (int t = 0; t < 8; ++t) { qi[t] = q[i][t]; qj[t] = q[j][t]; }
+        for (int t2 = 0; t2 < 8; ++t2) { qi[t2] = q[i][t2]; qj[t2] = q[j][t2]; }
         if (!region_pair_bound(qi, qj, i == j, Pref, c, h, dev)) bad = true;
     }
     if (bad) atomicOr(&bad_s, 1);
@@ -339,9 +373,18 @@ __global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_consta
     const int nb = nbx * nby * nbz;
     const int gl = threadIdx.x & (CLASSIFY_G - 1);
     const int ngroups = (gridDim.x * blockDim.x) / CLASSIFY_G;
-    for (int b = (blockIdx.x * blockDim.x + threadIdx.x) / CLASSIFY_G; b < nb; b += ngroups) {
-        int bxs, by, bz;
-        brick_thread_coords(b, nby, nbz, bxs, by, bz);
+    // bricks are visited region by region (a region = 4 x 4 x 1 bricks): the groups of a warp then share their region, and a
+    // warp whose region was settled as a whole leaves together instead of idling next to groups that still have work
+    constexpr int RBX = REGION_X / BRICK_X, RBY = REGION_Y / BRICK_Y;
+    static_assert(REGION_Z == BRICK_Z && RBX * RBY == 16, "region = 4 x 4 x 1 bricks");
+    const int nrx = (nbx + RBX - 1) / RBX, nry = (nby + RBY - 1) / RBY;
+    const int total = nrx * nry * nbz * 16;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) / CLASSIFY_G; g < total; g += ngroups) {
+        const int reg = g >> 4, local = g & 15;
+        const int bz = reg % nbz, t = reg / nbz;
+        const int bxs = (t / nry) * RBX + (local >> 2), by = (t % nry) * RBY + (local & 3);
+        if (bxs >= nbx || by >= nby) continue;
+        const int b = (bxs * nby + by) * nbz + bz;
         const BrickClass bc = brick_classify(P, brick_nodes, brick_count, brick_pairs, region_rec, nby, nbz, bxs, by, bz, GroupCtx<CLASSIFY_G>());
         if (gl == 0) {
             // four planes of nb bytes: class (0xFF = MIXED), frustum bits, open views, CLAMP bits of the settled views
@@ -582,10 +625,17 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
     uint32_t done = 0;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
         const size_t i = use_list ? (size_t)P.list[t] : t;
-        const int xs = (int)(i / plane);
-        const size_t rem = i - (size_t)xs * plane;
-        const int y = (int)(rem / P.rz);
-        const int z = (int)(rem - (size_t)y * P.rz);
+        int xs, y, z;
+        if (nvox <= 0xffffffffull) {   // 32-bit index arithmetic (the 64-bit divisions were 5 % of the kernel's instructions)
+            const uint32_t i32 = (uint32_t)i, plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
+            const uint32_t xq = i32 / plane32, rem = i32 - xq * plane32, yq = rem / rz32;
+            xs = (int)xq; y = (int)yq; z = (int)(rem - yq * rz32);
+        } else {
+            xs = (int)(i / plane);
+            const size_t rem = i - (size_t)xs * plane;
+            y = (int)(rem / P.rz);
+            z = (int)(rem - (size_t)y * P.rz);
+        }
         uint16_t ids[KMAX];
         if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
         if (!use_list && !all_mode) {
@@ -759,7 +809,7 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
                 rrec = B.rrec;
                 if (do_classify) {
                     const int nrx = (P.x1 - P.x0 + REGION_X - 1) / REGION_X, nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
-                    region_bounds_kernel<<<nrx * nry * nrz, 128, 0, s>>>(P, B.rnodes, B.rcount, B.rpairs, nry, nrz, B.rrec);
+                    region_bounds_kernel<<<dim3(nrz, nry, nrx), 128, 0, s>>>(P, B.rnodes, B.rcount, B.rpairs, nry, nrz, B.rrec);
                     DFB_LAUNCH_CHECK("region_bounds_kernel");
                 }
             }
@@ -768,9 +818,10 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
             const int grid = nb < 148 * 16 ? nb : 148 * 16;
             if (do_classify) {
                 static int G = 0;
-                if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : (rrec ? 4 : 8); }
+                if (G == 0) { const char* e = getenv("DFB_CLASSIFY_G"); G = e ? atoi(e) : 8; }
                 const int per_cta = 128 / G;
-                const int cgrid = (nb + per_cta - 1) / per_cta < 148 * 32 ? (nb + per_cta - 1) / per_cta : 148 * 32;
+                const int nb_pad = ((nbx + 3) / 4) * ((nby + 3) / 4) * nbz * 16;   // region-major enumeration (edge regions padded)
+                const int cgrid = (nb_pad + per_cta - 1) / per_cta < 148 * 32 ? (nb_pad + per_cta - 1) / per_cta : 148 * 32;
                 if (G == 1) brick_classify_kernel<1><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 else if (G == 2) brick_classify_kernel<2><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
                 else if (G == 4) brick_classify_kernel<4><<<cgrid, 128, 0, s>>>(P, B.nodes, B.count, B.pairs, rrec, nbx, nby, nbz, B.cls, stream_list, mixed_list);
