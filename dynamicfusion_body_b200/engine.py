@@ -59,10 +59,32 @@ class Workspace:
             s.brick_lists = self.brick_lists.data_ptr()
         return s
 
-    def stats(self):
-        c = self.counters.cpu().numpy().astype(np.int64) & 0xffffffff
+    def _decode(self, c):
+        c = c.astype(np.int64) & 0xffffffff
         return {"deferred": int(c[0]), "exact_processed": int(c[1]), "bricks_streamed": int(c[2]), "bricks_mixed": int(c[3]),
                 "bricks": self.n_bricks}
+
+    def stats(self):
+        return self._decode(self.counters.cpu().numpy())
+
+    def stats_async(self):
+        """Start the 32-byte device->host read of the counters on the current stream (pinned buffer) and return a handle
+        whose .result() waits for it: a streaming caller reads frame t's counters while frame t+1 is already queued."""
+        if not hasattr(self, "_pinned"):
+            self._pinned = [torch.empty(8, dtype=torch.int32).pin_memory() for _ in range(4)]
+            self._pin_i = 0
+        buf = self._pinned[self._pin_i % len(self._pinned)]
+        self._pin_i += 1
+        buf.copy_(self.counters, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ws = self
+
+        class _Pending:
+            def result(self):
+                ev.synchronize()
+                return ws._decode(buf.numpy().copy())
+        return _Pending()
 
 
 class DeviceVolume:

@@ -145,6 +145,10 @@ class _FusionBase:
         s = self._vol.workspace.stats()
         return s
 
+    def frame_stats_async(self):
+        """Same counters without stalling the stream: returns a handle, .result() waits for the copy."""
+        return self._vol.workspace.stats_async()
+
     # ---- warp helpers (core/fusion.py:502-551), evaluated on the device -------------------------
     def _lookup(self, pos, k):
         return self._wf.knn_points(np.asarray(pos, dtype=np.float32).reshape(-1, 3), k).cpu().numpy()
