@@ -161,49 +161,52 @@ def run_ours(args):
     fus.build_knn()                                                  # once per graph revision, outside the timed region
     torch.cuda.synchronize()
 
-    packet = ddist.FramePacket(sc.depths.shape[0], sc.depths.shape[1], sc.depths.shape[2], sc.n_nodes, dev)
-    packet.depths.copy_(depth_dev)
-
-    def step_resident(i):
-        # rank 0 owns the sensor + warp field: this frame (depth + node transforms) goes to every rank in one NVLink broadcast
-        packet.node_dq.copy_(dq_dev[i % n_frames])
-        packet.broadcast()
-        fus.set_node_dqs(packet.node_dq)
-        fus.fuseFrame(packet.depths, extrinsics=sc.extrinsics)
-
-    # end to end: the depth frame of step t+1 is uploaded (pinned host -> device, copy stream) while step t computes -- sensor
-    # data does not depend on the fusion result -- into the other half of a double-buffered frame packet; the node transforms
-    # (which in the application come out of the solve against the model updated by step t) are uploaded inside step t+1; the
-    # 32-byte frame counters of step t are read on the host while step t+1 is already queued.
-    packets = [packet, ddist.FramePacket(sc.depths.shape[0], sc.depths.shape[1], sc.depths.shape[2], sc.n_nodes, dev)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    # Frames travel in double-buffered packets.  The depth views of step t+1 (sensor data: independent of the fusion result)
+    # are put into the other packet -- and, with several GPUs, broadcast from rank 0 over NVLink on a side stream with its own
+    # process group -- while step t computes; the node transforms (which in the application come out of the solve against the
+    # model updated by step t) are uploaded / broadcast inside their own step.
+    shape = sc.depths.shape
+    packets = [ddist.FramePacket(shape[0], shape[1], shape[2], sc.n_nodes, dev) for _ in range(2)]
+    side = torch.cuda.Stream(device=dev)
+    side_group = dist.new_group() if world > 1 else None
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     done = [torch.cuda.Event(), torch.cuda.Event()]
     pending = {"h": None}
 
-    def stage_depth(slot):
-        copy_stream.wait_event(done[slot])                            # the step that last read this packet has finished
-        with torch.cuda.stream(copy_stream):
-            packets[slot].depths.copy_(depth_host, non_blocking=True)
-            ready[slot].record(copy_stream)
+    def stage_depth(slot, src):
+        side.wait_event(done[slot])                                   # the step that last read this packet has finished
+        with torch.cuda.stream(side):
+            if rank == 0:
+                packets[slot].depths.copy_(src, non_blocking=True)    # pinned host (e2e) or device-resident frame
+            packets[slot].broadcast_depths(group=side_group)
+            ready[slot].record(side)
 
-    def e2e_begin():
-        done[0].record(); done[1].record()
-        stage_depth(0)
-
-    def step_e2e(i):
+    def run_step(i, depth_src, dq_src):
         slot = i & 1
         pk = packets[slot]
         torch.cuda.current_stream().wait_event(ready[slot])
-        pk.node_dq.copy_(dq_host[i % n_frames], non_blocking=True)
-        pk.broadcast()
+        if rank == 0:
+            pk.node_dq.copy_(dq_src[i % n_frames], non_blocking=True)
+        pk.broadcast_transforms()
         fus.set_node_dqs(pk.node_dq)
         fus.fuseFrame(pk.depths, extrinsics=sc.extrinsics)
-        h = fus.frame_stats_async()                                   # D2H of the per-frame counters (32 B)
         done[slot].record()
-        stage_depth(slot ^ 1)
+        stage_depth(slot ^ 1, depth_src)
+
+    def begin(depth_src):
+        def f():
+            done[0].record(); done[1].record()
+            stage_depth(0, depth_src)
+        return f
+
+    def step_resident(i):
+        run_step(i, depth_dev, dq_dev)
+
+    def step_e2e(i):
+        run_step(i, depth_host, dq_host)
+        h = fus.frame_stats_async()                                   # D2H of the per-frame counters (32 B) ...
         if pending["h"] is not None:
-            pending["h"].result()
+            pending["h"].result()                                     # ... read on the host while the next step is queued
         pending["h"] = h
 
     def e2e_end():
@@ -240,7 +243,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total = timed(step_resident, args.steps, args.warmup)
+    ms_total = timed(step_resident, args.steps, args.warmup, begin(depth_dev))
     # the K timed steps last only a few tens of ms; keep the same step running (untimed, identical count on every rank so
     # that the collectives match) until the 20 ms sampler has seen ~0.4 s of this load
     n_extra = max(0, int(400.0 / max(ms_total / args.steps, 1e-3)) - args.steps)
@@ -250,7 +253,7 @@ def run_ours(args):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), e2e_begin, e2e_end)
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), begin(depth_host), e2e_end)
     stats = fus.frame_stats()
 
     # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----

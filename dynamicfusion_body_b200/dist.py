@@ -43,20 +43,35 @@ def broadcast_frame(depths, node_dq, lw=None, src=0, group=None):
 
 
 class FramePacket:
-    """One frame (global rigid dq, depth views, node transforms) in ONE contiguous float32 device buffer, so that the
-    per-frame broadcast root -> all is a single collective (two or three small NCCL launches cost more than the
-    1.3 MB they move).  `lw` (8,) float64, `depths` (V, rows, cols) float32 and `node_dq` (N, 8) float32 are views."""
+    """One frame in ONE contiguous float32 device buffer: [depth views | global rigid dq | node transforms].  `depths`
+    (V, rows, cols) float32, `lw` (8,) float64 and `node_dq` (N, 8) float32 are views.  broadcast() sends everything in
+    a single collective (two or three small NCCL launches cost more than the 1.3 MB they move); broadcast_depths() /
+    broadcast_transforms() send the two halves separately, so that a streaming caller can ship the sensor data of frame
+    t+1 on a side stream (and its own process group) while frame t is being fused -- depth does not depend on the fusion
+    result, the transforms do."""
 
     def __init__(self, n_views, rows, cols, n_nodes, device):
         nd = n_views * rows * cols
-        self.flat = torch.zeros(16 + nd + 8 * n_nodes, dtype=torch.float32, device=device)
-        self.lw = self.flat[:16].view(torch.float64)
-        self.depths = self.flat[16:16 + nd].view(n_views, rows, cols)
-        self.node_dq = self.flat[16 + nd:].view(n_nodes, 8)
+        nd_pad = (nd + 3) // 4 * 4                      # keeps the float64 view 16-byte aligned
+        self.flat = torch.zeros(nd_pad + 16 + 8 * n_nodes, dtype=torch.float32, device=device)
+        self.depths = self.flat[:nd].view(n_views, rows, cols)
+        self.transforms = self.flat[nd_pad:]
+        self.lw = self.flat[nd_pad:nd_pad + 16].view(torch.float64)
+        self.node_dq = self.flat[nd_pad + 16:].view(n_nodes, 8)
 
     def broadcast(self, src=0, group=None):
         if is_dist():
             dist.broadcast(self.flat, src, group=group)
+        return self
+
+    def broadcast_depths(self, src=0, group=None):
+        if is_dist():
+            dist.broadcast(self.depths, src, group=group)
+        return self
+
+    def broadcast_transforms(self, src=0, group=None):
+        if is_dist():
+            dist.broadcast(self.transforms, src, group=group)
         return self
 
 

@@ -148,7 +148,16 @@ def _packet_job(rank, world):
     if rank == 0:
         pk.lw.copy_(torch.from_numpy(lw)); pk.depths.copy_(torch.from_numpy(depths)); pk.node_dq.copy_(torch.from_numpy(dq))
     pk.broadcast()
-    return bool(np.array_equal(pk.lw.numpy(), lw) and np.array_equal(pk.depths.numpy(), depths) and np.array_equal(pk.node_dq.numpy(), dq))
+    ok = bool(np.array_equal(pk.lw.numpy(), lw) and np.array_equal(pk.depths.numpy(), depths) and np.array_equal(pk.node_dq.numpy(), dq))
+    # the two halves separately (depth ahead of time on its own group, transforms inside the step)
+    pk2 = ddist.FramePacket(3, 12, 16, 37, torch.device("cpu"))
+    g2 = dist.new_group()
+    if rank == 0:
+        pk2.lw.copy_(torch.from_numpy(lw)); pk2.depths.copy_(torch.from_numpy(depths)); pk2.node_dq.copy_(torch.from_numpy(dq))
+    pk2.broadcast_depths(group=g2)
+    ok = ok and bool(np.array_equal(pk2.depths.numpy(), depths)) and (rank == 0 or not pk2.node_dq.numpy().any())
+    pk2.broadcast_transforms()
+    return ok and bool(np.array_equal(pk2.lw.numpy(), lw) and np.array_equal(pk2.node_dq.numpy(), dq))
 
 
 def test_frame_packet_broadcast():
