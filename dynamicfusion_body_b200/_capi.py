@@ -64,6 +64,11 @@ class GNProblem(C.Structure):
                 ("rw", C.c_double), ("huber", C.c_int), ("f_scale", C.c_double)]
 
 
+class PointGrid(C.Structure):
+    _fields_ = [("pts", C.c_void_p), ("n", C.c_int64), ("origin", C.c_double * 3), ("cell", C.c_double),
+                ("dims", C.c_int * 3), ("cell_start", C.c_void_p), ("order", C.c_void_p)]
+
+
 def declare(lib, prefix="dfb_", device=True):
     """Attach argtypes/restype for every entry point of include/dfb.h present in `lib`."""
     vp = C.c_void_p
@@ -92,6 +97,11 @@ def declare(lib, prefix="dfb_", device=True):
         "gn_normal_eq": ([C.POINTER(GNProblem), vp, vp, vp, C.c_int64, vp, vp, vp] + ([vp] if device else []), C.c_int),
         "gn_lw_normal_eq": ([C.POINTER(GNProblem), vp, c_f64p, vp, vp, vp] + ([vp] if device else []), C.c_int),
         "gn_solve_workspace_doubles": ([C.c_int], C.c_int64),
+        "point_grid_build": ([C.POINTER(PointGrid), vp, vp, vp, vp], C.c_int),
+        "point_grid_knn": ([C.POINTER(PointGrid), vp, C.c_int64, C.c_int, vp, vp, vp], C.c_int),
+        "corr_select": ([vp, vp, C.c_int64, vp, vp, C.c_int, vp, vp, vp], C.c_int),
+        "graph_unsupported": ([vp, C.c_int64, vp, C.c_int, vp, vp, vp, vp], C.c_int),
+        "graph_sample_rounds": ([C.POINTER(PointGrid), C.c_double, C.c_int, vp, vp, vp], C.c_int),
         "gn_solve": ([C.c_int, vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
@@ -133,4 +143,5 @@ EXPORTS = [
     "dfb_tsdf_update_projective", "dfb_tsdf_update_volume", "dfb_fuse_depth_rigid", "dfb_warp_points", "dfb_dq_blend_points",
     "dfb_gn_residuals", "dfb_gn_residuals_lw", "dfb_gn_pattern_rows", "dfb_gn_pattern_cols", "dfb_gn_normal_eq",
     "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",
+    "dfb_point_grid_build", "dfb_point_grid_knn", "dfb_corr_select", "dfb_graph_unsupported", "dfb_graph_sample_rounds",
 ]

@@ -334,3 +334,104 @@ def warp_points(wf, lw, pts, normals=None, idx=None, k=None):
     s = wf.struct(lw, None, k=k)
     _capi.check(_capi.lib().dfb_warp_points(_ptr(p), _ptr(n), p.shape[0], _ptr(idx), C.byref(s), _ptr(out), _ptr(outn), _stream()))
     return (out, outn) if n is not None else out
+
+
+# ---- point-set search, correspondences, graph maintenance (csrc/graph.cu) -----------------
+class PointGrid:
+    """Uniform search grid over a float32 point set on the device: the stand-in for the scipy KDTree the reference
+    builds over live / canonical surface vertices (core/fusion.py:204,255,308; core/fusion_dm.py:226).  Exact results
+    (float64 distances, ties by lower id); the cell size only affects speed."""
+
+    MAX_CELLS = 1 << 24
+
+    def __init__(self, pts, cell=None, device=None):
+        dev = _require_cuda(device)
+        self.device = dev
+        self.pts = _to_dev(pts, torch.float32, dev).reshape(-1, 3)
+        n = self.pts.shape[0]
+        if n:
+            lo = self.pts.amin(0).double().cpu().numpy()
+            hi = self.pts.amax(0).double().cpu().numpy()
+        else:
+            lo = hi = np.zeros(3)
+        ext = np.maximum(hi - lo, 1e-6)
+        if cell is None:
+            # surface samples: about sqrt(n) of them along the longest extent -> a few points per occupied cell
+            cell = float(ext.max()) / float(min(256, max(4, int(round(np.sqrt(max(n, 1)) / 2)))))
+        cell = float(cell)
+        while True:
+            dims = np.floor(ext / cell).astype(np.int64) + 1
+            if int(dims.prod()) <= self.MAX_CELLS:
+                break
+            cell *= 1.26
+        self.cell, self.origin, self.dims = cell, lo, [int(d) for d in dims]
+        cells = int(dims.prod())
+        self.cell_start = torch.empty(cells + 1, dtype=torch.int32, device=dev)
+        self.order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        scratch = torch.empty(cells, dtype=torch.int32, device=dev)
+        if n == 0:
+            self.pts = torch.zeros((1, 3), dtype=torch.float32, device=dev)   # a valid pointer; n stays 0
+        self.n = n
+        _capi.check(_capi.lib().dfb_point_grid_build(C.byref(self.struct()), _ptr(self.cell_start), _ptr(self.order), _ptr(scratch), _stream()))
+
+    def struct(self):
+        s = _capi.PointGrid()
+        s.pts = self.pts.data_ptr()
+        s.n = self.n
+        for i in range(3):
+            s.origin[i] = float(self.origin[i])
+            s.dims[i] = self.dims[i]
+        s.cell = self.cell
+        s.cell_start = self.cell_start.data_ptr()
+        s.order = self.order.data_ptr()
+        return s
+
+    def knn(self, queries, k, want_d2=False):
+        """KDTree.query(q, k)[1] for (m,3) float64 queries: (m,k) int32, ascending distance."""
+        q = _to_dev(queries, torch.float64, self.device).reshape(-1, 3)
+        idx = torch.empty((q.shape[0], k), dtype=torch.int32, device=self.device)
+        d2 = torch.empty((q.shape[0], k), dtype=torch.float64, device=self.device) if want_d2 else None
+        _capi.check(_capi.lib().dfb_point_grid_knn(C.byref(self.struct()), _ptr(q), q.shape[0], k, _ptr(idx), _ptr(d2), _stream()))
+        return (idx, d2) if want_d2 else idx
+
+
+def corr_select(warped_pts, warped_normals, live_verts, nn):
+    """Best-of-k point-to-plane candidate (core/fusion.py:264-274): returns (best index (m,) int32, best cost (m,) float64)."""
+    dev = nn.device
+    wv = _to_dev(warped_pts, torch.float64, dev).reshape(-1, 3)
+    wn = _to_dev(warped_normals, torch.float64, dev).reshape(-1, 3)
+    lv = _to_dev(live_verts, torch.float32, dev).reshape(-1, 3)
+    best = torch.empty(wv.shape[0], dtype=torch.int32, device=dev)
+    cost = torch.empty(wv.shape[0], dtype=torch.float64, device=dev)
+    _capi.check(_capi.lib().dfb_corr_select(_ptr(wv), _ptr(wn), wv.shape[0], _ptr(lv), _ptr(nn), nn.shape[1], _ptr(best), _ptr(cost), _stream()))
+    return best, cost
+
+
+def graph_unsupported(wf, verts, vert_knn):
+    """core/fusion.py:211-215: bool (m,) -- surface points no node of `wf` supports."""
+    dev = wf.device
+    v = _to_dev(verts, torch.float32, dev).reshape(-1, 3)
+    kn = _to_dev(vert_knn, torch.int32, dev).reshape(v.shape[0], -1)
+    out = torch.empty(v.shape[0], dtype=torch.uint8, device=dev)
+    _capi.check(_capi.lib().dfb_graph_unsupported(_ptr(v), v.shape[0], _ptr(kn), kn.shape[1], _ptr(wf.node_pos), _ptr(wf.node_w), _ptr(out), _stream()))
+    return out.bool()
+
+
+def uniform_sample(pts, radius, device=None, rounds_per_call=16):
+    """`uniform_sample` (core/util.py:27-47) on the device: returns (samples (s,3) float32 numpy, indices (s,) int64 numpy),
+    identical to the sequential greedy sampler (parallel lexicographic maximal independent set, csrc/graph.cu)."""
+    dev = _require_cuda(device)
+    p = _to_dev(pts, torch.float32, dev).reshape(-1, 3)
+    n = p.shape[0]
+    if n == 0:
+        return np.zeros((0, 3), np.float32), np.zeros(0, np.int64)
+    grid = PointGrid(p, cell=float(radius), device=dev)
+    state = torch.zeros(n, dtype=torch.uint8, device=dev)
+    undecided = torch.ones(1, dtype=torch.int32, device=dev)
+    s = grid.struct()
+    while True:
+        _capi.check(_capi.lib().dfb_graph_sample_rounds(C.byref(s), float(radius), rounds_per_call, _ptr(state), _ptr(undecided), _stream()))
+        if int(undecided.item()) == 0:
+            break
+    idx = torch.nonzero(state == 1).reshape(-1)
+    return p[idx].cpu().numpy(), idx.cpu().numpy().astype(np.int64)

@@ -13,9 +13,12 @@ and error behaviour for the two hot paths, with state living on the 
   * the per-voxel KD-tree query of `updateTSDF` (core/fusion.py:175) is replaced by an exact kNN table
                           cached per graph revision.
 
-Graph maintenance that needs marching cubes (`update_graph`, `setupCorrespondences`, `marching_cubes`,
-mesh writers) is outside the hot path (SURVEY 8f "next") and raises NotImplementedError.
+The callers either side of the hot paths run on the device too: `setupCorrespondences`
+(closest-point correspondences), `update_graph` / `construct_graph` (node sampling, unsupported surface points,
+vertex->node tables).  Surface extraction (8f rank 3) is a hook: `surface_extractor`, or pass the vertices in.
 """
+import os
+
 import numpy as np
 import torch
 from scipy.spatial import KDTree
@@ -204,16 +207,44 @@ class _FusionBase:
         from . import io
         io.write_warp_field(self._nodes, path, filename, self._itercounter)
 
-    # ---- out-of-scope graph / mesh maintenance ---------------------------------------------------
+    # ---- surface extraction hook ------------------------------------------------------------------
+    surface_extractor = None
+    """callable(tsdf, step_size) -> (verts, faces, normals, values), the contract of
+    skimage.measure.marching_cubes_lewiner(tsdf, step_size=..., allow_degenerate=False) that the reference calls
+    (core/fusion.py:554-564).  Surface extraction itself is SURVEY 8f rank 3 and not part of this library: assign an
+    extractor here, or hand the vertices to setupCorrespondences / update_graph directly."""
+
     def marching_cubes(self, tsdf=None, step_size=0):
-        raise NotImplementedError("surface extraction is outside the accelerated hot path (SURVEY 8f rank 3)")
+        """core/fusion.py:553-568, delegating to `surface_extractor`."""
+        if self.surface_extractor is None:
+            raise NotImplementedError("surface extraction is outside the accelerated hot path (SURVEY 8f rank 3): set "
+                                      "`surface_extractor`, or pass live_vertices= / vertices= to the caller")
+        if step_size < 1:
+            step_size = self._marching_cubes_step_size
+        if tsdf is not None:
+            return self.surface_extractor(_as_np(tsdf), step_size)
+        v, f, n, _ = self.surface_extractor(_as_np(self._tsdf), step_size)
+        self._vertices, self._faces, self._normals = np.asarray(v, dtype=np.float32), f, np.asarray(n, dtype=np.float32)
 
-    def update_graph(self):
-        raise NotImplementedError("deformation-graph maintenance needs marching cubes (SURVEY 8f rank 2)")
+    # ---- SURVEY 8f rank 1: closest-point correspondences ---------------------------------------------
+    def _live_vertices(self, curr_tsdf, live_vertices):
+        if live_vertices is None:
+            live_vertices = self.marching_cubes(curr_tsdf, step_size=1)[0]
+        lv = engine._to_dev(live_vertices, torch.float32, self._device).reshape(-1, 3)
+        if lv.shape[0] < self._knn:
+            raise ValueError('the live surface has fewer vertices than knn')
+        return lv
 
-    def setupCorrespondences(self, curr_tsdf, *a, **kw):
-        raise NotImplementedError("correspondence search needs marching cubes of the live TSDF (SURVEY 8f rank 1); "
-                                  "pass correspondences to solve() explicitly")
+    def _closest_points(self, lv, wv, wn):
+        """core/fusion.py:264-274: k nearest live vertices of every warped canonical vertex, best point-to-plane cost."""
+        nn = engine.PointGrid(lv, device=self._device).knn(wv, self._knn)
+        return engine.corr_select(wv, wn, lv, nn)
+
+    def _relink_nodes(self):
+        """node -> index of its nearest canonical vertex (core/fusion.py:204-209,308-313)."""
+        if self._wf.n_nodes and self._vertices is not None and len(self._vertices):
+            grid = engine.PointGrid(self._vertices, device=self._device)
+            self._node_vertex_idx = grid.knn(self._wf.node_pos.double(), 1).reshape(-1).cpu().numpy().astype(np.int64)
 
 
 class Fusion(_FusionBase):
@@ -270,11 +301,72 @@ class Fusion(_FusionBase):
     def construct_graph(self):
         """core/fusion.py:101-123: radius-based node sampling from the canonical vertices, initial node dq
         [1,0,0,0,0,.01,.01,0] (Q5), w = 2*radius, vertex->node kNN table."""
-        from .synth import uniform_sample
-        nodes_v, nodes_idx = uniform_sample(self._vertices, self._radius)
+        nodes_v, nodes_idx = engine.uniform_sample(self._vertices, self._radius, device=self._device)
         dq0 = np.array([1, 0.00, 0.00, 0.00, 0.00, 0.01, 0.01, 0.00], dtype=np.float32)
         self._nodes = [(int(nodes_idx[i]), nodes_v[i], dq0, 2 * self._radius) for i in range(len(nodes_v))]
         self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
+
+    def update_graph(self, *, vertices=None, normals=None, faces=None):
+        """core/fusion.py:201-239.  The reference re-extracts the canonical surface first (`marching_cubes()`); pass
+        `vertices` (+ `normals`) to supply it instead.  Then, all on the device: nodes re-linked to their nearest vertex,
+        surface points no node supports (min |node - v| / dg_w >= 1 over the k nearest) found, new nodes sampled from
+        them with `uniform_sample` and initialised by `dq_blend` over the OLD graph, vertex->node table rebuilt.  As in
+        the reference the vertex index stored with a NEW node counts within the unsupported subset (core/fusion.py:217-219)."""
+        if vertices is not None:
+            self._vertices = np.asarray(vertices, dtype=np.float32)
+            self._normals = None if normals is None else np.asarray(normals, dtype=np.float32)
+            self._faces = faces
+        else:
+            self.marching_cubes()
+        self._relink_nodes()
+        vknn = self._wf.knn_points(self._vertices, self._knn)
+        uns = engine.graph_unsupported(self._wf, self._vertices, vknn).cpu().numpy()
+        new_v, new_idx = engine.uniform_sample(self._vertices[uns], self._radius, device=self._device)
+        if len(new_v):
+            new_dq = _gn.dq_blend_points(self._wf, new_v, self._wf.knn_points(new_v, self._knn))
+            pos = np.concatenate([self._wf.node_pos.cpu().numpy(), new_v])
+            dq = np.concatenate([self._wf.node_dq.cpu().numpy(), new_dq.astype(np.float32)])
+            w = np.concatenate([self._wf.node_w.cpu().numpy(), np.full(len(new_v), 2 * self._radius, dtype=np.float32)])
+            self._node_vertex_idx = np.concatenate([self._node_vertex_idx, new_idx])
+            self._wf.k = self._knn
+            self._wf.set_nodes(pos, dq, w)              # new graph revision: cached kNN tables are rebuilt on demand
+        if self._verbose:
+            print("Inserted %d new deformation nodes. Current number of deformation nodes: %d" % (len(new_v), self._wf.n_nodes))
+        self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
+        self._curr_tsdf = None
+        self._correspondences = []
+        if self._write_warpfield:
+            self.write_warp_field(os.environ.get("DFB_DATA_PATH", "."), 'test')
+
+    def setupCorrespondences(self, curr_tsdf, method='cnn', prune_result=True, tolerance=0.2, *, live_vertices=None):
+        """core/fusion.py:243-313, closest-points branch (the CNN branch is out of scope, so `method` only keeps the
+        signature; the reference itself takes this branch whenever no TF session exists, :252).  Every canonical vertex
+        is warped to the live frame, its k nearest live vertices are searched, and the one with the smallest
+        point-to-plane cost |n'.(v' - p)| (< 1, else the nearest) becomes its correspondence.  `live_vertices`
+        replaces `marching_cubes(curr_tsdf, step_size=1)`.
+        Pruning: vertices whose best cost exceeds `tolerance` are removed from `_vertices/_normals/_correspondences/
+        _neighbor_look_up` and the nodes re-linked (:294-313).  The reference's clpts loop records the wrong index here
+        (its inner `for idx in iidx` shadows the vertex index, :269-276, so it deletes the vertex whose number is the
+        k-th nearest LIVE vertex's); the intended vertex is pruned instead (stated deviation, like SURVEY Q7)."""
+        self._curr_tsdf = curr_tsdf
+        if self._vertices is None or self._normals is None:
+            raise ValueError('canonical vertices/normals have not been set')
+        lv = self._live_vertices(curr_tsdf, live_vertices)
+        loc = np.asarray(self._neighbor_look_up, dtype=np.int32).reshape(len(self._vertices), -1)
+        wv, wn = engine.warp_points(self._wf, self._lw, self._vertices, self._normals, idx=loc, k=loc.shape[1])
+        best, cost = self._closest_points(lv, wv, wn)
+        self._correspondences = lv[best.long()].cpu().numpy()
+        self._corr_cost = cost.cpu().numpy()
+        if prune_result:
+            pruned = np.nonzero(self._corr_cost > tolerance)[0]
+            if self._verbose:
+                print('ratio of correspondence outlier rejection', float(len(pruned)) / float(len(self._vertices)))
+            self._vertices = np.delete(self._vertices, pruned, axis=0)
+            self._correspondences = np.delete(self._correspondences, pruned, axis=0)
+            self._neighbor_look_up = np.delete(np.asarray(self._neighbor_look_up), pruned, axis=0)
+            self._normals = np.delete(self._normals, pruned, axis=0)
+            self._faces = None
+            self._relink_nodes()
 
     # ---- a1 ---------------------------------------------------------------------------------------
     def updateTSDF(self, curr_tsdf=None, wmax=100.0):
@@ -350,10 +442,12 @@ class Fusion(_FusionBase):
             self._lw = prob.solve_lw(np.asarray(self._lw, dtype=np.float64), max_iter=opts.get("lw_iterations", 20), verbose=self._verbose)
             if method == 'clpts' and correspondences is None:
                 self.setupCorrespondences(self._curr_tsdf, method='clpts')
+                prob = self._problem()
         rw = regularization_weight
         for it in range(iteration):
             if it > 0 and correspondences is None:
                 self.setupCorrespondences(self._curr_tsdf, method='clpts')
+                prob = self._problem()
             x0 = self._wf.node_dq.double().reshape(-1)
             res = prob.gauss_newton(x0, self._lw, rw, max_iter=gn_iterations, huber=opts.get("huber", True),
                                     f_scale=opts.get("f_scale", 1.0), verbose=self._verbose, **opts.get("gn", {}))
@@ -439,9 +533,42 @@ class FusionDM(_FusionBase):
         curr = engine._to_dev(curr_tsdf, torch.float32, self._device)
         engine.update_volume(self._vol, None, self._lw, curr, self._tdist, wmax, mode=self._mode, rigid=True)
 
-    def solve(self, curr_tsdf):
-        raise NotImplementedError("FusionDM.solve needs marching-cubes correspondences (core/fusion_dm.py:219-244; SURVEY 8f rank 1); "
-                                  "use Fusion.solve(correspondences=...) with k-nearest nodes for the rigid+non-rigid fit")
+    def setupCorrespondences(self, curr_tsdf, prune_result=True, tolerance=1.0, *, live_vertices=None):
+        """core/fusion_dm.py:219-244: canonical vertices/normals moved by the global rigid dq `_lw`, k nearest live
+        vertices, best point-to-plane candidate; vertices with best cost <= tolerance are kept in `_corridx` with their
+        `_correspondences`.  `live_vertices` replaces `marching_cubes(curr_tsdf, step_size=1)`."""
+        if self._vertices is None or self._normals is None:
+            raise ValueError('canonical vertices/normals have not been set')
+        lv = self._live_vertices(curr_tsdf, live_vertices)
+        wv, wn = engine.warp_points(self._wf, self._lw, self._vertices, self._normals, k=0)
+        best, cost = self._closest_points(lv, wv, wn)
+        keep = torch.nonzero(cost <= tolerance).reshape(-1)
+        self._corridx = [int(i) for i in keep.cpu().numpy()]
+        self._correspondences = list(lv[best[keep].long()].cpu().numpy())
+
+    def _rigid_problem(self):
+        """Data term of core/fusion_dm.py:284-297 as a warp-field problem whose single node carries the identity
+        transform (weight exp(-(d/2w)^2) = 1 for w = 1e30, so the blended dq is exactly [1,0,0,0,0,0,0,0])."""
+        wf = engine.DeviceWarpField(1, self._device)
+        wf.set_nodes(np.zeros((1, 3), np.float32), np.array([[1, 0, 0, 0, 0, 0, 0, 0]], np.float32), np.float32(1e30))
+        idx = np.asarray(self._corridx, dtype=np.int64)
+        return _gn.Problem(wf, self._vertices[idx], self._normals[idx], np.asarray(self._correspondences, dtype=np.float64).reshape(-1, 3),
+                           np.zeros((len(idx), 1), np.int64), np.zeros(1, np.int64))
+
+    def computef_lw(self, x):
+        """core/fusion_dm.py:284-297: point-to-plane residuals of the kept correspondences under the rigid dq x."""
+        return self._rigid_problem().residuals_lw(np.asarray(x, dtype=np.float64)).cpu().numpy()
+
+    def solve(self, curr_tsdf, *, live_vertices=None, lw_iterations=100):
+        """core/fusion_dm.py:262-281: three rounds of (correspondences, rigid least squares on `_lw`).  The reference's
+        `least_squares(self.computef_lw, ...)` (finite-difference TRF) is replaced by a damped Gauss-Newton on the
+        analytic 8x8 normal equations (csrc/gn.cu lw_normal_eq_kernel), as in Fusion.solve."""
+        self._itercounter += 1
+        for _ in range(3):
+            self.setupCorrespondences(curr_tsdf, live_vertices=live_vertices)
+            if not self._corridx:
+                raise ValueError('no correspondence within tolerance')
+            self._lw = self._rigid_problem().solve_lw(np.asarray(self._lw, dtype=np.float64), max_iter=lw_iterations, verbose=self._verbose)
 
 
 class FusionDM_GPU(FusionDM):

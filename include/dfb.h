@@ -190,6 +190,40 @@ int64_t dfb_gn_solve_workspace_doubles(int n_nodes);
 int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* g, double lambda,
                  int max_iter, double tol, const double* x, double* x_new, double* delta, double* workspace, dfb_stream_t stream);
 
+/* ---- correspondences and deformation-graph maintenance --------------------------------- */
+/* Uniform search grid over a float32 point set: the replacement of the scipy KDTree the reference builds over live /
+ * canonical surface vertices (core/fusion.py:204,255,308; core/fusion_dm.py:226).  Cell (cx,cy,cz) has index
+ * (cz*dims[1] + cy)*dims[0] + cx; its members are order[cell_start[c] .. cell_start[c+1]) in ascending id. */
+typedef struct dfb_point_grid {
+    const float* pts; /* [n][3] */
+    int64_t n;
+    double origin[3]; /* lower corner of cell (0,0,0) */
+    double cell;      /* edge length */
+    int dims[3];
+    const int32_t* cell_start; /* [cells + 1] */
+    const int32_t* order;      /* [n] */
+} dfb_point_grid;
+
+/* Fills cell_start / order for the geometry in *g (its own cell_start / order members are ignored);
+ * scratch: [cells] int32. */
+int dfb_point_grid_build(const dfb_point_grid* g, int32_t* cell_start, int32_t* order, int32_t* scratch, dfb_stream_t stream);
+/* KDTree.query(q, k) for float64 queries [m][3]: idx [m][k] ascending (float64 squared distance, id); -1 pads when the
+ * set has fewer than k points; dist2 [m][k] optional. */
+int dfb_point_grid_knn(const dfb_point_grid* g, const double* queries, int64_t m, int k, int32_t* idx, double* dist2,
+                       dfb_stream_t stream);
+/* Best-of-k point-to-plane candidate (core/fusion.py:264-274, core/fusion_dm.py:232-241): best [m] = index into
+ * live_verts, best_cost [m] = min(1, min_j |n . (v - p_j)|) with the reference's first-neighbour default. */
+int dfb_corr_select(const double* warped_pts, const double* warped_normals, int64_t m, const float* live_verts,
+                    const int32_t* nn, int k, int32_t* best, double* best_cost, dfb_stream_t stream);
+/* core/fusion.py:211-215: unsupported [m] = 1 where min over the k nearest nodes of |node - vert| / dg_w >= 1. */
+int dfb_graph_unsupported(const float* verts, int64_t m, const int32_t* vert_knn, int k, const float* node_pos,
+                          const float* node_w, uint8_t* unsupported, dfb_stream_t stream);
+/* uniform_sample (core/util.py:27-47) over the points of *g (cell >= radius / 4 recommended): runs `rounds` rounds of
+ * the parallel greedy selection on state [n] (0 undecided, 1 kept, 2 dropped; zero it before the first call);
+ * *undecided = candidates still open after the last round (repeat until 0). */
+int dfb_graph_sample_rounds(const dfb_point_grid* g, double radius, int rounds, uint8_t* state, int32_t* undecided,
+                            dfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,45 @@ def test_analytic_jacobian_vs_finite_differences():
     Jl, rl = ogn.lw_jacobian(lw, *args[:5], G["a1_node_dq"], float(G["a1_node_w"]))
     Jlfd = approx_derivative(lambda q: ogn.lw_jacobian(q, *args[:5], G["a1_node_dq"], float(G["a1_node_w"]))[1], lw, method="3-point")
     assert np.abs(Jl - Jlfd).max() <= 1e-7 * np.abs(Jlfd).max()
+
+
+# ---- SURVEY 8f ranks 1-2 (oracle/graph.py) against tests/golden/reference_graph_vectors.npz -------------------------
+GG = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_graph_vectors.npz"))
+
+
+def test_graph_correspondences_golden():
+    from oracle import graph as og
+    k, radius = int(GG["k"]), float(GG["radius"])
+    vknn = GG["vknn"]
+    nk, _ = og.knn_points(GG["node_pos"], GG["verts"], k)
+    assert np.array_equal(nk, vknn)
+    nw = np.full(vknn.shape, 2 * radius)
+    wv, wn = odq.warp(GG["verts"], GG["node_pos"][vknn], GG["node_dq"][vknn], nw, lw=GG["lw"], normal=GG["norms"])
+    nn, _ = og.knn_points(GG["lverts"], wv, k)
+    best, cost = og.corr_select(wv, wn, GG["lverts"], nn)
+    assert np.array_equal(GG["corr_fusion"], GG["lverts"][best])
+    # FusionDM: rigid
+    wv = odq.dqb_warp(GG["lw"], GG["verts"]); wn = odq.dqb_warp_normal(GG["lw"], GG["norms"])
+    nn, _ = og.knn_points(GG["lverts"], wv, k)
+    best, cost = og.corr_select(wv, wn, GG["lverts"], nn)
+    keep = np.nonzero(cost <= float(GG["dm_tolerance"]))[0]
+    assert np.array_equal(keep, GG["dm_corridx"]) and np.array_equal(GG["lverts"][best[keep]], GG["dm_corr"])
+
+
+def test_graph_maintenance_golden():
+    from oracle import graph as og
+    k, radius = int(GG["k"]), float(GG["radius"])
+    v, i = og.uniform_sample(GG["verts"], radius)
+    assert np.array_equal(i, GG["node_idx"]) and np.array_equal(v, GG["node_pos"])
+    _, i = og.uniform_sample(GG["lverts"][:1200], float(GG["us_radius"]))
+    assert np.array_equal(i, GG["us_idx"])
+    N = len(GG["node_pos"])
+    verts = GG["ug_verts"]
+    vknn, _ = og.knn_points(GG["node_pos"], verts, k)
+    uns = og.unsupported(verts, vknn, GG["node_pos"], np.full(N, 2 * radius))
+    new_v, new_i = og.uniform_sample(verts[uns], radius)
+    assert np.array_equal(GG["ug_node_pos"][N:], new_v) and np.array_equal(GG["ug_node_vidx"][N:], new_i)
+    link, _ = og.knn_points(verts, GG["node_pos"], 1)
+    assert np.array_equal(GG["ug_node_vidx"][:N], link[:, 0])
+    look, _ = og.knn_points(GG["ug_node_pos"], verts, k)
+    assert np.array_equal(look, GG["ug_lookup"])

@@ -95,3 +95,105 @@ def test_computef_live():
     sp = ogn.sparsity_pattern(vknn, nvi, N).toarray() > 0
     assert sp_ref[:V].sum() == sp[:V].sum()
     assert (sp_ref[V + 3 * N:].sum() == 0) and sp[V + 3 * N:].sum() > 0
+
+
+# ---- correspondences and graph maintenance (oracle/graph.py) --------------------------------
+def _corr_scene(rng, V=60, L=300, N=20, k=4):
+    from oracle import graph as og  # noqa: F401
+    node_pos = (rng.random((N, 3)) * 10).astype(np.float32)
+    node_dq = _dq(rng, N, np.float32)
+    verts = (rng.random((V, 3)) * 10).astype(np.float32)
+    norms = rng.normal(size=(V, 3)).astype(np.float32)
+    norms /= np.linalg.norm(norms, axis=1, keepdims=True)
+    lverts = (rng.random((L, 3)) * 10).astype(np.float32)
+    return node_pos, node_dq, verts, norms, lverts
+
+
+def test_setupCorrespondences_live():
+    """Fusion.setupCorrespondences (clpts branch, core/fusion.py:258-276) with marching cubes replaced by the live vertices."""
+    from oracle import graph as og
+    rng = np.random.default_rng(11)
+    N, k = 20, 4
+    node_pos, node_dq, verts, norms, lverts = _corr_scene(rng, N=N, k=k)
+    lw = _dq(rng, 1, np.float64)[0]
+    nodes = [(0, node_pos[i], node_dq[i], 5.0) for i in range(N)]
+    f = refload.make_fusion(nodes, None, None, 1.0, k, lw)
+    vknn = np.array([f._kdtree.query(v, k=k)[1] for v in verts])
+    f._vertices, f._normals, f._neighbor_look_up = verts, norms, list(vknn)
+    f.marching_cubes = lambda *a, **kw: (lverts, None, None, None)
+    with refload.quiet():
+        f.setupCorrespondences(np.zeros((2, 2, 2)), method='clpts', prune_result=False)
+    ref = np.array(f._correspondences)
+    wv, wn = odq.warp(verts, node_pos[vknn], node_dq[vknn], np.full(vknn.shape, 5.0), lw=lw, normal=norms)
+    nn, _ = og.knn_points(lverts, wv, k)
+    best, cost = og.corr_select(wv, wn, lverts, nn)
+    assert not og.knn_tie(lverts, wv, k).any()
+    assert np.array_equal(ref, lverts[best])
+    assert (cost < 1).any() and (cost == 1).any()
+
+
+def test_fusiondm_setupCorrespondences_live():
+    """FusionDM.setupCorrespondences (core/fusion_dm.py:219-244): rigid warp by _lw, keeps best_cost <= tolerance."""
+    from oracle import graph as og
+    util, Fusion, FusionDM = refload.load()
+    rng = np.random.default_rng(12)
+    _, _, verts, norms, lverts = _corr_scene(rng)
+    fdm = FusionDM(0.5, np.eye(3), tsdf_res=4)
+    fdm._lw = _dq(rng, 1, np.float64)[0]
+    fdm._vertices, fdm._normals = verts, norms
+    fdm.marching_cubes = lambda *a, **kw: (lverts, None, None, None)
+    with refload.quiet():
+        fdm.setupCorrespondences(None, tolerance=0.3)
+    wv = odq.dqb_warp(fdm._lw, verts)
+    wn = odq.dqb_warp_normal(fdm._lw, norms)
+    nn, _ = og.knn_points(lverts, wv, fdm._knn)
+    best, cost = og.corr_select(wv, wn, lverts, nn)
+    keep = np.nonzero(cost <= 0.3)[0]
+    assert 0 < len(keep) < len(verts)
+    assert np.array_equal(np.array(fdm._corridx), keep)
+    assert np.array_equal(np.array(fdm._correspondences), lverts[best[keep]])
+
+
+def test_uniform_sample_live():
+    from oracle import graph as og
+    util, _, _ = refload.load()
+    rng = np.random.default_rng(13)
+    pts = (rng.random((500, 3)) * 10).astype(np.float32)
+    for radius in (0.8, 1.7, 30.0):
+        rv, ri = util.uniform_sample(pts, radius)
+        ov, oi = og.uniform_sample(pts, radius)
+        assert np.array_equal(ri, oi) and np.array_equal(rv, ov)
+
+
+def test_update_graph_live():
+    """Fusion.update_graph (core/fusion.py:201-239) with marching cubes a no-op: vertex re-linking, unsupported points,
+    new nodes initialised by dq_blend, refreshed vertex->node table."""
+    from oracle import graph as og
+    rng = np.random.default_rng(14)
+    N, k, V = 12, 4, 150
+    node_pos = (rng.random((N, 3)) * 4 + 3).astype(np.float32)
+    node_dq = _dq(rng, N, np.float32)
+    verts = (rng.random((V, 3)) * 10).astype(np.float32)
+    radius = 1.1
+    nodes = [(0, node_pos[i], node_dq[i], 2 * radius) for i in range(N)]
+    f = refload.make_fusion(nodes, None, None, 1.0, k, _dq(rng, 1, np.float64)[0])
+    f._vertices, f._radius = verts, radius
+    f.marching_cubes = lambda *a, **kw: None
+    with refload.quiet():
+        f.update_graph()
+    vknn, _ = og.knn_points(node_pos, verts, k)
+    uns = og.unsupported(verts, vknn, node_pos, np.full(N, 2 * radius))
+    assert 0 < uns.sum() < V
+    new_v, new_i = og.uniform_sample(verts[uns], radius)
+    assert len(f._nodes) == N + len(new_v)
+    assert np.array_equal(np.array([n[1] for n in f._nodes[N:]]), new_v)
+    assert [n[0] for n in f._nodes[N:]] == list(new_i)
+    link, _ = og.knn_points(verts, node_pos, 1)
+    assert [n[0] for n in f._nodes[:N]] == list(link[:, 0])
+    # new node transforms: dq_blend at the new position over the OLD graph's k nearest nodes (core/fusion.py:219-223)
+    nk, _ = og.knn_points(node_pos, new_v, k)
+    b = odq.dq_blend(new_v, node_pos[nk], node_dq[nk], np.full(nk.shape, 2 * radius))
+    assert np.abs(np.array([n[2] for n in f._nodes[N:]]) - b).max() <= 1e-15
+    allpos = np.array([n[1] for n in f._nodes])
+    look, _ = og.knn_points(allpos, verts, k)
+    assert np.array_equal(np.array(f._neighbor_look_up), look)
