@@ -303,7 +303,7 @@ DFB_HDN bool voxel_volume_exact(const VolParams& P, int x, int y, int z, const u
     return upd;
 }
 
-// a1 fast classification: CLS_SKIP (certainly outside the live volume), CLS_CLAMP (all 8 corners >= tdist:
+// a1 fast classification: CLS_SKIP (certainly outside the live volume, or every corner below -tdist), CLS_CLAMP (all 8 corners >= tdist:
 // the update uses min(tdist, tl) = tdist up to 1e-16), else CLS_UNCERTAIN.  wi_out: Q4 weight (fp32).
 template <int KMAX>
 DFB_HD int voxel_volume_classify(const VolParams& P, int x, int y, int z, const uint16_t* ids, float* wi_out) {
@@ -328,10 +328,17 @@ DFB_HD int voxel_volume_classify(const VolParams& P, int x, int y, int z, const 
     const int x0 = (int)floorf(qx - e), x1 = (int)ceilf(qx + e);
     const int y0 = (int)floorf(qy - e), y1 = (int)ceilf(qy + e);
     const int z0 = (int)floorf(qz - e), z1 = (int)ceilf(qz + e);
-    float mn = 3.0e38f;
+    float mn = 3.0e38f, mxc = -3.0e38f;
     for (int a = x0; a <= x1; ++a)
         for (int b = y0; b <= y1; ++b)
-            for (int c = z0; c <= z1; ++c) mn = fminf(mn, P.curr[((size_t)a * P.cy + b) * P.cz + c]);
+            for (int c = z0; c <= z1; ++c) {
+                const float t = P.curr[((size_t)a * P.cy + b) * P.cz + c];
+                mn = fminf(mn, t);
+                mxc = fmaxf(mxc, t);
+            }
+    // the Q1 interpolation is a convex combination of the corners (its swapped y/z weights are still in [0,1]): with every
+    // corner below -tdist the reference's `tsdf_l > -tdist` (core/fusion.py:179) is certainly false
+    if (mxc <= -P.tdist_f * 1.000001f) return CLS_SKIP;
     if (!(mn >= P.tdist_f * 1.000001f)) return CLS_UNCERTAIN;
     if (P.k > 0) {
         float wi = 0.f;

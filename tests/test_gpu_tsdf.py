@@ -199,9 +199,10 @@ def test_projective_slabs_equal_full_volume(small_scene):
     assert np.array_equal(np.concatenate(parts_w), full.weight.cpu().numpy())
 
 
+@pytest.mark.parametrize("trunc", [False, True])
 @pytest.mark.parametrize("lw_kind", ["f32", "f64", "none"])
 @pytest.mark.parametrize("mode", [0, 1])
-def test_volume_update_a1(lw_kind, mode):
+def test_volume_update_a1(lw_kind, mode, trunc):
     torch, engine, _ = _engine()
     import scenes
     from dynamicfusion_body_b200 import synth
@@ -213,6 +214,10 @@ def test_volume_update_a1(lw_kind, mode):
     wv = synth.blend_warp(sc.vertices, sc.node_pos, sc.node_dq, nw, sc.vert_knn, lw=None if lw is None else lw.astype(np.float64))
     live = synth.mesh_sdf_volume((R + 2, R, R + 1), wv, sc.warped_normals)
     tdist = float(live.max())          # reference usage: Fusion(volume, volume.max(), ...) test.py:110
+    if trunc:
+        # a truncated live TSDF: whole neighbourhoods sit at +-1.5 tdist, which the fast tier settles (CLAMP / SKIP)
+        tdist = sc.tdist
+        live = np.clip(live, -1.5 * tdist, 1.5 * tdist)
     res = (R, R, R)
     vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k)
     t0, w0 = scenes.initial_state(R ** 3, tdist=tdist)
@@ -225,6 +230,9 @@ def test_volume_update_a1(lw_kind, mode):
     assert np.array_equal(mask.cpu().numpy().astype(bool)[ok], om[ok])
     assert np.abs(gv - ov)[ok].max() <= TSDF_TOL * tdist
     assert (np.abs(gw - ow) / np.maximum(1, ow))[ok].max() <= W_RTOL
+    if trunc and mode == 0:
+        st = vol.workspace.stats()
+        assert 0 < om.sum() < om.size and st["deferred"] < 0.8 * R ** 3      # the fast tier did settle voxels
 
 
 def test_rigid_volume_update():
