@@ -623,6 +623,49 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
     const size_t n = use_list ? (size_t)count : nvox;
     const size_t plane = (size_t)P.ry * P.rz;
     uint32_t done = 0;
+#ifndef DFB_EXACT_NO_PIPELINE
+    if (use_list && KT > 0 && !P.rigid && nvox <= 0xffffffffull) {
+        // Work-list path, software-pipelined: a voxel's state hangs on a chain of dependent gathers (list entry -> kNN ids,
+        // v, w -> node data) ahead of ~1000 instructions of arithmetic.  The list entry is fetched two iterations ahead and
+        // ids / v / w one iteration ahead, so only the node and depth gathers (L1 / L2 hits) are left inside an iteration.
+        const uint32_t stride = gridDim.x * blockDim.x, cnt = (uint32_t)n;
+        const uint32_t plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
+        uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < cnt) {
+            uint32_t i0 = P.list[t];
+            uint32_t i1 = t + stride < cnt && t + stride >= t ? P.list[t + stride] : i0;
+            uint16_t ids0[KMAX];
+            load_ids<KMAX>(P.knn, i0, KMAX, ids0);
+            float v0 = P.tsdf[i0], w0 = P.weight[i0];
+            for (;;) {
+                const uint32_t tn = t + stride, tnn = tn + stride;
+                const bool has1 = tn < cnt && tn > t;
+                const uint32_t i2 = (has1 && tnn < cnt && tnn > tn) ? P.list[tnn] : i1;
+                uint16_t ids1[KMAX];
+                load_ids<KMAX>(P.knn, i1, KMAX, ids1);
+                const float v1 = P.tsdf[i1], w1 = P.weight[i1];
+                const uint32_t xq = i0 / plane32, rem = i0 - xq * plane32, yq = rem / rz32;
+                float v = v0, w = w0;
+                int m, f;
+                voxel_projective_exact<KT>(P, (int)xq + P.x0, (int)yq, (int)(rem - yq * rz32), ids0, &v, &w, &m, &f);
+                if (m) {
+                    P.tsdf[i0] = v;
+                    P.weight[i0] = w;
+                }
+                if (P.mask_out) P.mask_out[i0] = (uint8_t)m;
+                if (P.frustum_out) P.frustum_out[i0] = (uint8_t)f;
+                ++done;
+                if (!has1) break;
+                t = tn; i0 = i1; i1 = i2; v0 = v1; w0 = w1;
+#pragma unroll
+                for (int j = 0; j < KMAX; ++j) ids0[j] = ids1[j];
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
+        if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);
+        return;
+    }
+#endif
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
         const size_t i = use_list ? (size_t)P.list[t] : t;
         int xs, y, z;
