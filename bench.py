@@ -36,8 +36,8 @@ sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_VOXEL = 16.0  # read v, read w, write v, write w (fp32) -- SURVEY 8d
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC_PER_LAUNCH = {"brick_update_kernel": 893870848, "proj_exact_kernel": 222599424, "brick_classify_kernel": 2328832,
-                      "region_bounds_kernel": 4719616}  # profiles/r1_ncu_full_summary.md
+TRAFFIC_PER_LAUNCH = {"brick_update_kernel": 971359744, "proj_exact_kernel": 198060288, "brick_classify_kernel": 1899008,
+                      "region_bounds_kernel": 5570304}  # profiles/r1_ncu_full_summary.md
 
 
 def measured_peaks():
