@@ -41,57 +41,87 @@ __device__ __forceinline__ int cell_of(const Grid& g, double x, double y, double
     return (cell_coord(z, g.oz, g.h, g.dz) * g.dy + cell_coord(y, g.oy, g.h, g.dy)) * g.dx + cell_coord(x, g.ox, g.h, g.dx);
 }
 
-// ---- build: count -> scan -> fill -> per-cell sort by id ------------------------------------------------
+// ---- build: count -> three-launch scan -> fill -> per-cell sort by id ------------------------------------------------
 __global__ void grid_count_kernel(Grid g, int32_t* count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     atomicAdd(&count[cell_of(g, g.pts[3 * i], g.pts[3 * i + 1], g.pts[3 * i + 2])], 1);
 }
 
-// exclusive scan of count[0..cells) into start[0..cells], one CTA of 1024 threads (chunked; cells <= 2^26)
-__global__ void __launch_bounds__(1024) grid_scan_kernel(const int32_t* count, int64_t cells, int32_t* start) {
-    __shared__ int32_t warp_sum[32];
-    __shared__ int32_t carry_s;
+// Exclusive scan of count[0..cells) into start[0..cells] in three launches: every CTA scans its own 4096-cell chunk and
+// reports the chunk total; one CTA scans the (<= 16385) chunk totals; the chunk offsets are added back.
+constexpr int SCAN_CHUNK = 4096;   // 1024 threads x 4 consecutive cells
+
+// block-wide exclusive scan of one chunk; returns this thread's exclusive prefix of its four cells, `total` = chunk sum
+__device__ __forceinline__ int32_t chunk_scan(const int32_t c[4], int32_t* warp_sum, int32_t& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < cells; base += 4096) {
-        // four consecutive cells per thread
-        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
-        int32_t c[4];
+    const int32_t mine = c[0] + c[1] + c[2] + c[3];
+    int32_t incl = mine;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = (i0 + j < cells) ? count[i0 + j] : 0;
-        const int32_t mine = c[0] + c[1] + c[2] + c[3];
-        int32_t incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int32_t s = warp_sum[lane];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
+            const int32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
         }
-        if (lane == 31) warp_sum[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            int32_t s = warp_sum[lane];
+        warp_sum[lane] = s;
+    }
+    __syncthreads();
+    total = warp_sum[31];
+    return (wid ? warp_sum[wid - 1] : 0) + incl - mine;
+}
+
+__global__ void __launch_bounds__(1024) scan_chunks_kernel(const int32_t* count, int64_t n, int32_t* start, int32_t* chunk_total) {
+    __shared__ int32_t warp_sum[32];
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_CHUNK + 4 * (int64_t)threadIdx.x;
+    int32_t c[4];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t t = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += t;
-            }
-            warp_sum[lane] = s;
-        }
-        __syncthreads();
-        const int32_t carry = carry_s;
-        int32_t run = carry + (wid ? warp_sum[wid - 1] : 0) + incl - mine;
+    for (int j = 0; j < 4; ++j) c[j] = (i0 + j < n) ? count[i0 + j] : 0;
+    int32_t total;
+    int32_t run = chunk_scan(c, warp_sum, total);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < n) start[i0 + j] = run;
+        run += c[j];
+    }
+    if (threadIdx.x == 0) chunk_total[blockIdx.x] = total;
+}
+
+// one CTA: in-place exclusive scan of v[0..n), grand total to *total_out
+__global__ void __launch_bounds__(1024) scan_totals_kernel(int32_t* v, int n, int32_t* total_out) {
+    __shared__ int32_t warp_sum[32];
+    int32_t carry = 0;
+    for (int base = 0; base < n; base += SCAN_CHUNK) {
+        const int i0 = base + 4 * (int)threadIdx.x;
+        int32_t c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[j] = (i0 + j < n) ? v[i0 + j] : 0;
+        int32_t total;
+        int32_t run = carry + chunk_scan(c, warp_sum, total);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (i0 + j < cells) start[i0 + j] = run;
+            if (i0 + j < n) v[i0 + j] = run;
             run += c[j];
         }
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = carry + warp_sum[31];
+        carry += total;
         __syncthreads();
     }
-    if (threadIdx.x == 0) start[cells] = carry_s;
+    if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(1024) scan_add_kernel(int32_t* start, int64_t n, const int32_t* chunk_offset) {
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_CHUNK + 4 * (int64_t)threadIdx.x;
+    const int32_t off = chunk_offset[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (i0 + j < n) start[i0 + j] += off;
 }
 
 __global__ void grid_fill_kernel(Grid g, int32_t* cursor, int32_t* order) {
@@ -281,6 +311,8 @@ int check_grid(const dfb_point_grid* g) {
 }  // namespace dfb
 using namespace dfb;
 
+extern "C" int64_t dfb_point_grid_scratch_ints(int64_t cells) { return cells + (cells + SCAN_CHUNK - 1) / SCAN_CHUNK + 1; }
+
 extern "C" int dfb_point_grid_build(const dfb_point_grid* g, int32_t* cell_start, int32_t* order, int32_t* scratch, dfb_stream_t stream) {
     DFB_REQUIRE(g && g->pts && cell_start && order && scratch, "null pointer");
     dfb_point_grid gg = *g;
@@ -294,7 +326,11 @@ extern "C" int dfb_point_grid_build(const dfb_point_grid* g, int32_t* cell_start
     DFB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * cells, s));
     const unsigned pb = (unsigned)((g->n + 255) / 256), cb = (unsigned)((cells + 255) / 256);
     if (g->n) grid_count_kernel<<<pb, 256, 0, s>>>(G, scratch);
-    grid_scan_kernel<<<1, 1024, 0, s>>>(scratch, cells, cell_start);
+    const int chunks = (int)((cells + SCAN_CHUNK - 1) / SCAN_CHUNK);
+    int32_t* chunk_total = scratch + cells;
+    scan_chunks_kernel<<<chunks, 1024, 0, s>>>(scratch, cells, cell_start, chunk_total);
+    scan_totals_kernel<<<1, 1024, 0, s>>>(chunk_total, chunks, cell_start + cells);
+    scan_add_kernel<<<chunks, 1024, 0, s>>>(cell_start, cells, chunk_total);
     DFB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int32_t) * cells, s));
     if (g->n) {
         grid_fill_kernel<<<pb, 256, 0, s>>>(G, scratch, order);

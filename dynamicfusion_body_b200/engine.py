@@ -356,8 +356,11 @@ class PointGrid:
             lo = hi = np.zeros(3)
         ext = np.maximum(hi - lo, 1e-6)
         if cell is None:
-            # surface samples: about sqrt(n) of them along the longest extent -> a few points per occupied cell
+            # surface samples: about sqrt(n) of them along the longest extent -> a few points per occupied cell ...
             cell = float(ext.max()) / float(min(256, max(4, int(round(np.sqrt(max(n, 1)) / 2)))))
+            # ... but no more than ~8 cells per point (most cells of a surface's bounding box are empty; measured at
+            # 300 k points: 13.7 M cells -> build 6.5 ms, query 0.52 ms; 1.9 M cells -> 1.0 / 0.64 ms)
+            cell = max(cell, float(np.cbrt(ext.prod() / (8.0 * max(n, 1)))))
         cell = float(cell)
         while True:
             dims = np.floor(ext / cell).astype(np.int64) + 1
@@ -368,7 +371,7 @@ class PointGrid:
         cells = int(dims.prod())
         self.cell_start = torch.empty(cells + 1, dtype=torch.int32, device=dev)
         self.order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-        scratch = torch.empty(cells, dtype=torch.int32, device=dev)
+        scratch = torch.empty(int(_capi.lib().dfb_point_grid_scratch_ints(cells)), dtype=torch.int32, device=dev)
         if n == 0:
             self.pts = torch.zeros((1, 3), dtype=torch.float32, device=dev)   # a valid pointer; n stays 0
         self.n = n
@@ -425,7 +428,7 @@ def uniform_sample(pts, radius, device=None, rounds_per_call=16):
     n = p.shape[0]
     if n == 0:
         return np.zeros((0, 3), np.float32), np.zeros(0, np.int64)
-    grid = PointGrid(p, cell=float(radius), device=dev)
+    grid = PointGrid(p, cell=float(radius) * 1.001, device=dev)      # just above the radius: the 3x3x3 cell neighbourhood covers the ball
     state = torch.zeros(n, dtype=torch.uint8, device=dev)
     undecided = torch.ones(1, dtype=torch.int32, device=dev)
     s = grid.struct()

@@ -205,7 +205,8 @@ typedef struct dfb_point_grid {
 } dfb_point_grid;
 
 /* Fills cell_start / order for the geometry in *g (its own cell_start / order members are ignored);
- * scratch: [cells] int32. */
+ * scratch: dfb_point_grid_scratch_ints(cells) int32. */
+int64_t dfb_point_grid_scratch_ints(int64_t cells);
 int dfb_point_grid_build(const dfb_point_grid* g, int32_t* cell_start, int32_t* order, int32_t* scratch, dfb_stream_t stream);
 /* KDTree.query(q, k) for float64 queries [m][3]: idx [m][k] ascending (float64 squared distance, id); -1 pads when the
  * set has fewer than k points; dist2 [m][k] optional. */
