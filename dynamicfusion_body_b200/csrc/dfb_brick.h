@@ -230,7 +230,7 @@ DFB_HDN BrickClass box_classify_views(const ProjParams& P, const Box3& bx, int m
         for (int t = ctx.lane(); t < npx; t += ctx.nlanes()) {
             const int iv = iv0 + t / nu, iu = iu0 + t % nu;
             const float z = -P.depth[v][(size_t)iv * P.cols + iu];
-            nan |= !(z == z);
+            nan |= !(fabsf(z) <= 3.0e38f);   // NaN or +-inf: the reference's K^-1 product turns an infinite depth into NaN (0 * inf)
             zmin = fminf(zmin, z);
             zmax = fmaxf(zmax, z);
         }

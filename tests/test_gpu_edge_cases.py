@@ -109,6 +109,29 @@ def test_empty_and_saturated_depth_and_wmax():
     assert (vol.weight.cpu().numpy() == 100.0).all()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+def test_nonfinite_and_positive_depth_pixels(mode):
+    """Invalid sensor values follow the reference's comparisons (core/fusion_dm.py:196-203): z = -dm must be > 0, so NaN,
+    +inf and positive depth values are skipped; -inf passes that test but K^-1 * (z*u, z*v, z) multiplies it by the zeros
+    of a pinhole K^-1, tsdf_l is NaN and `tsdf_l > -tdist` fails: skipped as well."""
+    from dynamicfusion_body_b200 import synth
+    import scenes
+    sc = synth.make_scene(res=32, k=4, n_nodes=100, seed=6, rows=64, cols=80)
+    R = 32
+    rng = np.random.default_rng(0)
+    d = sc.depths.copy()
+    r = rng.random(d.shape)
+    d[r < 0.10] = np.nan
+    d[(r >= 0.10) & (r < 0.15)] = np.inf
+    d[(r >= 0.15) & (r < 0.20)] = -np.inf
+    d[(r >= 0.20) & (r < 0.25)] = 7.5
+    d[:, 10:30, 20:50] = np.nan                                                            # a whole block without data
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    with np.errstate(invalid="ignore"):
+        om, vol = _run(sc, (R, R, R), 0, R, t0, w0, depths=d, mode=mode)
+    assert om.any() and not om.all() and np.isfinite(vol.tsdf.cpu().numpy()).all()
+
+
 def test_degenerate_blends_fall_back_like_the_reference():
     """All-zero node dual quaternions and weights that underflow in float64 both make the blended dq the zero vector;
     the reference then substitutes the identity (core/fusion.py:544-549)."""

@@ -197,3 +197,23 @@ def test_update_graph_live():
     allpos = np.array([n[1] for n in f._nodes])
     look, _ = og.knn_points(allpos, verts, k)
     assert np.array_equal(np.array(f._neighbor_look_up), look)
+
+
+def test_fuseDepths_invalid_depth_values_live():
+    """NaN, +-inf and positive depth pixels through the unmodified FusionDM.fuseDepths: all skipped (an infinite depth
+    becomes NaN in K^-1 * (z*u, z*v, z) for a pinhole K) -- the oracle follows op for op."""
+    util, Fusion, FusionDM = refload.load()
+    rng = np.random.default_rng(4)
+    R = 8
+    K = np.array([[50., 0, 20], [0, 55., 15], [0, 0, 1]])
+    fdm = FusionDM(0.5, K, tsdf_res=R)
+    dm = -(rng.random((32, 40)) * 6 + 10).astype(np.float32)
+    r = rng.random(dm.shape)
+    dm[r < 0.15] = np.nan; dm[(r >= 0.15) & (r < 0.3)] = np.inf; dm[(r >= 0.3) & (r < 0.45)] = -np.inf; dm[(r >= 0.45) & (r < 0.6)] = 3.0
+    lw34 = np.concatenate([np.eye(3), np.array([[0.2], [0.1], [12.]])], 1)
+    t0 = rng.normal(size=(R, R, R)); w0 = np.floor(rng.random((R, R, R)) * 3)
+    with refload.quiet(), np.errstate(invalid="ignore"):
+        rt, rw = fdm.fuseDepths(dm, lw34, t0.copy(), w0.copy())
+        v, w, m, fr = ot.fuse_depth_rigid(t0.ravel(), w0.ravel(), ot.voxel_grid((R, R, R)), dm, lw34, K, np.linalg.inv(K), 0.5, R)
+    assert np.array_equal(v, rt.ravel()) and np.array_equal(w, rw.ravel())
+    assert 0 < m.sum() < fr.sum() and np.isfinite(rt).all()
