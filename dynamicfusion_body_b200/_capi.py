@@ -54,7 +54,7 @@ class Views(C.Structure):
 
 class Workspace(C.Structure):
     _fields_ = [("list", C.c_void_p), ("capacity", C.c_uint32), ("counters", C.c_void_p),
-                ("brick_cls", C.c_void_p), ("brick_lists", C.c_void_p)]
+                ("brick_cls", C.c_void_p), ("brick_lists", C.c_void_p), ("overflow_bits", C.c_void_p)]
 
 
 class GNProblem(C.Structure):

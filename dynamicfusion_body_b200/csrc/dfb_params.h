@@ -88,7 +88,7 @@ inline void fill_common(ProjParams& P, const dfb_volume* vol, const dfb_workspac
     P.rx = vol->rx; P.ry = vol->ry; P.rz = vol->rz; P.x0 = vol->x0; P.x1 = vol->x1;
     P.tdist = fabs(tdist); P.wmax = wmax;
     P.tdist_f = (float)fabs(tdist); P.wmax_f = (float)wmax;
-    P.list = ws->list; P.capacity = ws->capacity; P.counters = ws->counters;
+    P.list = ws->list; P.capacity = ws->capacity; P.counters = ws->counters; P.overflow_bits = ws->overflow_bits;
     P.mask_out = mask_out; P.frustum_out = frustum_out;
 }
 
@@ -211,7 +211,7 @@ inline int build_volume(VolParams& P, const dfb_volume* vol, const dfb_warpfield
     double mag = fmax(fmax(vol->rx, vol->ry), vol->rz);
     mag = fmax(mag, affine_corner_mag(A, vol->rx, vol->ry, vol->rz));
     P.coord_mag = (float)(2.0 * mag + 8.0);
-    P.list = ws->list; P.capacity = ws->capacity; P.counters = ws->counters;
+    P.list = ws->list; P.capacity = ws->capacity; P.counters = ws->counters; P.overflow_bits = ws->overflow_bits;
     P.mask_out = mask_out;
     return DFB_OK;
 }

@@ -54,6 +54,7 @@ struct ProjParams {
     uint32_t* list;
     uint32_t capacity;
     uint32_t* counters;
+    uint32_t* overflow_bits;   // optional: deferred voxels that did not fit the list (one bit per slab voxel)
     uint8_t* mask_out;
     uint8_t* frustum_out;
 };
@@ -78,6 +79,7 @@ struct VolParams {
     uint32_t* list;
     uint32_t capacity;
     uint32_t* counters;
+    uint32_t* overflow_bits;
     uint8_t* mask_out;
 };
 

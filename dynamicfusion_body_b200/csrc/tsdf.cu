@@ -37,7 +37,14 @@ __device__ __forceinline__ void load_ids(const uint16_t* knn, size_t i, int k, u
         if (j < k) ids[j] = knn[i * (size_t)k + j];
 }
 
-__device__ __forceinline__ void push_uncertain(bool unc, uint32_t i, uint32_t* list, uint32_t capacity, uint32_t* counters) {
+// a deferred voxel that found the list full is marked in the overflow bitmap (the exact pass sweeps it after the list)
+__device__ __forceinline__ void defer_voxel(uint32_t pos, uint32_t i, uint32_t* list, uint32_t capacity, uint32_t* overflow_bits) {
+    if (pos < capacity) list[pos] = i;
+    else if (overflow_bits) atomicOr(overflow_bits + (i >> 5), 1u << (i & 31));
+}
+
+__device__ __forceinline__ void push_uncertain(bool unc, uint32_t i, uint32_t* list, uint32_t capacity, uint32_t* counters,
+                                               uint32_t* overflow_bits) {
     const unsigned ballot = __ballot_sync(0xffffffffu, unc);
     if (ballot == 0) return;
     const int lane = threadIdx.x & 31;
@@ -47,7 +54,7 @@ __device__ __forceinline__ void push_uncertain(bool unc, uint32_t i, uint32_t* l
     base = __shfl_sync(0xffffffffu, base, leader);
     if (unc) {
         const uint32_t pos = base + __popc(ballot & ((1u << lane) - 1u));
-        if (pos < capacity) list[pos] = i;
+        defer_voxel(pos, i, list, capacity, overflow_bits);
     }
 }
 
@@ -67,7 +74,7 @@ __global__ void __launch_bounds__(256) proj_fast_kernel(const __grid_constant__ 
         if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
         cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f);
     }
-    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters, P.overflow_bits);
     if (!in || cls == CLS_UNCERTAIN) return;
     if (m) {
         float v = P.tsdf[i], w = P.weight[i];
@@ -466,7 +473,7 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
             if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
             cls = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
         }
-        push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+        push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters, P.overflow_bits);
         if (!in || cls == CLS_UNCERTAIN) continue;
         if (m) {
             float v = P.tsdf[i], w = P.weight[i];
@@ -534,7 +541,7 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
         for (int q = 0; q < 4; ++q) {
             if (cls[q] == CLS_UNCERTAIN) {
                 const uint32_t pos = base + __popc(bal[q] & ((1u << lane) - 1u));
-                if (pos < P.capacity) P.list[pos] = (uint32_t)(i0 + q);
+                defer_voxel(pos, (uint32_t)(i0 + q), P.list, P.capacity, P.overflow_bits);
             }
             base += __popc(bal[q]);
         }
@@ -620,7 +627,31 @@ __global__ void DFB_UPDATE_BOUNDS brick_update_kernel(const __grid_constant__ Pr
     }
 }
 
-// mode: 0 = work list (or re-scan on overflow), 1 = every voxel
+// One deferred voxel through the reference-exact tier (a2 / a3).
+template <int KMAX, int KT>
+__device__ __forceinline__ void exact_voxel(const ProjParams& P, size_t i, size_t nvox, size_t plane, const uint16_t* ids, float v, float w) {
+    int xs, y, z;
+    if (nvox <= 0xffffffffull) {   // 32-bit index arithmetic (the 64-bit divisions were 5 % of the kernel's instructions)
+        const uint32_t i32 = (uint32_t)i, plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
+        const uint32_t xq = i32 / plane32, rem = i32 - xq * plane32, yq = rem / rz32;
+        xs = (int)xq; y = (int)yq; z = (int)(rem - yq * rz32);
+    } else {
+        xs = (int)(i / plane);
+        const size_t rem = i - (size_t)xs * plane;
+        y = (int)(rem / P.rz);
+        z = (int)(rem - (size_t)y * P.rz);
+    }
+    int m, f;
+    voxel_projective_exact<KT>(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
+    if (m) {
+        P.tsdf[i] = v;
+        P.weight[i] = w;
+    }
+    if (P.mask_out) P.mask_out[i] = (uint8_t)m;
+    if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
+}
+
+// mode: 0 = work list (+ overflow bitmap; without one, a re-scan of the volume when the list overflowed), 1 = every voxel
 #ifndef DFB_EXACT_MINB
 #define DFB_EXACT_MINB 8
 #endif
@@ -628,17 +659,18 @@ template <int KMAX, int KT>
 __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const __grid_constant__ ProjParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
-    const bool use_list = !all_mode && count <= P.capacity;
-    const size_t n = use_list ? (size_t)count : nvox;
+    const bool overflow = !all_mode && count > P.capacity;
+    const bool sweep_bits = overflow && P.overflow_bits != nullptr;
+    const bool use_list = !all_mode && (!overflow || sweep_bits);
+    const size_t n = use_list ? (size_t)(overflow ? P.capacity : count) : nvox;
     const size_t plane = (size_t)P.ry * P.rz;
+    const int kk = KT > 0 ? KT : P.k;
     uint32_t done = 0;
-#ifndef DFB_EXACT_NO_PIPELINE
     if (use_list && KT > 0 && !P.rigid && nvox <= 0xffffffffull) {
         // Work-list path, software-pipelined: a voxel's state hangs on a chain of dependent gathers (list entry -> kNN ids,
         // v, w -> node data) ahead of ~1000 instructions of arithmetic.  The list entry is fetched two iterations ahead and
         // ids / v / w one iteration ahead, so only the node and depth gathers (L1 / L2 hits) are left inside an iteration.
         const uint32_t stride = gridDim.x * blockDim.x, cnt = (uint32_t)n;
-        const uint32_t plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
         uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
         if (t < cnt) {
             uint32_t i0 = P.list[t];
@@ -653,16 +685,7 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
                 uint16_t ids1[KMAX];
                 load_ids<KMAX>(P.knn, i1, KMAX, ids1);
                 const float v1 = P.tsdf[i1], w1 = P.weight[i1];
-                const uint32_t xq = i0 / plane32, rem = i0 - xq * plane32, yq = rem / rz32;
-                float v = v0, w = w0;
-                int m, f;
-                voxel_projective_exact<KT>(P, (int)xq + P.x0, (int)yq, (int)(rem - yq * rz32), ids0, &v, &w, &m, &f);
-                if (m) {
-                    P.tsdf[i0] = v;
-                    P.weight[i0] = w;
-                }
-                if (P.mask_out) P.mask_out[i0] = (uint8_t)m;
-                if (P.frustum_out) P.frustum_out[i0] = (uint8_t)f;
+                exact_voxel<KMAX, KT>(P, i0, nvox, plane, ids0, v0, w0);
                 ++done;
                 if (!has1) break;
                 t = tn; i0 = i1; i1 = i2; v0 = v1; w0 = w1;
@@ -670,40 +693,36 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
                 for (int j = 0; j < KMAX; ++j) ids0[j] = ids1[j];
             }
         }
-        for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
-        if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);
-        return;
+    } else {
+        for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+            const size_t i = use_list ? (size_t)P.list[t] : t;
+            uint16_t ids[KMAX];
+            if (!P.rigid) load_ids<KMAX>(P.knn, i, kk, ids);
+            if (!use_list && !all_mode) {
+                const size_t xq = i / plane, rem = i - xq * plane;
+                int m0, f0;
+                if (voxel_projective_classify<KMAX>(P, (int)xq + P.x0, (int)(rem / P.rz), (int)(rem % P.rz), ids, &m0, &f0) != CLS_UNCERTAIN) continue;
+            }
+            exact_voxel<KMAX, KT>(P, i, nvox, plane, ids, P.tsdf[i], P.weight[i]);
+            ++done;
+        }
     }
-#endif
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = use_list ? (size_t)P.list[t] : t;
-        int xs, y, z;
-        if (nvox <= 0xffffffffull) {   // 32-bit index arithmetic (the 64-bit divisions were 5 % of the kernel's instructions)
-            const uint32_t i32 = (uint32_t)i, plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
-            const uint32_t xq = i32 / plane32, rem = i32 - xq * plane32, yq = rem / rz32;
-            xs = (int)xq; y = (int)yq; z = (int)(rem - yq * rz32);
-        } else {
-            xs = (int)(i / plane);
-            const size_t rem = i - (size_t)xs * plane;
-            y = (int)(rem / P.rz);
-            z = (int)(rem - (size_t)y * P.rz);
+    if (sweep_bits) {
+        // the voxels that did not fit the list: sweep the bitmap, clearing it for the next call
+        const size_t nwords = (nvox + 31) / 32;
+        for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < nwords; wd += (size_t)gridDim.x * blockDim.x) {
+            uint32_t bits = P.overflow_bits[wd];
+            if (!bits) continue;
+            P.overflow_bits[wd] = 0u;
+            while (bits) {
+                const size_t i = wd * 32 + (size_t)(__ffs(bits) - 1);
+                bits &= bits - 1;
+                uint16_t ids[KMAX];
+                if (!P.rigid) load_ids<KMAX>(P.knn, i, kk, ids);
+                exact_voxel<KMAX, KT>(P, i, nvox, plane, ids, P.tsdf[i], P.weight[i]);
+                ++done;
+            }
         }
-        uint16_t ids[KMAX];
-        if (!P.rigid) load_ids<KMAX>(P.knn, i, P.k, ids);
-        if (!use_list && !all_mode) {
-            int m0, f0;
-            if (voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m0, &f0) != CLS_UNCERTAIN) continue;
-        }
-        float v = P.tsdf[i], w = P.weight[i];
-        int m, f;
-        voxel_projective_exact<KT>(P, xs + P.x0, y, z, ids, &v, &w, &m, &f);
-        if (m) {
-            P.tsdf[i] = v;
-            P.weight[i] = w;
-        }
-        if (P.mask_out) P.mask_out[i] = (uint8_t)m;
-        if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
-        ++done;
     }
     for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
     if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);
@@ -726,7 +745,7 @@ __global__ void __launch_bounds__(256, 3) vol_fast_kernel(const __grid_constant_
         if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
         cls = voxel_volume_classify<KMAX>(P, xs + P.x0, y, z, ids, &wi);
     }
-    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters);
+    push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters, P.overflow_bits);
     if (!in || cls == CLS_UNCERTAIN) return;
     if (cls == CLS_CLAMP) {
         float v = P.tsdf[i], w = P.weight[i];
@@ -745,33 +764,57 @@ __global__ void __launch_bounds__(256, 3) vol_fast_kernel(const __grid_constant_
 }
 
 template <int KMAX>
+__device__ __forceinline__ void vol_exact_voxel(const VolParams& P, size_t i, size_t plane) {
+    const int xs = (int)(i / plane);
+    const size_t rem = i - (size_t)xs * plane;
+    const int y = (int)(rem / P.rz);
+    const int z = (int)(rem - (size_t)y * P.rz);
+    uint16_t ids[KMAX];
+    if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
+    float v = P.tsdf[i], w = P.weight[i];
+    const bool upd = voxel_volume_exact(P, xs + P.x0, y, z, ids, &v, &w);
+    if (upd) {
+        P.tsdf[i] = v;
+        P.weight[i] = w;
+    }
+    if (P.mask_out) P.mask_out[i] = upd ? 1 : 0;
+}
+
+template <int KMAX>
 __global__ void __launch_bounds__(128) vol_exact_kernel(const __grid_constant__ VolParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
-    const bool use_list = !all_mode && count <= P.capacity;
-    const size_t n = use_list ? (size_t)count : nvox;
+    const bool overflow = !all_mode && count > P.capacity;
+    const bool sweep_bits = overflow && P.overflow_bits != nullptr;
+    const bool use_list = !all_mode && (!overflow || sweep_bits);
+    const size_t n = use_list ? (size_t)(overflow ? P.capacity : count) : nvox;
     const size_t plane = (size_t)P.ry * P.rz;
     uint32_t done = 0;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
         const size_t i = use_list ? (size_t)P.list[t] : t;
-        const int xs = (int)(i / plane);
-        const size_t rem = i - (size_t)xs * plane;
-        const int y = (int)(rem / P.rz);
-        const int z = (int)(rem - (size_t)y * P.rz);
-        uint16_t ids[KMAX];
-        if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
         if (!use_list && !all_mode) {
+            const int xs = (int)(i / plane);
+            const size_t rem = i - (size_t)xs * plane;
+            uint16_t ids[KMAX];
+            if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
             float wi;
-            if (voxel_volume_classify<KMAX>(P, xs + P.x0, y, z, ids, &wi) != CLS_UNCERTAIN) continue;
+            if (voxel_volume_classify<KMAX>(P, xs + P.x0, (int)(rem / P.rz), (int)(rem % P.rz), ids, &wi) != CLS_UNCERTAIN) continue;
         }
-        float v = P.tsdf[i], w = P.weight[i];
-        const bool upd = voxel_volume_exact(P, xs + P.x0, y, z, ids, &v, &w);
-        if (upd) {
-            P.tsdf[i] = v;
-            P.weight[i] = w;
-        }
-        if (P.mask_out) P.mask_out[i] = upd ? 1 : 0;
+        vol_exact_voxel<KMAX>(P, i, plane);
         ++done;
+    }
+    if (sweep_bits) {
+        const size_t nwords = (nvox + 31) / 32;
+        for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < nwords; wd += (size_t)gridDim.x * blockDim.x) {
+            uint32_t bits = P.overflow_bits[wd];
+            if (!bits) continue;
+            P.overflow_bits[wd] = 0u;
+            while (bits) {
+                vol_exact_voxel<KMAX>(P, wd * 32 + (size_t)(__ffs(bits) - 1), plane);
+                bits &= bits - 1;
+                ++done;
+            }
+        }
     }
     for (int o = 16; o > 0; o >>= 1) done += __shfl_xor_sync(0xffffffffu, done, o);
     if ((threadIdx.x & 31) == 0 && done) atomicAdd(P.counters + 1, done);

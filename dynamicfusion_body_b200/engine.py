@@ -48,12 +48,15 @@ class Workspace:
         self.n_bricks = int(n_bricks)
         self.brick_cls = torch.zeros(4 * self.n_bricks, dtype=torch.uint8, device=device) if n_bricks else None
         self.brick_lists = torch.zeros(2 * self.n_bricks, dtype=torch.int32, device=device) if n_bricks else None
+        # one bit per voxel for deferred voxels that find the list full (kept all-zero between calls by the exact pass)
+        self.overflow_bits = torch.zeros((int(n_voxels) + 31) // 32, dtype=torch.int32, device=device)
 
     def struct(self, use_bricks=True):
         s = _capi.Workspace()
         s.list = self.list.data_ptr()
         s.capacity = self.capacity
         s.counters = self.counters.data_ptr()
+        s.overflow_bits = self.overflow_bits.data_ptr()
         if use_bricks and self.brick_cls is not None:
             s.brick_cls = self.brick_cls.data_ptr()
             s.brick_lists = self.brick_lists.data_ptr()

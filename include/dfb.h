@@ -92,6 +92,11 @@ typedef struct dfb_workspace {
     /* optional (NULL = no brick culling), n_bricks = dfb_brick_count(x1-x0, ry, rz): */
     uint8_t* brick_cls;    /* device [4*n_bricks]: class (0xFF = MIXED), frustum bits, open views, settled CLAMP bits */
     uint32_t* brick_lists; /* device [2*n_bricks] */
+    /* optional, device [ceil(slab voxels / 32)], zeroed once by the caller: voxels deferred after `list` has filled up are
+     * marked here instead and the exact pass consumes (and clears) the marks -- a call that overflows the list is then
+     * still exact.  NULL: an overflowing call re-scans the volume with the per-voxel classifier, which is only equivalent
+     * when no brick workspace is given (brick-level decisions are not replayed by the re-scan). */
+    uint32_t* overflow_bits;
 } dfb_workspace;
 
 int dfb_version(void);

@@ -185,3 +185,54 @@ def test_class_level_errors_and_signatures():
         fdm.compute_live_tsdf([sc.depths[0]], [])
     t, w = fdm.fuseDepths(sc.depths[0], np.eye(4)[:3], np.full((16, 16, 16), 0.2), np.zeros((16, 16, 16)))
     assert t.shape == (16, 16, 16) and t.dtype == np.float64
+
+
+@pytest.mark.parametrize("views,k", [(1, 4), (3, 8)])
+def test_deferred_list_overflow_is_still_exact(views, k):
+    """More voxels deferred than the work list holds: the rest is marked in the overflow bitmap and swept by the exact
+    pass (brick-level decisions included) -- same result as with a list that fits."""
+    torch, engine = _ctx()
+    from dynamicfusion_body_b200 import synth
+    import scenes
+    from oracle import tsdf as ot
+    sc = synth.make_scene(res=40, k=k, n_nodes=150, seed=8, rows=96, cols=128, n_views=views)
+    R = 40
+    res = (R, R, R)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k, 0, R)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    nw = np.full(sc.n_nodes, np.float32(sc.node_w))
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, sc.node_pos, sc.node_dq, nw, sc.lw,
+                                           sc.depths, sc.K, sc.Kinv, sc.tdist, extrinsics=sc.extrinsics)
+    wf = engine.DeviceWarpField(sc.k)
+    wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
+    depths = torch.from_numpy(sc.depths).cuda()
+    outs = []
+    for capacity in (None, 1024):
+        vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+        if capacity:
+            vol.workspace.capacity = capacity
+        for frame in range(2):                           # twice: the bitmap must come back clean
+            m, f = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, sc.extrinsics, sc.tdist, want_masks=True)
+        st = vol.workspace.stats()
+        assert st["exact_processed"] == st["deferred"] and (capacity is None or st["deferred"] > capacity)
+        assert not vol.workspace.overflow_bits.any()
+        outs.append((vol.tsdf.cpu().numpy().ravel(), vol.weight.cpu().numpy().ravel(), m.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+    ok = ~tie
+    for v in range(views):
+        assert np.array_equal(((outs[1][2] >> v) & 1).astype(bool)[ok], om[v][ok])
+    # a1 through the same mechanism (live TSDF of the node-warped mesh, no global lw, a thick band)
+    wv = synth.blend_warp(sc.vertices, sc.node_pos, sc.node_dq, nw, sc.vert_knn, lw=None)
+    td = 3.0
+    live = torch.from_numpy(np.clip(synth.mesh_sdf_volume(res, wv, sc.normals), -1.5 * td, 1.5 * td)).cuda()
+    a1 = []
+    for capacity in (None, 128):
+        vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+        if capacity:
+            vol.workspace.capacity = capacity
+        engine.update_volume(vol, wf, None, live, td)
+        st = vol.workspace.stats()
+        assert st["exact_processed"] == st["deferred"] > 128
+        assert not vol.workspace.overflow_bits.any()
+        a1.append((vol.tsdf.cpu().numpy(), vol.weight.cpu().numpy()))
+    assert np.array_equal(a1[0][0], a1[1][0]) and np.array_equal(a1[0][1], a1[1][1])
