@@ -24,3 +24,40 @@ def oracle_knn(res, node_pos, k, x0=0, x1=None):
 
 def bits(mask_bits, view):
     return ((np.asarray(mask_bits) >> view) & 1).astype(bool)
+
+
+def edge_scene(kind, views=1):
+    """Small a3 scenes for the edge cases that both the GPU tests and the host build of the kernel logic run:
+    'invalid_depth' (NaN, +-inf, positive pixels), 'general_K' (skewed K, third row != (0,0,1)),
+    'camera_inside' (voxels behind the camera and exactly on the camera plane)."""
+    import copy
+    from dynamicfusion_body_b200 import synth
+    if kind == "invalid_depth":
+        sc = copy.copy(synth.make_scene(res=32, k=4, n_nodes=100, seed=6, rows=64, cols=80))
+        rng = np.random.default_rng(0)
+        d = sc.depths.copy()
+        r = rng.random(d.shape)
+        d[r < 0.10] = np.nan
+        d[(r >= 0.10) & (r < 0.15)] = np.inf
+        d[(r >= 0.15) & (r < 0.20)] = -np.inf
+        d[(r >= 0.20) & (r < 0.25)] = 7.5
+        d[:, 10:30, 20:50] = np.nan                                                        # a whole block without data
+        sc.depths = d
+    elif kind == "general_K":
+        sc = copy.copy(synth.make_scene(res=32, k=4, n_nodes=100, seed=7, rows=64, cols=80, n_views=views))
+        K = sc.K.copy()
+        K[0, 1] = 1.5; K[1, 0] = -0.7; K[2] = [2e-4, -1e-4, 1.05]
+        sc.K, sc.Kinv = K, np.linalg.inv(K)
+    elif kind == "camera_inside":
+        sc = copy.copy(synth.make_scene(res=32, k=4, n_nodes=100, seed=9, rows=64, cols=80))
+        E = np.concatenate([np.eye(3), -np.array([[15.5], [16.25], [16.0]])], 1)           # camera at the volume centre, looking along +z
+        sc.extrinsics = E[None]
+        sc.lw = np.array([1.0, 0, 0, 0, 0, 0, 0, 0])
+        sc.node_dq = np.tile(np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32), (sc.n_nodes, 1))  # identity warp: voxel z = 16 is the camera plane
+        sc.K = np.array([[30.0, 0, 40.0], [0, 30.0, 32.0], [0, 0, 1.0]])
+        sc.Kinv = np.linalg.inv(sc.K)
+        rng = np.random.default_rng(1)
+        sc.depths = -(4.0 + 6.0 * rng.random((1, 64, 80))).astype(np.float32)
+    else:
+        raise ValueError(kind)
+    return sc

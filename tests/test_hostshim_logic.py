@@ -201,3 +201,30 @@ def test_degenerate_blends(case):
         assert np.array_equal(scenes.bits(mask, 0), om[0]) and np.array_equal(scenes.bits(frus, 0), ofr[0])
         assert np.abs(tv - ov).max() <= 1e-5 * s.tdist
     hs.set_bricks(enable=False)
+
+
+@pytest.mark.parametrize("kind", ["invalid_depth", "general_K", "camera_inside"])
+@pytest.mark.parametrize("bricks", [False, True])
+def test_projective_edge_scenes(kind, bricks):
+    """NaN / +-inf / positive depth pixels, a non-pinhole K, voxels behind and on the camera plane: the host build of the
+    two tiers (with and without the brick / region classifier in front) against the oracle, masks bit for bit."""
+    s = scenes.edge_scene(kind)
+    R = s.res
+    vox, idx, tie = scenes.oracle_knn((R, R, R), s.node_pos, s.k)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=s.tdist)
+    nw = np.full(s.n_nodes, s.node_w)
+    with np.errstate(all="ignore"):
+        ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, s.node_pos, s.node_dq, nw, s.lw,
+                                               s.depths, s.K, s.Kinv, s.tdist, extrinsics=s.extrinsics)
+    wf = hs.HostWarpField(s.node_pos, s.node_dq, np.float32(s.node_w), s.k, knn=idx, lw=s.lw)
+    cls_b = hs.set_bricks(idx, s.k, (R, R, R), enable=True) if bricks else hs.set_bricks(enable=False)
+    try:
+        tv, tw = t0.copy(), w0.copy()
+        mask, frus, cls, nunc = hs.update_projective(tv, tw, (R, R, R), wf, s.depths, s.K, s.Kinv, s.tdist, extrinsics=s.extrinsics)
+    finally:
+        hs.set_bricks(enable=False)
+    ok = ~tie
+    assert np.array_equal(scenes.bits(mask, 0)[ok], om[0][ok]) and np.array_equal(scenes.bits(frus, 0)[ok], ofr[0][ok])
+    assert np.abs(tv - ov)[ok].max() <= 1e-5 * s.tdist
+    assert (np.abs(tw - ow) / np.maximum(1, ow))[ok].max() <= 1e-6
+    assert om[0].any() and not om[0].all()

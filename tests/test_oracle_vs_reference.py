@@ -217,3 +217,22 @@ def test_fuseDepths_invalid_depth_values_live():
         v, w, m, fr = ot.fuse_depth_rigid(t0.ravel(), w0.ravel(), ot.voxel_grid((R, R, R)), dm, lw34, K, np.linalg.inv(K), 0.5, R)
     assert np.array_equal(v, rt.ravel()) and np.array_equal(w, rw.ravel())
     assert 0 < m.sum() < fr.sum() and np.isfinite(rt).all()
+
+
+def test_fuseDepths_camera_inside_volume_live():
+    """Voxels behind the camera (negative projective divisor) and exactly on the camera plane (divisor 0 -> None) through
+    the unmodified FusionDM.fuseDepths (core/util.py:312-320 has no sign test)."""
+    util, Fusion, FusionDM = refload.load()
+    rng = np.random.default_rng(6)
+    R = 8
+    K = np.array([[12., 0, 20], [0, 12., 16], [0, 0, 1]])
+    fdm = FusionDM(0.5, K, tsdf_res=R)
+    dm = -(rng.random((32, 40)) * 3 + 1).astype(np.float32)
+    lw34 = np.concatenate([np.eye(3), np.zeros((3, 1))], 1)                     # camera at the volume centre (pos = idx - R/2)
+    t0 = rng.normal(size=(R, R, R)); w0 = np.floor(rng.random((R, R, R)) * 3)
+    with refload.quiet(), np.errstate(all="ignore"):
+        rt, rw = fdm.fuseDepths(dm, lw34, t0.copy(), w0.copy())
+        v, w, m, fr = ot.fuse_depth_rigid(t0.ravel(), w0.ravel(), ot.voxel_grid((R, R, R)), dm, lw34, K, np.linalg.inv(K), 0.5, R)
+    assert np.array_equal(v, rt.ravel()) and np.array_equal(w, rw.ravel())
+    m = m.reshape(R, R, R)
+    assert m[:, :, :R // 2].any() and m[:, :, R // 2 + 1:].any() and not m[:, :, R // 2].any()
