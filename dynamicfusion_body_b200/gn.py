@@ -193,9 +193,10 @@ class Problem:
             H2, g2, c2 = assemble(x_new)
             cost_new = float(c2[0].item())
             ok = np.isfinite(cost_new) and cost_new < cost
-            hist.append({"cost": cost_new, "lambda": lam, "accepted": bool(ok), "pcg_iterations": int(info[6].item())})
+            # the PCG iteration count stays on the device until the loop is over (one host sync per iteration: the cost)
+            hist.append({"cost": cost_new, "lambda": lam, "accepted": bool(ok), "pcg_iterations": info[6:7].clone()})
             if verbose:
-                print("GN it %d: cost %.6e -> %.6e  lambda %.2e  %s  pcg %d" % (it, cost, cost_new, lam, "ok" if ok else "rejected", hist[-1]["pcg_iterations"]))
+                print("GN it %d: cost %.6e -> %.6e  lambda %.2e  %s  pcg %d" % (it, cost, cost_new, lam, "ok" if ok else "rejected", int(info[6].item())))
             if ok:
                 rel = (cost - cost_new) / max(cost, 1e-300)
                 x, H, g, cost = x_new, H2, g2, cost_new
@@ -207,6 +208,10 @@ class Problem:
                 lam *= 4.0
                 if lam > 1e8:
                     break
+        if hist:
+            its = torch.cat([h["pcg_iterations"] for h in hist]).cpu().numpy()
+            for h, n_it in zip(hist, its):
+                h["pcg_iterations"] = int(n_it)
         return GNResult(x=x, cost0=cost0, cost=cost, iterations=it, accepted=accepted, history=hist)
 
     # -- rigid fit of the global dq (core/fusion.py:350-362) -----------------------------------------------------------
