@@ -93,3 +93,18 @@ def test_scene_is_deterministic_and_consistent():
     assert np.allclose(np.linalg.norm(a.node_dq[:, :4], axis=1), 1, atol=1e-6)
     t = a.nodes_as_reference_tuples()
     assert len(t) == a.n_nodes and t[0][2].shape == (8,) and isinstance(t[0][3], float)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--res", "64", "--nodes", "200", "--ref-sample", "20000"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "warped_tsdf_voxels_per_sec" and d["unit"] == "voxels/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
