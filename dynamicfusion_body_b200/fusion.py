@@ -226,6 +226,23 @@ class _FusionBase:
         v, f, n, _ = self.surface_extractor(_as_np(self._tsdf), step_size)
         self._vertices, self._faces, self._normals = np.asarray(v, dtype=np.float32), f, np.asarray(n, dtype=np.float32)
 
+    def average_edge_dist_in_face(self, f):
+        """core/fusion.py:592-596."""
+        v1, v2, v3 = self._vertices[f[0]], self._vertices[f[1]], self._vertices[f[2]]
+        return (np.linalg.norm(v1 - v2) + np.linalg.norm(v1 - v3) + np.linalg.norm(v2 - v3)) / 3
+
+    def write_canonical_mesh(self, path, filename):
+        """core/fusion.py:577-586 / core/fusion_dm.py:339-354: extract the canonical surface (through `surface_extractor`,
+        step size 1) and write it as OBJ; FusionDM maps vertices and normals to world coordinates with `_IND` first."""
+        from . import io
+        verts, faces, normals, _ = self.marching_cubes(self._tsdf, step_size=1)
+        ind = getattr(self, "_IND", None)
+        if ind is not None:
+            rot, trans = ind[:3, :3], ind[:3, 3]
+            verts = np.asarray(verts, dtype=np.float64) @ rot.T + trans
+            normals = np.asarray(normals, dtype=np.float64) @ rot.T
+        io.write_obj(os.path.join(path, filename), verts, normals, faces, face_normals=ind is not None)
+
     # ---- SURVEY 8f rank 1: closest-point correspondences ---------------------------------------------
     def _live_vertices(self, curr_tsdf, live_vertices):
         if live_vertices is None:
@@ -283,6 +300,9 @@ class Fusion(_FusionBase):
             self._vertices = np.asarray(vertices, dtype=np.float32)
             self._normals = None if normals is None else np.asarray(normals, dtype=np.float32)
             self._faces = faces
+        elif self.surface_extractor is not None and nodes is None:
+            self.marching_cubes()                                     # core/fusion.py:88 (initial marching cubes)
+            faces = self._faces
         if radius is not None:
             self._radius = float(radius)
         elif self._vertices is not None and faces is not None and len(faces):

@@ -66,3 +66,20 @@ def write_warp_field(nodes, path, filename, itercounter):
 def read_warp_field(fpath):
     with open(fpath, 'rb') as f:
         return pickle.load(f)
+
+
+def write_obj(fpath, verts, normals=None, faces=None, face_normals=False):
+    """OBJ text in the reference's two flavours: Fusion.write_canonical_mesh (core/fusion.py:577-586: `v`, `vn`, `f a b c`)
+    and FusionDM.write_canonical_mesh (core/fusion_dm.py:339-354: faces as `f a//a b//b c//c`); 1-based indices, %f formatting."""
+    with open(fpath, 'w') as f:
+        for v in verts:
+            f.write('v %f %f %f\n' % (v[0], v[1], v[2]))
+        if normals is not None:
+            for n in normals:
+                f.write('vn %f %f %f\n' % (n[0], n[1], n[2]))
+        if faces is not None:
+            for t in faces:
+                if face_normals:
+                    f.write('f %d//%d %d//%d %d//%d\n' % (t[0] + 1, t[0] + 1, t[1] + 1, t[1] + 1, t[2] + 1, t[2] + 1))
+                else:
+                    f.write('f %d %d %d\n' % (t[0] + 1, t[1] + 1, t[2] + 1))

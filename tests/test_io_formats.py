@@ -56,3 +56,29 @@ def test_proj_matrix_and_warp_field(tmp_path):
     io.write_warp_field(nodes, str(tmp_path), "test", 7)
     back = io.read_warp_field(os.path.join(str(tmp_path), "test__7.p"))
     assert back[0][0] == 3 and np.array_equal(back[0][2], nodes[0][2]) and back[0][3] == 2.5
+
+
+@pytest.mark.skipif(not refload.available(), reason="reference checkout not present")
+def test_obj_writer_matches_reference(tmp_path):
+    """io.write_obj against the unmodified Fusion.write_canonical_mesh / FusionDM.write_canonical_mesh (core/fusion.py:577-586,
+    core/fusion_dm.py:339-354) with skimage's marching cubes stubbed to return a fixed mesh."""
+    import sys
+    util, Fusion, FusionDM = refload.load()
+    rng = np.random.default_rng(2)
+    verts = (rng.random((30, 3)) * 20).astype(np.float32); normals = rng.normal(size=(30, 3)).astype(np.float32)
+    faces = rng.integers(0, 30, size=(40, 3)).astype(np.int32)
+    sys.modules["skimage.measure"].marching_cubes_lewiner = lambda *a, **kw: (verts, faces, normals, None)
+    try:
+        f = refload.make_fusion([(0, np.zeros(3, np.float32), np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32), 1.0)] * 5, np.zeros((2, 2, 2)),
+                                np.zeros((2, 2, 2)), 1.0, 4, None)
+        f.write_canonical_mesh(str(tmp_path), "ref.obj")
+        io.write_obj(str(tmp_path / "mine.obj"), verts, normals, faces)
+        assert (tmp_path / "ref.obj").read_text() == (tmp_path / "mine.obj").read_text()
+        fdm = FusionDM(0.5, np.eye(3), tsdf_res=4)
+        fdm._IND = np.array([[0.5, 0, 0, 1.0], [0, 0.5, 0, -2.0], [0, 0, 0.5, 0.25], [0, 0, 0, 1]])
+        fdm.write_canonical_mesh(str(tmp_path), "refdm.obj")
+        rot, trans = fdm._IND[:3, :3], fdm._IND[:3, 3]
+        io.write_obj(str(tmp_path / "minedm.obj"), verts.astype(np.float64) @ rot.T + trans, normals.astype(np.float64) @ rot.T, faces, face_normals=True)
+        assert (tmp_path / "refdm.obj").read_text() == (tmp_path / "minedm.obj").read_text()
+    finally:
+        del sys.modules["skimage.measure"].marching_cubes_lewiner
