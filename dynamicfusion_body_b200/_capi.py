@@ -103,6 +103,12 @@ def declare(lib, prefix="dfb_", device=True):
         "corr_select": ([vp, vp, C.c_int64, vp, vp, C.c_int, vp, vp, vp], C.c_int),
         "graph_unsupported": ([vp, C.c_int64, vp, C.c_int, vp, vp, vp, vp], C.c_int),
         "graph_sample_rounds": ([C.POINTER(PointGrid), C.c_double, C.c_int, vp, vp, vp], C.c_int),
+        "mc_level_scratch_floats": ([], C.c_int64),
+        "mc_level": ([vp, C.c_int64, vp, vp, vp], C.c_int),
+        "mc_rows": ([C.c_int, C.c_int, C.c_int], C.c_int64),
+        "mc_chunks": ([C.c_int, C.c_int, C.c_int, C.c_int], C.c_int64),
+        "mc_count": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp], C.c_int),
+        "mc_emit": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
         "gn_solve": ([C.c_int, vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
@@ -145,4 +151,5 @@ EXPORTS = [
     "dfb_gn_residuals", "dfb_gn_residuals_lw", "dfb_gn_pattern_rows", "dfb_gn_pattern_cols", "dfb_gn_normal_eq",
     "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",
     "dfb_point_grid_scratch_ints", "dfb_point_grid_build", "dfb_point_grid_knn", "dfb_corr_select", "dfb_graph_unsupported", "dfb_graph_sample_rounds",
+    "dfb_mc_level_scratch_floats", "dfb_mc_level", "dfb_mc_rows", "dfb_mc_chunks", "dfb_mc_count", "dfb_mc_emit",
 ]

@@ -6,7 +6,7 @@ import sys
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 OUT = os.path.join(_PKG, "libdfb_b200.so")
-SOURCES = ["common.cu", "tsdf.cu", "knn.cu", "gn.cu", "graph.cu"]
+SOURCES = ["common.cu", "tsdf.cu", "knn.cu", "gn.cu", "graph.cu", "mc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

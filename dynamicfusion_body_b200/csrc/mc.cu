@@ -1,0 +1,231 @@
+// mc.cu -- device surface extraction: indexed level-set mesh of a device-resident volume, the replacement
+// of skimage.measure.marching_cubes_lewiner as called by Fusion.marching_cubes / write_canonical_mesh (core/fusion.py:554-586).
+// Per-sample logic in dfb_mc.h; here: level (min/max), count + scan, emit.  One warp walks one z-row of the sampled grid, 32
+// samples at a time, so the volume is read in 128-byte lines (step 1) and every prefix is a ballot / shuffle away.
+#include "common.h"
+#include "dfb_mc.h"
+
+namespace dfb {
+namespace {
+
+constexpr int MC_WARPS = 8;
+constexpr int LEVEL_BLOCKS = 592;   // 4 CTAs per SM x 148 SMs
+
+__global__ void __launch_bounds__(256) mc_minmax_kernel(const float* __restrict__ vol, int64_t n, float* __restrict__ part) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __ldg(vol + i);
+        lo = fminf(lo, v); hi = fmaxf(hi, v);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float s_lo[8], s_hi[8];
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+        part[2 * blockIdx.x] = lo; part[2 * blockIdx.x + 1] = hi;
+    }
+}
+
+// level = 0.5 * (min + max) in float64, rounded to the volume's float32 (skimage: level=None)
+__global__ void __launch_bounds__(32) mc_level_kernel(const float* __restrict__ part, int nblocks, float* __restrict__ out) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < nblocks; i += 32) { lo = fminf(lo, part[2 * i]); hi = fmaxf(hi, part[2 * i + 1]); }
+    for (int o = 16; o; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if (threadIdx.x == 0) { out[0] = (float)(0.5 * ((double)lo + (double)hi)); out[1] = lo; out[2] = hi; }
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_excl_scan(int v, int lane) {
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    return inc - v;
+}
+
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_count_kernel(McGrid g, const float* __restrict__ level, McChunk* __restrict__ chunks,
+                                                                 int32_t* __restrict__ row_nv, int32_t* __restrict__ row_nt) {
+    g.level = *level;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
+    if (row >= g.nx * g.ny) return;
+    const int i = row / g.ny, j = row - i * g.ny;
+    const bool cell_row = i + 1 < g.nx && j + 1 < g.ny;
+    int nv = 0, nt = 0;
+    for (int c = 0; c < g.ncz; ++c) {
+        const int k = 32 * c + lane;
+        uint32_t bits = 0;
+        if (k < g.nz) {
+            const float v0 = mc_val(g, i, j, k);
+            bits = mc_edge_bits(g, i, j, k, v0);
+            if (cell_row && k + 1 < g.nz) {
+                float v[8];
+                const int cs = mc_cell_case(g, i, j, k, v);
+                if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i, j, k, nullptr);
+            }
+        }
+        McChunk rec;
+        rec.voff = nv;
+        rec.m[0] = __ballot_sync(0xffffffffu, bits & 1u);
+        rec.m[1] = __ballot_sync(0xffffffffu, bits & 2u);
+        rec.m[2] = __ballot_sync(0xffffffffu, bits & 4u);
+        if (lane == 0) chunks[(size_t)row * g.ncz + c] = rec;
+        nv += __popc(rec.m[0]) + __popc(rec.m[1]) + __popc(rec.m[2]);
+    }
+    nt = warp_sum(nt);
+    if (lane == 0) { row_nv[row] = nv; row_nt[row] = nt; }
+}
+
+// one CTA: in-place exclusive scan of both row arrays; totals land in slot [rows]
+__global__ void __launch_bounds__(1024) mc_scan_kernel(int32_t* __restrict__ row_nv, int32_t* __restrict__ row_nt, int rows) {
+    __shared__ int s_a[32], s_b[32];
+    __shared__ int s_carry[2];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_carry[0] = 0; s_carry[1] = 0; }
+    __syncthreads();
+    for (int base = 0; base < rows; base += 1024) {
+        const int r = base + threadIdx.x;
+        const int a = r < rows ? row_nv[r] : 0, b = r < rows ? row_nt[r] : 0;
+        int ea = warp_excl_scan(a, lane), eb = warp_excl_scan(b, lane);
+        if (lane == 31) { s_a[w] = ea + a; s_b[w] = eb + b; }
+        __syncthreads();
+        if (w == 0) {
+            const int ta = s_a[lane], tb = s_b[lane];
+            const int xa = warp_excl_scan(ta, lane), xb = warp_excl_scan(tb, lane);
+            s_a[lane] = xa; s_b[lane] = xb;
+        }
+        __syncthreads();
+        const int ca = s_carry[0], cb = s_carry[1];
+        ea += s_a[w] + ca; eb += s_b[w] + cb;
+        if (r < rows) { row_nv[r] = ea; row_nt[r] = eb; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_carry[0] = ea + a; s_carry[1] = eb + b; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { row_nv[rows] = s_carry[0]; row_nt[rows] = s_carry[1]; }
+}
+
+__global__ void __launch_bounds__(MC_WARPS * 32) mc_emit_kernel(McGrid g, const float* __restrict__ level, const McChunk* __restrict__ chunks,
+                                                                const int32_t* __restrict__ row_voff, const int32_t* __restrict__ row_toff,
+                                                                float* __restrict__ verts, float* __restrict__ normals,
+                                                                float* __restrict__ values, int32_t* __restrict__ faces) {
+    g.level = *level;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * MC_WARPS + (threadIdx.x >> 5);
+    if (row >= g.nx * g.ny) return;
+    if (row_voff[row + 1] == row_voff[row] && row_toff[row + 1] == row_toff[row]) return;   // nothing crosses this row
+    const int i = row / g.ny, j = row - i * g.ny;
+    const bool cell_row = i + 1 < g.nx && j + 1 < g.ny;
+    int tbase = row_toff[row];
+    for (int c = 0; c < g.ncz; ++c) {
+        const int k = 32 * c + lane;
+        const McChunk rec = chunks[(size_t)row * g.ncz + c];
+        const uint32_t any = rec.m[0] | rec.m[1] | rec.m[2];
+        int8_t edges[3 * DFB_MC_MAX_TRIS];
+        int nt = 0;
+        if (k < g.nz) {
+            if ((any >> lane) & 1u) {
+                int id = mc_vertex_id(g, chunks, row_voff, i, j, k, 0);
+                for (int d = 0; d < 3; ++d)
+                    if ((rec.m[d] >> lane) & 1u) {
+                        float p[3], n[3], val;
+                        mc_vertex(g, i, j, k, d, p, n, val);
+                        verts[3 * (size_t)id] = p[0]; verts[3 * (size_t)id + 1] = p[1]; verts[3 * (size_t)id + 2] = p[2];
+                        if (normals) { normals[3 * (size_t)id] = n[0]; normals[3 * (size_t)id + 1] = n[1]; normals[3 * (size_t)id + 2] = n[2]; }
+                        if (values) values[id] = val;
+                        ++id;
+                    }
+            }
+            if (cell_row && k + 1 < g.nz) {
+                float v[8];
+                const int cs = mc_cell_case(g, i, j, k, v);
+                if (cs != 0 && cs != 255) nt = mc_cell_tris(cs, v, g.level, i, j, k, edges);
+            }
+        }
+        const int toff = tbase + warp_excl_scan(nt, lane);
+        for (int t = 0; t < nt; ++t)
+            for (int q = 0; q < 3; ++q)
+                faces[3 * (size_t)(toff + t) + q] = mc_cell_edge_vertex(g, chunks, row_voff, i, j, k, edges[3 * t + q]);
+        tbase += warp_sum(nt);
+    }
+}
+
+int check_grid(const float* vol, int rx, int ry, int rz, int step) {
+    DFB_REQUIRE(vol != nullptr, "mc: null volume");
+    DFB_REQUIRE(rx >= 2 && ry >= 2 && rz >= 2, "mc: the volume needs at least 2 samples per axis (got %d x %d x %d)", rx, ry, rz);
+    DFB_REQUIRE(step >= 1, "mc: step must be >= 1 (got %d)", step);
+    DFB_REQUIRE((int64_t)rx * ry * rz < ((int64_t)1 << 31), "mc: volume too large for 32-bit vertex ids");
+    return DFB_OK;
+}
+
+}  // namespace
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" int64_t dfb_mc_level_scratch_floats(void) { return 2 * LEVEL_BLOCKS; }
+
+extern "C" int dfb_mc_level(const float* vol, int64_t n, float* scratch, float* level_out, dfb_stream_t stream) {
+    DFB_REQUIRE(vol && scratch && level_out, "mc_level: null pointer");
+    DFB_REQUIRE(n > 0, "mc_level: empty volume");
+    cudaStream_t s = (cudaStream_t)stream;
+    mc_minmax_kernel<<<LEVEL_BLOCKS, 256, 0, s>>>(vol, n, scratch);
+    DFB_LAUNCH_CHECK("mc_minmax_kernel");
+    mc_level_kernel<<<1, 32, 0, s>>>(scratch, LEVEL_BLOCKS, level_out);
+    DFB_LAUNCH_CHECK("mc_level_kernel");
+    return DFB_OK;
+}
+
+extern "C" int64_t dfb_mc_rows(int rx, int ry, int step) {
+    if (rx < 1 || ry < 1 || step < 1) return 0;
+    return (int64_t)((rx - 1) / step + 1) * ((ry - 1) / step + 1);
+}
+
+extern "C" int64_t dfb_mc_chunks(int rx, int ry, int rz, int step) {
+    if (rz < 1 || step < 1) return 0;
+    return dfb_mc_rows(rx, ry, step) * ((((rz - 1) / step + 1) + 31) / 32);
+}
+
+extern "C" int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, const float* level, dfb_mc_chunk* chunks,
+                            int32_t* row_voff, int32_t* row_toff, dfb_stream_t stream) {
+    int rc = check_grid(vol, rx, ry, rz, step);
+    if (rc != DFB_OK) return rc;
+    DFB_REQUIRE(level && chunks && row_voff && row_toff, "mc_count: null pointer");
+    McGrid g;
+    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f);
+    const int rows = g.nx * g.ny;
+    cudaStream_t s = (cudaStream_t)stream;
+    mc_count_kernel<<<(rows + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, 0, s>>>(g, level, reinterpret_cast<McChunk*>(chunks), row_voff, row_toff);
+    DFB_LAUNCH_CHECK("mc_count_kernel");
+    mc_scan_kernel<<<1, 1024, 0, s>>>(row_voff, row_toff, rows);
+    DFB_LAUNCH_CHECK("mc_scan_kernel");
+    return DFB_OK;
+}
+
+extern "C" int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, const float* level, const dfb_mc_chunk* chunks,
+                           const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values,
+                           int32_t* faces, dfb_stream_t stream) {
+    int rc = check_grid(vol, rx, ry, rz, step);
+    if (rc != DFB_OK) return rc;
+    DFB_REQUIRE(level && chunks && row_voff && row_toff, "mc_emit: null pointer");
+    DFB_REQUIRE(verts && faces, "mc_emit: verts and faces are required (normals / values may be null)");
+    McGrid g;
+    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f);
+    const int rows = g.nx * g.ny;
+    cudaStream_t s = (cudaStream_t)stream;
+    mc_emit_kernel<<<(rows + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, 0, s>>>(g, level, reinterpret_cast<const McChunk*>(chunks), row_voff, row_toff,
+                                                                             verts, normals, values, faces);
+    DFB_LAUNCH_CHECK("mc_emit_kernel");
+    return DFB_OK;
+}

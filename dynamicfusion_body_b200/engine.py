@@ -441,3 +441,45 @@ def uniform_sample(pts, radius, device=None, rounds_per_call=16):
             break
     idx = torch.nonzero(state == 1).reshape(-1)
     return p[idx].cpu().numpy(), idx.cpu().numpy().astype(np.int64)
+
+
+def marching_cubes(vol, step_size=1, level=None):
+    """Surface extraction on the device (include/dfb.h `dfb_mc_*`): the call the reference makes as
+    measure.marching_cubes_lewiner(volume, step_size=..., allow_degenerate=False) (core/fusion.py:554-568, 579).
+    vol: (rx, ry, rz) CUDA tensor or host array; level None = 0.5 * (min + max) like skimage.  Returns host arrays
+    (verts (V,3) float32 voxel coordinates, faces (F,3) int32, normals (V,3) float32, values (V,) float32)."""
+    if not isinstance(vol, torch.Tensor):
+        vol = _to_dev(np.asarray(vol), torch.float32, _require_cuda(None))
+    if vol.dim() != 3:
+        raise ValueError("marching_cubes needs a 3-D volume")
+    step = int(step_size)
+    if step < 1:
+        raise ValueError("step_size must be >= 1")
+    if not vol.is_cuda:
+        vol = vol.to(_require_cuda(None))
+    vol = vol.to(dtype=torch.float32).contiguous()
+    rx, ry, rz = (int(n) for n in vol.shape)
+    if min(rx, ry, rz) < 2:
+        raise ValueError("marching_cubes needs at least 2 samples per axis")
+    L = _capi.lib()
+    dev = vol.device
+    with torch.cuda.device(dev):
+        lv = torch.empty(3, dtype=torch.float32, device=dev)
+        if level is None:
+            scratch = torch.empty(int(L.dfb_mc_level_scratch_floats()), dtype=torch.float32, device=dev)
+            _capi.check(L.dfb_mc_level(_ptr(vol), vol.numel(), _ptr(scratch), _ptr(lv), _stream()))
+        else:
+            lv.fill_(float(np.float32(level)))
+        rows = int(L.dfb_mc_rows(rx, ry, step))
+        chunks = torch.empty((int(L.dfb_mc_chunks(rx, ry, rz, step)), 4), dtype=torch.int32, device=dev)
+        offs = torch.empty((2, rows + 1), dtype=torch.int32, device=dev)
+        _capi.check(L.dfb_mc_count(_ptr(vol), rx, ry, rz, step, _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]), _stream()))
+        nv, nt = (int(x) for x in offs[:, rows].tolist())            # the one synchronisation: sizes of the outputs
+        verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        normals = torch.empty((nv, 3), dtype=torch.float32, device=dev)
+        values = torch.empty(nv, dtype=torch.float32, device=dev)
+        faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
+        if nv or nt:
+            _capi.check(L.dfb_mc_emit(_ptr(vol), rx, ry, rz, step, _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]),
+                                      _ptr(verts), _ptr(normals), _ptr(values), _ptr(faces), _stream()))
+        return verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy()

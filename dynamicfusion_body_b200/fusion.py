@@ -15,7 +15,7 @@ and error behaviour for the two hot paths, with state living on the 
 
 The callers either side of the hot paths run on the device too: `setupCorrespondences`
 (closest-point correspondences), `update_graph` / `construct_graph` (node sampling, unsupported surface points,
-vertex->node tables).  Surface extraction (8f rank 3) is a hook: `surface_extractor`, or pass the vertices in.
+vertex->node tables), and so does surface extraction (8f rank 3, `marching_cubes`; `surface_extractor` swaps it out).
 """
 import os
 
@@ -207,24 +207,34 @@ class _FusionBase:
         from . import io
         io.write_warp_field(self._nodes, path, filename, self._itercounter)
 
-    # ---- surface extraction hook ------------------------------------------------------------------
-    surface_extractor = None
-    """callable(tsdf, step_size) -> (verts, faces, normals, values), the contract of
+    # ---- surface extraction ------------------------------------------------------
+    surface_extractor = "device"
+    """"device" (default): the library's own extractor (`engine.marching_cubes`, include/dfb.h `dfb_mc_*`) on the
+    device-resident volume.  A callable(tsdf, step_size) -> (verts, faces, normals, values) -- the contract of
     skimage.measure.marching_cubes_lewiner(tsdf, step_size=..., allow_degenerate=False) that the reference calls
-    (core/fusion.py:554-564).  Surface extraction itself is SURVEY 8f rank 3 and not part of this library: assign an
-    extractor here, or hand the vertices to setupCorrespondences / update_graph directly."""
+    (core/fusion.py:554-564) -- replaces it (e.g. skimage itself where it is installed).  None: no extraction; the
+    methods that need a surface raise NotImplementedError unless the vertices are handed to them."""
 
     def marching_cubes(self, tsdf=None, step_size=0):
-        """core/fusion.py:553-568, delegating to `surface_extractor`."""
-        if self.surface_extractor is None:
-            raise NotImplementedError("surface extraction is outside the accelerated hot path (SURVEY 8f rank 3): set "
-                                      "`surface_extractor`, or pass live_vertices= / vertices= to the caller")
+        """core/fusion.py:553-568.  Vertices are in voxel coordinates of the whole grid (a slab's x offset is added)."""
+        ext = self.surface_extractor
+        if ext is None:
+            raise NotImplementedError("no surface extractor configured: set `surface_extractor` (\"device\" or a callable), "
+                                      "or pass live_vertices= / vertices= to the caller")
         if step_size < 1:
             step_size = self._marching_cubes_step_size
+        step_size = max(1, int(step_size))                            # the reference's test.py:74 passes 0.5; skimage needs an int >= 1
         if tsdf is not None:
-            return self.surface_extractor(_as_np(tsdf), step_size)
-        v, f, n, _ = self.surface_extractor(_as_np(self._tsdf), step_size)
+            return engine.marching_cubes(tsdf, step_size) if ext == "device" else ext(_as_np(tsdf), step_size)
+        if ext == "device":
+            v, f, n, _ = engine.marching_cubes(self._vol.tsdf, step_size)
+            if self._vol.x0:
+                v[:, 0] += np.float32(self._vol.x0)
+        else:
+            v, f, n, _ = ext(_as_np(self._tsdf), step_size)
         self._vertices, self._faces, self._normals = np.asarray(v, dtype=np.float32), f, np.asarray(n, dtype=np.float32)
+        if self._verbose:
+            print("Marching Cubes result: number of extracted vertices is %d" % (len(self._vertices)))
 
     def average_edge_dist_in_face(self, f):
         """core/fusion.py:592-596."""
@@ -232,10 +242,11 @@ class _FusionBase:
         return (np.linalg.norm(v1 - v2) + np.linalg.norm(v1 - v3) + np.linalg.norm(v2 - v3)) / 3
 
     def write_canonical_mesh(self, path, filename):
-        """core/fusion.py:577-586 / core/fusion_dm.py:339-354: extract the canonical surface (through `surface_extractor`,
-        step size 1) and write it as OBJ; FusionDM maps vertices and normals to world coordinates with `_IND` first."""
+        """core/fusion.py:577-586 / core/fusion_dm.py:339-354: extract the canonical surface (step size 1) and write it as OBJ; FusionDM maps vertices and normals to world coordinates with `_IND` first."""
         from . import io
-        verts, faces, normals, _ = self.marching_cubes(self._tsdf, step_size=1)
+        verts, faces, normals, _ = self.marching_cubes(self._vol.tsdf if self.surface_extractor == "device" else self._tsdf, step_size=1)
+        if self._vol.x0:
+            verts = np.array(verts); verts[:, 0] += self._vol.x0
         ind = getattr(self, "_IND", None)
         if ind is not None:
             rot, trans = ind[:3, :3], ind[:3, 3]
@@ -279,7 +290,7 @@ class Fusion(_FusionBase):
     def InitializeCanonicalSpace(self, tsdf=None, depths=None, lws=None, K=None, tsdf_size=256, *, tsdf_shape=None,
                                  slab=None, vertices=None, normals=None, faces=None, nodes=None, radius=None):
         """core/fusion.py:73-96.  The reference extracts the canonical surface with marching cubes and samples
-        the nodes from it; surface extraction is out of scope here, so the canonical `vertices`/`normals`
+        the nodes from it; so does this (device extractor, `marching_cubes`) unless the canonical `vertices`/`normals`
         (and optionally ready-made `nodes`) are passed in.  `slab=(x0,x1)` keeps only that x-range of the
         volume on this GPU (multi-GPU sharding); `tsdf_shape` creates the fresh volume (tsdf=+tdist, w=0)."""
         if K is not None:
@@ -300,9 +311,11 @@ class Fusion(_FusionBase):
             self._vertices = np.asarray(vertices, dtype=np.float32)
             self._normals = None if normals is None else np.asarray(normals, dtype=np.float32)
             self._faces = faces
-        elif self.surface_extractor is not None and nodes is None:
+        elif self.surface_extractor is not None and nodes is None and min(self._vol.tsdf.shape) >= 2:
             self.marching_cubes()                                     # core/fusion.py:88 (initial marching cubes)
             faces = self._faces
+            if not len(self._vertices):                               # empty volume: nothing to sample a graph from yet
+                self._vertices = self._faces = self._normals = faces = None
         if radius is not None:
             self._radius = float(radius)
         elif self._vertices is not None and faces is not None and len(faces):

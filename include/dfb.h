@@ -230,6 +230,34 @@ int dfb_graph_unsupported(const float* verts, int64_t m, const int32_t* vert_knn
 int dfb_graph_sample_rounds(const dfb_point_grid* g, double radius, int rounds, uint8_t* state, int32_t* undecided,
                             dfb_stream_t stream);
 
+/* ---- surface extraction ------------------------------------------------------------------- */
+/* Indexed level-set mesh of a device-resident float32 volume [rx][ry][rz]: the replacement of
+ * skimage.measure.marching_cubes_lewiner(volume, step_size=step, allow_degenerate=False) as called by Fusion.marching_cubes /
+ * write_canonical_mesh (core/fusion.py:554-568, 579; core/fusion_dm.py:341).  Cells span `step` voxels; one vertex per crossed
+ * edge of the sampled grid (no welding pass), vertices in (x, y, z) voxel coordinates ordered by owning sample then axis, faces
+ * ordered by cell; triangles with two vertices on one grid sample are dropped.  Call order: [dfb_mc_level] -> dfb_mc_count ->
+ * read row_voff[rows] / row_toff[rows] (vertex / triangle totals) -> allocate -> dfb_mc_emit. */
+typedef struct dfb_mc_chunk {
+    int32_t voff;  /* vertices of the row before this 32-sample chunk */
+    uint32_t m[3]; /* per axis: bit l = the edge owned by sample 32*c + l crosses the level */
+} dfb_mc_chunk;
+
+/* level_out [3] (device) = {0.5 * (min + max), min, max}: the level skimage uses when none is passed, as the reference does.
+ * scratch: dfb_mc_level_scratch_floats() floats. */
+int64_t dfb_mc_level_scratch_floats(void);
+int dfb_mc_level(const float* vol, int64_t n, float* scratch, float* level_out, dfb_stream_t stream);
+/* rows = sampled (x, y) pairs; chunks = rows * ceil(samples_z / 32) */
+int64_t dfb_mc_rows(int rx, int ry, int step);
+int64_t dfb_mc_chunks(int rx, int ry, int rz, int step);
+/* level: device pointer to one float.  Writes chunks [dfb_mc_chunks] and the exclusive vertex / triangle offsets of every
+ * row, row_voff / row_toff [rows + 1] (slot [rows] = total). */
+int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, const float* level, dfb_mc_chunk* chunks, int32_t* row_voff,
+                 int32_t* row_toff, dfb_stream_t stream);
+/* verts [nv][3], faces [nt][3] int32; normals [nv][3] (unit, along the +gradient) and values [nv] may be NULL. */
+int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, const float* level, const dfb_mc_chunk* chunks,
+                const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values, int32_t* faces,
+                dfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -390,3 +390,88 @@ extern "C" int hs_gn_lw_normal_eq(const dfb_gn_problem* prob, const double* dq, 
     }
     return 0;
 }
+
+// ---- surface extraction (csrc/dfb_mc.h): the loops of mc.cu's count / scan / emit kernels with HOST pointers ------------------
+#include "../../dynamicfusion_body_b200/csrc/dfb_mc.h"
+
+extern "C" float hs_mc_level(const float* vol, int64_t n) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int64_t i = 0; i < n; ++i) { lo = fminf(lo, vol[i]); hi = fmaxf(hi, vol[i]); }
+    return (float)(0.5 * ((double)lo + (double)hi));
+}
+
+extern "C" void hs_mc_count(const float* vol, int rx, int ry, int rz, int step, float level, McChunk* chunks, int32_t* row_voff,
+                            int32_t* row_toff) {
+    McGrid g;
+    mc_grid_init(g, vol, rx, ry, rz, step, level);
+    const int rows = g.nx * g.ny;
+    for (int row = 0; row < rows; ++row) {
+        const int i = row / g.ny, j = row - i * g.ny;
+        const bool cell_row = i + 1 < g.nx && j + 1 < g.ny;
+        int nv = 0, nt = 0;
+        for (int c = 0; c < g.ncz; ++c) {
+            McChunk rec;
+            rec.voff = nv; rec.m[0] = rec.m[1] = rec.m[2] = 0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int k = 32 * c + lane;
+                if (k >= g.nz) break;
+                const uint32_t bits = mc_edge_bits(g, i, j, k, mc_val(g, i, j, k));
+                for (int d = 0; d < 3; ++d) rec.m[d] |= ((bits >> d) & 1u) << lane;
+                if (cell_row && k + 1 < g.nz) {
+                    float v[8];
+                    const int cs = mc_cell_case(g, i, j, k, v);
+                    if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i, j, k, nullptr);
+                }
+            }
+            chunks[(size_t)row * g.ncz + c] = rec;
+            nv += mc_popc(rec.m[0]) + mc_popc(rec.m[1]) + mc_popc(rec.m[2]);
+        }
+        row_voff[row] = nv; row_toff[row] = nt;
+    }
+    int32_t a = 0, b = 0;
+    for (int row = 0; row < rows; ++row) {
+        const int32_t na = row_voff[row], nb = row_toff[row];
+        row_voff[row] = a; row_toff[row] = b;
+        a += na; b += nb;
+    }
+    row_voff[rows] = a; row_toff[rows] = b;
+}
+
+extern "C" void hs_mc_emit(const float* vol, int rx, int ry, int rz, int step, float level, const McChunk* chunks,
+                           const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values, int32_t* faces) {
+    McGrid g;
+    mc_grid_init(g, vol, rx, ry, rz, step, level);
+    const int rows = g.nx * g.ny;
+    for (int row = 0; row < rows; ++row) {
+        const int i = row / g.ny, j = row - i * g.ny;
+        const bool cell_row = i + 1 < g.nx && j + 1 < g.ny;
+        int tbase = row_toff[row];
+        for (int c = 0; c < g.ncz; ++c) {
+            const McChunk rec = chunks[(size_t)row * g.ncz + c];
+            for (int lane = 0; lane < 32; ++lane) {
+                const int k = 32 * c + lane;
+                if (k >= g.nz) break;
+                if (((rec.m[0] | rec.m[1] | rec.m[2]) >> lane) & 1u) {
+                    int id = mc_vertex_id(g, chunks, row_voff, i, j, k, 0);
+                    for (int d = 0; d < 3; ++d)
+                        if ((rec.m[d] >> lane) & 1u) {
+                            float val;
+                            mc_vertex(g, i, j, k, d, verts + 3 * (size_t)id, normals + 3 * (size_t)id, val);
+                            values[id] = val;
+                            ++id;
+                        }
+                }
+                if (cell_row && k + 1 < g.nz) {
+                    float v[8];
+                    int8_t edges[3 * DFB_MC_MAX_TRIS];
+                    const int cs = mc_cell_case(g, i, j, k, v);
+                    const int nt = (cs != 0 && cs != 255) ? mc_cell_tris(cs, v, g.level, i, j, k, edges) : 0;
+                    for (int t = 0; t < nt; ++t)
+                        for (int q = 0; q < 3; ++q)
+                            faces[3 * (size_t)(tbase + t) + q] = mc_cell_edge_vertex(g, chunks, row_voff, i, j, k, edges[3 * t + q]);
+                    tbase += nt;
+                }
+            }
+        }
+    }
+}

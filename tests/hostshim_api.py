@@ -16,7 +16,7 @@ _CSRC = os.path.join(os.path.dirname(_HERE), "dynamicfusion_body_b200", "csrc")
 
 
 def build(force=False):
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h", "dfb_brick.h")]
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("dfb_math.h", "dfb_voxel.h", "dfb_params.h", "dfb_gn.h", "dfb_brick.h", "dfb_mc.h", "dfb_mc_table.h")]
     if not force and os.path.isfile(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(d) for d in deps):
         return _SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", _SRC, "-o", _SO])
@@ -265,3 +265,27 @@ class HostGN:
         H = np.zeros((8, 8)); g = np.zeros(8); cost = np.zeros(2)
         lib().hs_gn_lw_normal_eq(C.byref(self.p), _p(dqd), _p(lwd), _p(H), _p(g), _p(cost))
         return H, g, cost
+
+
+def marching_cubes(vol, step_size=1, level=None):
+    """Host run of csrc/dfb_mc.h in the composition of mc.cu (count -> scan -> emit)."""
+    L = lib()
+    vp = C.c_void_p
+    vol = np.ascontiguousarray(vol, dtype=np.float32)
+    rx, ry, rz = vol.shape
+    s = int(step_size)
+    L.hs_mc_level.restype = C.c_float
+    L.hs_mc_level.argtypes = [vp, C.c_int64]
+    L.hs_mc_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]
+    L.hs_mc_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    lv = L.hs_mc_level(_p(vol), vol.size) if level is None else float(np.float32(level))
+    nx, ny, nz = (rx - 1) // s + 1, (ry - 1) // s + 1, (rz - 1) // s + 1
+    rows, ncz = nx * ny, (nz + 31) // 32
+    chunks = np.zeros((rows * ncz, 4), dtype=np.int32)
+    voff = np.zeros(rows + 1, dtype=np.int32); toff = np.zeros(rows + 1, dtype=np.int32)
+    L.hs_mc_count(_p(vol), rx, ry, rz, s, lv, _p(chunks), _p(voff), _p(toff))
+    nv, nt = int(voff[-1]), int(toff[-1])
+    verts = np.zeros((nv, 3), np.float32); normals = np.zeros((nv, 3), np.float32); values = np.zeros(nv, np.float32)
+    faces = np.zeros((nt, 3), np.int32)
+    L.hs_mc_emit(_p(vol), rx, ry, rz, s, lv, _p(chunks), _p(voff), _p(toff), _p(verts), _p(normals), _p(values), _p(faces))
+    return verts, faces, normals, values

@@ -195,6 +195,7 @@ def test_class_level_errors_and_signatures():
     p = fus.warp(sc.vertices[0], m_lw=fus._lw)
     assert p.shape == (3,)
     assert fus.dq_blend(sc.vertices[0]).shape == (8,)
+    fus.surface_extractor = None                                        # extraction switched off: the callers say so
     for name in ("update_graph", "marching_cubes"):
         with pytest.raises(NotImplementedError):
             getattr(fus, name)()

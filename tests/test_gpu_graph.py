@@ -87,6 +87,7 @@ def test_setupCorrespondences_prune_and_errors():
     link, _ = og.knn_points(GG["verts"][keep], GG["node_pos"], 1)
     assert np.array_equal(f._node_vertex_idx, link[:, 0])
     assert len(f._correspondences) == len(f._vertices)                                  # solve()'s precondition (core/fusion.py:337)
+    f.surface_extractor = None
     with pytest.raises(NotImplementedError):
         f.setupCorrespondences(np.zeros((4, 4, 4)))                                     # no surface extractor configured
     with pytest.raises(ValueError):
@@ -147,6 +148,7 @@ def test_update_graph_golden():
     assert np.abs(dq[N:] - GG["ug_node_dq"][N:]).max() <= 6e-8 * np.abs(GG["ug_node_dq"][N:]).max()  # float32 storage of a float64 blend
     assert np.array_equal(np.asarray(f._neighbor_look_up), GG["ug_lookup"])
     assert f._curr_tsdf is None and f._correspondences == []
+    f.surface_extractor = None
     with pytest.raises(NotImplementedError):
         f.update_graph()                                                                             # no surface extractor
 
