@@ -23,6 +23,8 @@ struct McGrid {
     int nx, ny, nz;    // samples per axis: (r - 1) / step + 1; cells per axis: n - 1
     int ncz;           // 32-sample chunks per row: ceil(nz / 32)
     float level;
+    int xs0;           // sample index of the volume's first x-plane in the full grid (x-slabs: vertex coordinates and the
+                       // degenerate-triangle test are those of the whole grid); 0 for a whole volume
 };
 
 struct McChunk {       // one per 32 consecutive samples of a row
@@ -59,8 +61,8 @@ DFB_HD int mc_popc(uint32_t x) {
 #endif
 }
 
-DFB_HD void mc_grid_init(McGrid& g, const float* vol, int rx, int ry, int rz, int step, float level) {
-    g.vol = vol; g.rx = rx; g.ry = ry; g.rz = rz; g.step = step; g.level = level;
+DFB_HD void mc_grid_init(McGrid& g, const float* vol, int rx, int ry, int rz, int step, float level, int xs0 = 0) {
+    g.vol = vol; g.rx = rx; g.ry = ry; g.rz = rz; g.step = step; g.level = level; g.xs0 = xs0;
     g.nx = (rx - 1) / step + 1; g.ny = (ry - 1) / step + 1; g.nz = (rz - 1) / step + 1;
     g.ncz = (g.nz + 31) / 32;
 }
@@ -109,7 +111,7 @@ DFB_HD int mc_edge_key(int e, const float v[8], float level, const int ijk[3]) {
     return u == (float)ijk[d] ? c0 : u == (float)(ijk[d] + 1) ? c1 : 8 + e;
 }
 
-// non-degenerate triangles of cell (i,j,k): writes 3 edge ids per triangle, returns their number
+// non-degenerate triangles of cell (i,j,k) (i counted in the full grid: local index + McGrid::xs0): writes 3 edge ids per triangle, returns their number
 DFB_HD int mc_cell_tris(int cs, const float v[8], float level, int i, int j, int k, int8_t* edges /* [3 * DFB_MC_MAX_TRIS] or null */) {
     const int n = mc_table_ntri(cs);
     const int ijk[3] = {i, j, k};
@@ -162,8 +164,8 @@ DFB_HD void mc_vertex(const McGrid& g, int i, int j, int k, int d, float pos[3],
     const float v0 = mc_val(g, i, j, k), v1 = mc_val(g, i1, j1, k1);
     const float t = fdiv(fsub(g.level, v0), fsub(v1, v0));
     const float fs = (float)g.step;
-    pos[0] = fmul((float)i, fs); pos[1] = fmul((float)j, fs); pos[2] = fmul((float)k, fs);
-    pos[d] = fmul(mc_cross_coord(d == 0 ? i : d == 1 ? j : k, v0, v1, g.level), fs);
+    pos[0] = fmul((float)(i + g.xs0), fs); pos[1] = fmul((float)j, fs); pos[2] = fmul((float)k, fs);
+    pos[d] = fmul(mc_cross_coord(d == 0 ? i + g.xs0 : d == 1 ? j : k, v0, v1, g.level), fs);
     float g0[3], g1[3], n[3];
     mc_gradient(g, i, j, k, g0);
     mc_gradient(g, i1, j1, k1, g1);

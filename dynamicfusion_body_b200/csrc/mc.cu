@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_count_kernel(McGrid g, const
             if (cell_row && k + 1 < g.nz) {
                 float v[8];
                 const int cs = mc_cell_case(g, i, j, k, v);
-                if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i, j, k, nullptr);
+                if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i + g.xs0, j, k, nullptr);
             }
         }
         McChunk rec;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(MC_WARPS * 32) mc_emit_kernel(McGrid g, const 
             if (cell_row && k + 1 < g.nz) {
                 float v[8];
                 const int cs = mc_cell_case(g, i, j, k, v);
-                if (cs != 0 && cs != 255) nt = mc_cell_tris(cs, v, g.level, i, j, k, edges);
+                if (cs != 0 && cs != 255) nt = mc_cell_tris(cs, v, g.level, i + g.xs0, j, k, edges);
             }
         }
         const int toff = tbase + warp_excl_scan(nt, lane);
@@ -197,13 +197,14 @@ extern "C" int64_t dfb_mc_chunks(int rx, int ry, int rz, int step) {
     return dfb_mc_rows(rx, ry, step) * ((((rz - 1) / step + 1) + 31) / 32);
 }
 
-extern "C" int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, const float* level, dfb_mc_chunk* chunks,
+extern "C" int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, int x_origin, const float* level, dfb_mc_chunk* chunks,
                             int32_t* row_voff, int32_t* row_toff, dfb_stream_t stream) {
     int rc = check_grid(vol, rx, ry, rz, step);
     if (rc != DFB_OK) return rc;
     DFB_REQUIRE(level && chunks && row_voff && row_toff, "mc_count: null pointer");
     McGrid g;
-    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f);
+    DFB_REQUIRE(x_origin >= 0 && (int64_t)x_origin + (rx - 1) / step < (1 << 24), "mc: x_origin out of range (sample indices must stay exact in float32)");
+    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f, x_origin);
     const int rows = g.nx * g.ny;
     cudaStream_t s = (cudaStream_t)stream;
     mc_count_kernel<<<(rows + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, 0, s>>>(g, level, reinterpret_cast<McChunk*>(chunks), row_voff, row_toff);
@@ -213,7 +214,7 @@ extern "C" int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, 
     return DFB_OK;
 }
 
-extern "C" int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, const float* level, const dfb_mc_chunk* chunks,
+extern "C" int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, int x_origin, const float* level, const dfb_mc_chunk* chunks,
                            const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values,
                            int32_t* faces, dfb_stream_t stream) {
     int rc = check_grid(vol, rx, ry, rz, step);
@@ -221,7 +222,8 @@ extern "C" int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, c
     DFB_REQUIRE(level && chunks && row_voff && row_toff, "mc_emit: null pointer");
     DFB_REQUIRE(verts && faces, "mc_emit: verts and faces are required (normals / values may be null)");
     McGrid g;
-    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f);
+    DFB_REQUIRE(x_origin >= 0 && (int64_t)x_origin + (rx - 1) / step < (1 << 24), "mc: x_origin out of range (sample indices must stay exact in float32)");
+    mc_grid_init(g, vol, rx, ry, rz, step, 0.0f, x_origin);
     const int rows = g.nx * g.ny;
     cudaStream_t s = (cudaStream_t)stream;
     mc_emit_kernel<<<(rows + MC_WARPS - 1) / MC_WARPS, MC_WARPS * 32, 0, s>>>(g, level, reinterpret_cast<const McChunk*>(chunks), row_voff, row_toff,

@@ -115,3 +115,111 @@ def max_over_ranks(value_ms, device):
     t = torch.tensor([float(value_ms)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+# ---- surface extraction over x-slabs (SURVEY 8e x 8f rank 3) ---------------------------------------------------------
+def slab_sample_planes(x0, x1, rx, step):
+    """Sample x-planes (voxel x, multiples of `step`) inside the slab [x0, x1): (first, last, last plane of the whole grid)."""
+    s = int(step)
+    last = (int(rx) - 1) // s * s
+    a = -(-int(x0) // s) * s
+    b = min((int(x1) - 1) // s * s, last)
+    if b - a < s:
+        raise ValueError("surface extraction over slabs needs at least two sample planes per slab (slab [%d, %d), step %d)" % (x0, x1, s))
+    return a, b, last
+
+
+def global_level(slab, group=None):
+    """0.5 * (min + max) of the whole volume, float32 of the float64 mean like dfb_mc_level (the level skimage takes when the
+    reference passes none, core/fusion.py:559)."""
+    mm = torch.stack([slab.min(), -slab.max()]).to(torch.float32)
+    if is_dist():
+        dist.all_reduce(mm, op=dist.ReduceOp.MIN, group=group)
+    mn, mx = float(mm[0].item()), -float(mm[1].item())
+    return float(np.float32(0.5 * (np.float64(np.float32(mn)) + np.float64(np.float32(mx)))))
+
+
+def slab_halo_volume(slab, x0, x1, rx, step, prev_plane=None, next_planes=None):
+    """The slab extended by the sample planes the extractor needs from its neighbours: one before (gradient of the first owned plane)
+    and two after (far face of the last owned cells; gradient on it).  Planes that are not sample planes stay zero (never read).
+    Returns (sub volume, voxel x of sub[0], first owned plane, last owned plane)."""
+    s = int(step)
+    a, b, last = slab_sample_planes(x0, x1, rx, s)
+    lo = a - s if prev_plane is not None else min(a, int(x0))
+    hi = b + 2 * s if next_planes is not None else int(x1) - 1
+    if prev_plane is None and a != 0:
+        raise ValueError("slab does not start the grid: the sample plane before it is required")
+    if next_planes is None and b != last:
+        raise ValueError("slab does not end the grid: the two sample planes after it are required")
+    sub = torch.zeros((hi - lo + 1,) + tuple(slab.shape[1:]), dtype=torch.float32, device=slab.device)
+    sub[int(x0) - lo:int(x1) - lo] = slab
+    if prev_plane is not None:
+        sub[0] = prev_plane
+    if next_planes is not None:
+        sub[b + s - lo] = next_planes[0]
+        sub[b + 2 * s - lo] = next_planes[1]
+    return sub, lo, a, b
+
+
+def cut_owned_mesh(mesh, lo, a, b, step):
+    """From the mesh of a halo volume (with plane offsets) keep what the slab owns: the vertices of its sample planes [a, b] and the
+    triangles of the cells that start on them.  Face ids are made relative to the first owned vertex; ids >= the number of owned
+    vertices point into the next slab's first plane, whose vertices come in the same order there."""
+    v, f, n, val, pv, pt = mesh
+    s = int(step)
+    j0, j1 = (a - lo) // s, (b - lo) // s
+    v_lo, v_hi, t_lo, t_hi = int(pv[j0]), int(pv[j1 + 1]), int(pt[j0]), int(pt[j1 + 1])
+    return v[v_lo:v_hi], f[t_lo:t_hi].astype(np.int64) - v_lo, n[v_lo:v_hi], val[v_lo:v_hi]
+
+
+def extract_surface_slab(slab, x0, x1, rx, step=1, level=None, extractor=None, group=None):
+    """This rank's part of the whole volume's surface mesh: (verts, faces with GLOBAL vertex ids int32, normals, values).  The parts
+    of all ranks concatenated in rank order are the single-volume mesh of engine.marching_cubes bit for bit (vertices are ordered by
+    owning sample and triangles by cell, x slowest, so a slab's share is a contiguous range of both).  Exchanges three (ry, rz)
+    planes per slab boundary and the vertex counts; extractor(vol, step, level, x_origin=, plane_offsets=True) defaults to the
+    device extractor."""
+    if extractor is None:
+        from . import engine
+        extractor = engine.marching_cubes
+    s = int(step)
+    slab = slab.to(torch.float32)
+    if level is None:
+        level = global_level(slab, group)
+    prev_plane = next_planes = None
+    rank, world = 0, 1
+    if is_dist():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        a, b, _ = slab_sample_planes(x0, x1, rx, s)
+        plane = tuple(slab.shape[1:])
+        ops, keep = [], []
+        if rank > 0:
+            prev_plane = torch.empty(plane, dtype=torch.float32, device=slab.device)
+            first_two = torch.stack([slab[a - int(x0)], slab[a + s - int(x0)]]).contiguous()
+            keep.append(first_two)
+            ops += [dist.P2POp(dist.isend, first_two, rank - 1, group), dist.P2POp(dist.irecv, prev_plane, rank - 1, group)]
+        if rank < world - 1:
+            next_planes = torch.empty((2,) + plane, dtype=torch.float32, device=slab.device)
+            mine = slab[b - int(x0)].contiguous()
+            keep.append(mine)
+            ops += [dist.P2POp(dist.isend, mine, rank + 1, group), dist.P2POp(dist.irecv, next_planes, rank + 1, group)]
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+    sub, lo, a, b = slab_halo_volume(slab, x0, x1, rx, s, prev_plane, next_planes)
+    v, f, n, val = cut_owned_mesh(extractor(sub, s, level, x_origin=lo // s, plane_offsets=True), lo, a, b, s)
+    offset = 0
+    if is_dist():
+        counts = torch.zeros(world, dtype=torch.int64, device=slab.device)
+        counts[rank] = len(v)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        offset = int(counts[:rank].sum().item())
+    return v, (f + offset).astype(np.int32), n, val
+
+
+def allgather_mesh(part, group=None):
+    """Concatenate the ranks' mesh parts (rank order) on every rank: the whole-volume mesh the reference keeps in
+    `_vertices / _faces / _normals` (core/fusion.py:565-567)."""
+    if not is_dist():
+        return part
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, tuple(np.ascontiguousarray(x) for x in part), group=group)
+    return tuple(np.concatenate([p[i] for p in parts]) for i in range(4))

@@ -443,11 +443,15 @@ def uniform_sample(pts, radius, device=None, rounds_per_call=16):
     return p[idx].cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
 
-def marching_cubes(vol, step_size=1, level=None):
+def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False):
     """Surface extraction on the device (include/dfb.h `dfb_mc_*`): the call the reference makes as
     measure.marching_cubes_lewiner(volume, step_size=..., allow_degenerate=False) (core/fusion.py:554-568, 579).
     vol: (rx, ry, rz) CUDA tensor or host array; level None = 0.5 * (min + max) like skimage.  Returns host arrays
-    (verts (V,3) float32 voxel coordinates, faces (F,3) int32, normals (V,3) float32, values (V,) float32)."""
+    (verts (V,3) float32 voxel coordinates, faces (F,3) int32, normals (V,3) float32, values (V,) float32).
+    x_origin: sample index (voxel x / step) of vol[0] in the whole grid when `vol` is an x-slab -- coordinates and degenerate-triangle
+    decisions are then those of the whole grid.  plane_offsets=True appends (plane_voff, plane_toff), int64 [nx + 1]: first vertex /
+    triangle of every sample x-plane (vertices are ordered by owning sample, triangles by cell, x slowest) -- what
+    dist.extract_surface_slab cuts the halo planes off with."""
     if not isinstance(vol, torch.Tensor):
         vol = _to_dev(np.asarray(vol), torch.float32, _require_cuda(None))
     if vol.dim() != 3:
@@ -473,13 +477,18 @@ def marching_cubes(vol, step_size=1, level=None):
         rows = int(L.dfb_mc_rows(rx, ry, step))
         chunks = torch.empty((int(L.dfb_mc_chunks(rx, ry, rz, step)), 4), dtype=torch.int32, device=dev)
         offs = torch.empty((2, rows + 1), dtype=torch.int32, device=dev)
-        _capi.check(L.dfb_mc_count(_ptr(vol), rx, ry, rz, step, _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]), _stream()))
+        _capi.check(L.dfb_mc_count(_ptr(vol), rx, ry, rz, step, int(x_origin), _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]), _stream()))
         nv, nt = (int(x) for x in offs[:, rows].tolist())            # the one synchronisation: sizes of the outputs
         verts = torch.empty((nv, 3), dtype=torch.float32, device=dev)
         normals = torch.empty((nv, 3), dtype=torch.float32, device=dev)
         values = torch.empty(nv, dtype=torch.float32, device=dev)
         faces = torch.empty((nt, 3), dtype=torch.int32, device=dev)
         if nv or nt:
-            _capi.check(L.dfb_mc_emit(_ptr(vol), rx, ry, rz, step, _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]),
+            _capi.check(L.dfb_mc_emit(_ptr(vol), rx, ry, rz, step, int(x_origin), _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]),
                                       _ptr(verts), _ptr(normals), _ptr(values), _ptr(faces), _stream()))
-        return verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy()
+        out = (verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy())
+        if plane_offsets:
+            ny = (ry - 1) // step + 1
+            po = offs[:, ::ny].cpu().numpy().astype(np.int64)        # rows are (x, y) pairs: every ny-th entry starts an x-plane; [rows] = total
+            out += (po[0], po[1])
+        return out

@@ -24,6 +24,7 @@ import torch
 from scipy.spatial import KDTree
 
 from . import _capi, engine
+from . import dist as ddist
 from . import gn as _gn
 
 
@@ -227,14 +228,26 @@ class _FusionBase:
         if tsdf is not None:
             return engine.marching_cubes(tsdf, step_size) if ext == "device" else ext(_as_np(tsdf), step_size)
         if ext == "device":
-            v, f, n, _ = engine.marching_cubes(self._vol.tsdf, step_size)
-            if self._vol.x0:
-                v[:, 0] += np.float32(self._vol.x0)
+            v, f, n, _ = self._device_surface(step_size)
         else:
             v, f, n, _ = ext(_as_np(self._tsdf), step_size)
         self._vertices, self._faces, self._normals = np.asarray(v, dtype=np.float32), f, np.asarray(n, dtype=np.float32)
         if self._verbose:
             print("Marching Cubes result: number of extracted vertices is %d" % (len(self._vertices)))
+
+    def _device_surface(self, step_size):
+        """Surface of the resident canonical volume.  A rank that holds an x-slab of a volume sharded over the process group
+         extracts its share with three halo planes per boundary and every rank receives the whole mesh, identical to the
+        single-GPU one (dist.extract_surface_slab); a lone slab is extracted as is, in whole-grid coordinates."""
+        vol = self._vol
+        rx = int(vol.res[0])
+        if ddist.is_dist() and (vol.x0 > 0 or vol.x1 < rx):
+            return ddist.allgather_mesh(ddist.extract_surface_slab(vol.tsdf, vol.x0, vol.x1, rx, step_size))
+        if vol.x0 % step_size == 0:
+            return engine.marching_cubes(vol.tsdf, step_size, x_origin=vol.x0 // step_size)
+        v, f, n, val = engine.marching_cubes(vol.tsdf, step_size)
+        v[:, 0] += np.float32(vol.x0)
+        return v, f, n, val
 
     def average_edge_dist_in_face(self, f):
         """core/fusion.py:592-596."""
@@ -244,9 +257,12 @@ class _FusionBase:
     def write_canonical_mesh(self, path, filename):
         """core/fusion.py:577-586 / core/fusion_dm.py:339-354: extract the canonical surface (step size 1) and write it as OBJ; FusionDM maps vertices and normals to world coordinates with `_IND` first."""
         from . import io
-        verts, faces, normals, _ = self.marching_cubes(self._vol.tsdf if self.surface_extractor == "device" else self._tsdf, step_size=1)
-        if self._vol.x0:
-            verts = np.array(verts); verts[:, 0] += self._vol.x0
+        if self.surface_extractor == "device":
+            verts, faces, normals, _ = self._device_surface(1)
+        else:
+            verts, faces, normals, _ = self.marching_cubes(self._tsdf, step_size=1)
+            if self._vol.x0:
+                verts = np.array(verts); verts[:, 0] += self._vol.x0
         ind = getattr(self, "_IND", None)
         if ind is not None:
             rot, trans = ind[:3, :3], ind[:3, 3]

@@ -236,7 +236,11 @@ int dfb_graph_sample_rounds(const dfb_point_grid* g, double radius, int rounds, 
  * write_canonical_mesh (core/fusion.py:554-568, 579; core/fusion_dm.py:341).  Cells span `step` voxels; one vertex per crossed
  * edge of the sampled grid (no welding pass), vertices in (x, y, z) voxel coordinates ordered by owning sample then axis, faces
  * ordered by cell; triangles with two vertices on one grid sample are dropped.  Call order: [dfb_mc_level] -> dfb_mc_count ->
- * read row_voff[rows] / row_toff[rows] (vertex / triangle totals) -> allocate -> dfb_mc_emit. */
+ * read row_voff[rows] / row_toff[rows] (vertex / triangle totals) -> allocate -> dfb_mc_emit.
+ * x_origin (count and emit, same value): sample index of the volume's first x-plane in the whole grid, 0 for a whole volume.  An
+ * x-slab passed with its origin yields the coordinates AND the degenerate-triangle decisions of the whole grid, so the
+ * slabs' meshes concatenate to the single-volume mesh bit for bit (dist.extract_surface_slab).  Rows of one x-plane are
+ * contiguous: row_voff[i * ny] / row_toff[i * ny] are the first vertex / triangle of sample plane i. */
 typedef struct dfb_mc_chunk {
     int32_t voff;  /* vertices of the row before this 32-sample chunk */
     uint32_t m[3]; /* per axis: bit l = the edge owned by sample 32*c + l crosses the level */
@@ -251,10 +255,10 @@ int64_t dfb_mc_rows(int rx, int ry, int step);
 int64_t dfb_mc_chunks(int rx, int ry, int rz, int step);
 /* level: device pointer to one float.  Writes chunks [dfb_mc_chunks] and the exclusive vertex / triangle offsets of every
  * row, row_voff / row_toff [rows + 1] (slot [rows] = total). */
-int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, const float* level, dfb_mc_chunk* chunks, int32_t* row_voff,
-                 int32_t* row_toff, dfb_stream_t stream);
+int dfb_mc_count(const float* vol, int rx, int ry, int rz, int step, int x_origin, const float* level, dfb_mc_chunk* chunks,
+                 int32_t* row_voff, int32_t* row_toff, dfb_stream_t stream);
 /* verts [nv][3], faces [nt][3] int32; normals [nv][3] (unit, along the +gradient) and values [nv] may be NULL. */
-int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, const float* level, const dfb_mc_chunk* chunks,
+int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, int x_origin, const float* level, const dfb_mc_chunk* chunks,
                 const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values, int32_t* faces,
                 dfb_stream_t stream);
 

@@ -125,8 +125,9 @@ def default_level(vol):
     return np.float32(0.5 * (np.float64(vol.min()) + np.float64(vol.max())))
 
 
-def marching_cubes(vol, step_size=1, level=None):
-    """-> verts (V,3) f32, faces (F,3) i32, normals (V,3) f32, values (V,) f32."""
+def marching_cubes(vol, step_size=1, level=None, x_origin=0):
+    """-> verts (V,3) f32, faces (F,3) i32, normals (V,3) f32, values (V,) f32.  x_origin: sample index of vol[0] in a larger grid
+    (x-slabs): x coordinates, and the "index + t rounds onto a sample" test, use the index in that grid."""
     global _TABLE
     if _TABLE is None:
         _TABLE = case_table()
@@ -149,6 +150,7 @@ def marching_cubes(vol, step_size=1, level=None):
         v0, v1 = S[lo][m], S[hi][m]
         with np.errstate(all="ignore"):
             t = (level - v0) / (v1 - v0)
+        idx = idx + np.array([int(x_origin), 0, 0])
         p = idx.astype(np.float32) * np.float32(s)
         p[:, d] = (idx[:, d].astype(np.float32) + t) * np.float32(s)
         g0, g1 = G[lo][m], G[hi][m]
@@ -182,8 +184,9 @@ def marching_cubes(vol, step_size=1, level=None):
                     ids.append(int(np.searchsorted(keys, lin[owner] * 3 + d)))
                     far = (i + hi[0], j + hi[1], k + hi[2])
                     with np.errstate(all="ignore"):
-                        u = np.float32(owner[d]) + (level - S[owner]) / (S[far] - S[owner])
-                    spots.append(owner if u == owner[d] else far if u == far[d] else ("edge", e))
+                        xo = int(x_origin) if d == 0 else 0
+                        u = np.float32(owner[d] + xo) + (level - S[owner]) / (S[far] - S[owner])
+                    spots.append(owner if u == owner[d] + xo else far if u == far[d] + xo else ("edge", e))
                 if len(set(spots)) == 3:
                     faces.append(ids)
     faces = np.asarray(faces, dtype=np.int32).reshape(-1, 3)

@@ -400,10 +400,10 @@ extern "C" float hs_mc_level(const float* vol, int64_t n) {
     return (float)(0.5 * ((double)lo + (double)hi));
 }
 
-extern "C" void hs_mc_count(const float* vol, int rx, int ry, int rz, int step, float level, McChunk* chunks, int32_t* row_voff,
+extern "C" void hs_mc_count(const float* vol, int rx, int ry, int rz, int step, int x_origin, float level, McChunk* chunks, int32_t* row_voff,
                             int32_t* row_toff) {
     McGrid g;
-    mc_grid_init(g, vol, rx, ry, rz, step, level);
+    mc_grid_init(g, vol, rx, ry, rz, step, level, x_origin);
     const int rows = g.nx * g.ny;
     for (int row = 0; row < rows; ++row) {
         const int i = row / g.ny, j = row - i * g.ny;
@@ -420,7 +420,7 @@ extern "C" void hs_mc_count(const float* vol, int rx, int ry, int rz, int step, 
                 if (cell_row && k + 1 < g.nz) {
                     float v[8];
                     const int cs = mc_cell_case(g, i, j, k, v);
-                    if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i, j, k, nullptr);
+                    if (cs != 0 && cs != 255) nt += mc_cell_tris(cs, v, g.level, i + g.xs0, j, k, nullptr);
                 }
             }
             chunks[(size_t)row * g.ncz + c] = rec;
@@ -437,10 +437,10 @@ extern "C" void hs_mc_count(const float* vol, int rx, int ry, int rz, int step, 
     row_voff[rows] = a; row_toff[rows] = b;
 }
 
-extern "C" void hs_mc_emit(const float* vol, int rx, int ry, int rz, int step, float level, const McChunk* chunks,
+extern "C" void hs_mc_emit(const float* vol, int rx, int ry, int rz, int step, int x_origin, float level, const McChunk* chunks,
                            const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values, int32_t* faces) {
     McGrid g;
-    mc_grid_init(g, vol, rx, ry, rz, step, level);
+    mc_grid_init(g, vol, rx, ry, rz, step, level, x_origin);
     const int rows = g.nx * g.ny;
     for (int row = 0; row < rows; ++row) {
         const int i = row / g.ny, j = row - i * g.ny;
@@ -465,7 +465,7 @@ extern "C" void hs_mc_emit(const float* vol, int rx, int ry, int rz, int step, f
                     float v[8];
                     int8_t edges[3 * DFB_MC_MAX_TRIS];
                     const int cs = mc_cell_case(g, i, j, k, v);
-                    const int nt = (cs != 0 && cs != 255) ? mc_cell_tris(cs, v, g.level, i, j, k, edges) : 0;
+                    const int nt = (cs != 0 && cs != 255) ? mc_cell_tris(cs, v, g.level, i + g.xs0, j, k, edges) : 0;
                     for (int t = 0; t < nt; ++t)
                         for (int q = 0; q < 3; ++q)
                             faces[3 * (size_t)(tbase + t) + q] = mc_cell_edge_vertex(g, chunks, row_voff, i, j, k, edges[3 * t + q]);

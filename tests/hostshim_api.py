@@ -267,8 +267,8 @@ class HostGN:
         return H, g, cost
 
 
-def marching_cubes(vol, step_size=1, level=None):
-    """Host run of csrc/dfb_mc.h in the composition of mc.cu (count -> scan -> emit)."""
+def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False):
+    """Host run of csrc/dfb_mc.h in the composition of mc.cu (count -> scan -> emit); same arguments as engine.marching_cubes."""
     L = lib()
     vp = C.c_void_p
     vol = np.ascontiguousarray(vol, dtype=np.float32)
@@ -276,16 +276,18 @@ def marching_cubes(vol, step_size=1, level=None):
     s = int(step_size)
     L.hs_mc_level.restype = C.c_float
     L.hs_mc_level.argtypes = [vp, C.c_int64]
-    L.hs_mc_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]
-    L.hs_mc_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp, vp]
+    L.hs_mc_count.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp]
+    L.hs_mc_emit.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp, vp, vp, vp, vp]
     lv = L.hs_mc_level(_p(vol), vol.size) if level is None else float(np.float32(level))
     nx, ny, nz = (rx - 1) // s + 1, (ry - 1) // s + 1, (rz - 1) // s + 1
     rows, ncz = nx * ny, (nz + 31) // 32
     chunks = np.zeros((rows * ncz, 4), dtype=np.int32)
     voff = np.zeros(rows + 1, dtype=np.int32); toff = np.zeros(rows + 1, dtype=np.int32)
-    L.hs_mc_count(_p(vol), rx, ry, rz, s, lv, _p(chunks), _p(voff), _p(toff))
+    L.hs_mc_count(_p(vol), rx, ry, rz, s, int(x_origin), lv, _p(chunks), _p(voff), _p(toff))
     nv, nt = int(voff[-1]), int(toff[-1])
     verts = np.zeros((nv, 3), np.float32); normals = np.zeros((nv, 3), np.float32); values = np.zeros(nv, np.float32)
     faces = np.zeros((nt, 3), np.int32)
-    L.hs_mc_emit(_p(vol), rx, ry, rz, s, lv, _p(chunks), _p(voff), _p(toff), _p(verts), _p(normals), _p(values), _p(faces))
+    L.hs_mc_emit(_p(vol), rx, ry, rz, s, int(x_origin), lv, _p(chunks), _p(voff), _p(toff), _p(verts), _p(normals), _p(values), _p(faces))
+    if plane_offsets:
+        return verts, faces, normals, values, voff[::ny].astype(np.int64), toff[::ny].astype(np.int64)
     return verts, faces, normals, values

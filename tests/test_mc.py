@@ -140,3 +140,92 @@ def test_device_marching_cubes_full_size_properties():
         fwd = np.unique(e[:, 0] * len(v) + e[:, 1]); bwd = np.unique(e[:, 1] * len(v) + e[:, 0])
         assert len(fwd) == len(e) and np.array_equal(fwd, bwd)             # every directed edge once, with its opposite
         assert len(v) - len(e) // 2 + len(f) == 2
+
+
+# ---- x-slabs (SURVEY 8e x 8f rank 3): the slabs' meshes concatenate to the single-volume mesh bit for bit --------------------
+def _slab_cases():
+    rng = np.random.default_rng(11)
+    noise = rng.normal(size=(23, 6, 35)).astype(np.float32)
+    snapped = sphere(20, (10, 10, 10), 6.0)                                # samples exactly at the level: degenerate-triangle decisions
+    return [("sphere_w2", sphere(), 1, 0.0, 2), ("sphere_w3_step2", sphere(33, (16.2, 15.7, 16.4), 11.0), 2, 0.0, 3),
+            ("noise_w4", noise, 1, 0.1, 4), ("noise_w3_step3", noise, 3, 0.05, 3), ("snapped_w5", snapped, 1, 0.0, 5)]
+
+
+def _slabwise(extract, vol, step, level, world):
+    """extract_surface_slab's single-process composition: every slab with the halo planes its neighbours would send."""
+    import torch
+    from dynamicfusion_body_b200 import dist as ddist
+    rx = vol.shape[0]
+    parts, offset = [], 0
+    for r, (x0, x1) in enumerate(ddist.slab_partition(rx, world)):
+        a, b, _ = ddist.slab_sample_planes(x0, x1, rx, step)
+        prev = torch.from_numpy(vol[a - step]) if r > 0 else None
+        nxt = torch.from_numpy(np.stack([vol[b + step], vol[b + 2 * step]])) if r < world - 1 else None
+        sub, lo, a, b = ddist.slab_halo_volume(torch.from_numpy(vol[x0:x1]), x0, x1, rx, step, prev, nxt)
+        v, f, n, val = ddist.cut_owned_mesh(extract(sub, step, level, x_origin=lo // step, plane_offsets=True), lo, a, b, step)
+        parts.append((v, (f + offset).astype(np.int32), n, val))
+        offset += len(v)
+    return tuple(np.concatenate([p[i] for p in parts]) for i in range(4))
+
+
+def _assert_identical(got, want, name):
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and np.array_equal(g, w), name
+
+
+def test_slab_meshes_concatenate_to_the_full_mesh_host_build():
+    import hostshim_api as hs
+    for name, vol, step, level, world in _slab_cases():
+        full = hs.marching_cubes(vol, step, level)
+        assert len(full[1]) > 50, name
+        got = _slabwise(lambda sub, s, lv, **kw: hs.marching_cubes(sub.numpy(), s, lv, **kw), vol, step, level, world)
+        _assert_identical(got, full, name)
+
+
+def test_x_origin_matches_oracle_and_moves_the_degenerate_decisions():
+    import hostshim_api as hs
+    rng = np.random.default_rng(3)
+    vol = rng.normal(size=(6, 7, 9)).astype(np.float32)
+    vol[2, 3, 4] = np.float32(0.1) + np.float32(5e-6)                      # x edge: t = 1e-5, distinct from the sample at x index 2,
+    vol[3, 3, 4] = np.float32(-0.4)                                        # rounds onto it at x index 2 + 4096;
+    vol[2, 4, 4] = np.float32(-100)                                        # y edge: t = 5e-8, on the sample either way
+    for xo in (0, 5, 4096):
+        assert_same_mesh(hs.marching_cubes(vol, 1, 0.1, x_origin=xo), omc.marching_cubes(vol, 1, 0.1, x_origin=xo), "xo%d" % xo)
+    v0, f0 = hs.marching_cubes(vol, 1, 0.1)[:2]
+    v1, f1 = hs.marching_cubes(vol, 1, 0.1, x_origin=4096)[:2]
+    assert np.array_equal(v1[:, 1:], v0[:, 1:]) and np.abs(v1[:, 0] - 4096 - v0[:, 0]).max() < 1e-3
+    assert len(f1) == len(f0) - 4                                          # triangles that only degenerate at the large origin
+    with pytest.raises(ValueError):
+        from dynamicfusion_body_b200 import dist as ddist
+        ddist.slab_sample_planes(4, 6, 16, 2)                              # one sample plane only
+
+
+@pytest.mark.gpu
+def test_device_slab_meshes_concatenate_to_the_full_mesh():
+    import torch
+    from dynamicfusion_body_b200 import engine
+    for name, vol, step, level, world in _slab_cases():
+        full = engine.marching_cubes(torch.from_numpy(vol).cuda(), step, level)
+        got = _slabwise(lambda sub, s, lv, **kw: engine.marching_cubes(sub.cuda(), s, lv, **kw), vol, step, level, world)
+        _assert_identical(got, full, name)
+        assert_same_mesh(full, omc.marching_cubes(vol, step, level), name)
+
+
+@pytest.mark.gpu
+def test_fusion_classes_extract_on_the_device(tmp_path):
+    """Fusion.marching_cubes / InitializeCanonicalSpace / write_canonical_mesh with the default ("device") extractor; a lone x-slab
+    comes out in whole-grid coordinates."""
+    from dynamicfusion_body_b200 import fusion
+    vol = np.clip(sphere(32, (15.2, 16.1, 15.7), 10.3), -3, 3).astype(np.float32)
+    want = omc.marching_cubes(vol, 1, None)
+    fus = fusion.Fusion(3.0, subsample_rate=2.0, knn=3, marching_cubes_step_size=1, verbose=False, use_cnn=False, write_warpfield=False)
+    fus.InitializeCanonicalSpace(tsdf=vol)                                  # core/fusion.py:73-96: marching cubes -> radius -> graph
+    assert np.array_equal(fus._vertices, want[0]) and np.array_equal(fus._faces, want[1])
+    assert np.allclose(fus._normals, want[2], atol=1e-6) and len(fus._nodes) > 5 and fus._radius > 1.0
+    fus.write_canonical_mesh(str(tmp_path), "canonical.obj")
+    lines = open(os.path.join(str(tmp_path), "canonical.obj")).read().split("\n")
+    assert sum(l.startswith("v ") for l in lines) == len(want[0]) and sum(l.startswith("f ") for l in lines) == len(want[1])
+    slab = fusion.Fusion(3.0, subsample_rate=2.0, knn=3, marching_cubes_step_size=1, verbose=False, use_cnn=False, write_warpfield=False)
+    slab._set_volume(vol[8:20].copy(), None, shape=(32, 32, 32), slab=(8, 20))
+    slab.marching_cubes()
+    assert_same_mesh((slab._vertices, slab._faces, slab._normals, want[3][:0]), omc.marching_cubes(vol[8:20], 1, None, x_origin=8)[:3] + (want[3][:0],), "slab")
