@@ -249,6 +249,10 @@ class _FusionBase:
         v[:, 0] += np.float32(vol.x0)
         return v, f, n, val
 
+    def write_live_frame_mesh(self, path, filename, warpfield_path):
+        """core/fusion_dm.py:357-358: an empty method in the reference."""
+        pass
+
     def average_edge_dist_in_face(self, f):
         """core/fusion.py:592-596."""
         v1, v2, v3 = self._vertices[f[0]], self._vertices[f[1]], self._vertices[f[2]]
@@ -622,3 +626,19 @@ class FusionDM(_FusionBase):
 
 class FusionDM_GPU(FusionDM):
     """Name kept for drop-in with test.py:158-159 (`FusionDM_GPU(0.2, K, tsdf_res=256, verbose=True)`)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if self._verbose:
+            self.verbose_gpu()                                        # core/fusion_dm.py:573-574
+
+    def verbose_gpu(self):
+        """core/fusion_dm.py:576-598 lists the OpenCL platforms and devices; this lists the CUDA devices the library runs on."""
+        print('\n' + '=' * 60 + '\nCUDA devices (libdfb_b200 version %d)' % int(_capi.lib().dfb_version()))
+        for i in range(torch.cuda.device_count()):
+            p = torch.cuda.get_device_properties(i)
+            print('    Device %d - Name:  %s' % (i, p.name))
+            print('    Device %d - Compute capability:  %d.%d' % (i, p.major, p.minor))
+            print('    Device %d - Multiprocessors:  %d' % (i, p.multi_processor_count))
+            print('    Device %d - Global Memory:  %.0f GB' % (i, p.total_memory / 1024.0 ** 3))
+        print('\n')

@@ -201,6 +201,8 @@ def test_class_level_errors_and_signatures():
             getattr(fus, name)()
     fdm = FusionDM_GPU(0.2, sc.K, tsdf_res=16)
     assert isinstance(fdm, FusionDM) and fdm._tsdf.shape == (16, 16, 16) and (fdm._tsdf == np.float32(0.2)).all() and (fdm._tsdfw == 0).all()
+    fdm.verbose_gpu()                                                   # core/fusion_dm.py:576 (device listing)
+    assert fdm.write_live_frame_mesh("", "", "") is None                # core/fusion_dm.py:357-358 (empty in the reference)
     with pytest.raises(ValueError):
         fdm.compute_live_tsdf([sc.depths[0]], [])
     t, w = fdm.fuseDepths(sc.depths[0], np.eye(4)[:3], np.full((16, 16, 16), 0.2), np.zeros((16, 16, 16)))
