@@ -35,9 +35,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ALG_BYTES_PER_VOXEL = 16.0  # read v, read w, write v, write w (fp32) -- SURVEY 8d
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes
-TRAFFIC_PER_LAUNCH = {"brick_update_kernel": 971359744, "proj_exact_kernel": 198060288, "brick_classify_kernel": 1899008,
-                      "region_bounds_kernel": 5570304}  # profiles/r1_ncu_full_summary.md
 
 
 def measured_peaks():
@@ -141,130 +138,129 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    per_gpu_res = args.res
-    # y/z extent: the multiple of 32 nearest to per_gpu_res * N^(1/3), so that every z-row starts on a 128-byte line like the
-    # power-of-two grids of the reference's configurations (a 645-voxel row at N=2 put the streaming pass on its unaligned
-    # scalar path: 0.27 instead of 0.11 ms); x-thickness of a slab: the multiple of 4 giving >= per_gpu_res^3 voxels per rank
-    res = max(32, int(round(per_gpu_res * world ** (1.0 / 3.0) / 32.0)) * 32)
-    slab = -(-int(math.ceil(per_gpu_res ** 3 / float(res * res))) // 4) * 4
-    res_x = slab * world
-    grid = (res_x, res, res)
-    x0, x1 = rank * slab, (rank + 1) * slab
+    # STRONG scaling (BASELINE configs[4]): ONE res^3 grid, x-slab [x0, x1) per rank
+    res = args.res
+    grid = (res, res, res)
+    x0, x1 = ddist.slab_partition(res, world)[rank]
     sc = build_scene(res, args.nodes, args.k, args.views)
-    # the scene is generated for a cubic `res` grid; with world>1 res_x can differ from res by rounding
     fus = Fusion(sc.tdist, knn=args.k, device=dev, use_cnn=False, write_warpfield=False)
     fus.InitializeCanonicalSpace(tsdf_shape=grid, slab=(x0, x1), K=sc.K, vertices=sc.vertices, normals=sc.normals,
                                  nodes=sc.nodes_as_reference_tuples())
     fus._lw = sc.lw
     nvox_rank = (x1 - x0) * res * res
+    nvox_total = res ** 3
     n_frames = 15
     dqs = frame_dqs(sc, n_frames)
     dq_dev = [torch.from_numpy(d).to(dev) for d in dqs]
     depth_dev = torch.from_numpy(sc.depths.copy()).to(dev)
     depth_host = torch.from_numpy(sc.depths.copy()).pin_memory()
-    dq_host = [torch.from_numpy(d).pin_memory() for d in dqs]
-    fus.build_knn()                                                  # once per graph revision, outside the timed region
+
+    # ---- graph revision: voxel kNN table + brick / region candidate sets (once per update_graph, core/fusion.py:229) ----
     torch.cuda.synchronize()
+    rev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    rev[0].record()
+    fus.build_knn()
+    rev[1].record()
+    torch.cuda.synchronize()
+    graph_revision_ms = ddist.max_over_ranks(rev[0].elapsed_time(rev[1]), dev)
 
-    # Frames travel in double-buffered packets.  The depth views of step t+1 (sensor data: independent of the fusion result)
-    # are put into the other packet -- and, with several GPUs, broadcast from rank 0 over NVLink on a side stream with its own
-    # process group -- while step t computes; the node transforms (which in the application come out of the solve against the
-    # model updated by step t) are uploaded / broadcast inside their own step.
+    # ---- communicators (raw NCCL through the C ABI): one for the in-step transform broadcast, one for the sensor prefetch ----
+    comm = comm_pre = None
+    if world > 1:
+        comm = engine.Comm.from_torch(dev)
+        comm_pre = engine.Comm.from_torch(dev)
+
+    stream = torch.cuda.Stream(device=dev)           # a capturable (non-default) stream: the step is one CUDA-graph launch
     shape = sc.depths.shape
-    packets = [ddist.FramePacket(shape[0], shape[1], shape[2], sc.n_nodes, dev) for _ in range(2)]
-    side = torch.cuda.Stream(device=dev)
-    side_group = dist.new_group() if world > 1 else None
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    done = [torch.cuda.Event(), torch.cuda.Event()]
-    pending = {"h": None}
+    packets = [torch.zeros(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+    dq_stage = [torch.zeros((sc.n_nodes, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+    counters_host = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+    slot_done = [torch.cuda.Event(), torch.cuda.Event()]
+    wf, vol = fus._wf, fus._vol
+    steps_obj, ios_res, ios_e2e = [], [], []
+    for slot in range(2):
+        views = engine.make_views(packets[slot], sc.K, sc.Kinv, sc.extrinsics)
+        st = engine.FrameStep(vol, wf, sc.lw, views, sc.tdist)
+        steps_obj.append(st)
+        # resident frame: the transforms are already in wf.node_dq on the root, the next depth frame is a device buffer
+        ios_res.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, prefetch_dst=packets[slot ^ 1], prefetch_src=depth_dev))
+        # end to end: transforms and depth come from pinned host memory, the counters go back to pinned host memory
+        ios_e2e.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, dq_src=dq_stage[slot], prefetch_dst=packets[slot ^ 1],
+                             prefetch_src=depth_host, counters_host=counters_host[slot]))
 
-    def stage_depth(slot, src):
-        side.wait_event(done[slot])                                   # the step that last read this packet has finished
-        with torch.cuda.stream(side):
+    def prime(src):
+        """frame 0's sensor data into packet 0 (every later frame arrives through the prefetch branch of the step before it)"""
+        with torch.cuda.stream(stream):
             if rank == 0:
-                packets[slot].depths.copy_(src, non_blocking=True)    # pinned host (e2e) or device-resident frame
-            packets[slot].broadcast_depths(group=side_group)
-            ready[slot].record(side)
-
-    def run_step(i, depth_src, dq_src):
-        slot = i & 1
-        pk = packets[slot]
-        torch.cuda.current_stream().wait_event(ready[slot])
-        if rank == 0:
-            pk.node_dq.copy_(dq_src[i % n_frames], non_blocking=True)
-        pk.broadcast_transforms()
-        fus.set_node_dqs(pk.node_dq)
-        fus.fuseFrame(pk.depths, extrinsics=sc.extrinsics)
-        done[slot].record()
-        stage_depth(slot ^ 1, depth_src)
-
-    def begin(depth_src):
-        def f():
-            done[0].record(); done[1].record()
-            stage_depth(0, depth_src)
-        return f
+                packets[0].copy_(src, non_blocking=True)
+            if comm_pre is not None:
+                comm_pre.broadcast(packets[0])
+        stream.synchronize()
 
     def step_resident(i):
-        run_step(i, depth_dev, dq_dev)
+        slot = i & 1
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                wf.node_dq.copy_(dq_dev[i % n_frames], non_blocking=True)
+            steps_obj[slot].run(ios_res[slot])
 
     def step_e2e(i):
-        run_step(i, depth_host, dq_host)
-        h = fus.frame_stats_async()                                   # D2H of the per-frame counters (32 B) ...
-        if pending["h"] is not None:
-            pending["h"].result()                                     # ... read on the host while the next step is queued
-        pending["h"] = h
-
-    def e2e_end():
-        if pending["h"] is not None:
-            pending["h"].result()
-            pending["h"] = None
+        slot = i & 1
+        slot_done[slot].synchronize()                                  # step i-2 has consumed this slot's staging buffers
+        stats = counters_host[slot].numpy().copy()                     # D2H result of step i-2, read on the host
+        if rank == 0:
+            dq_stage[slot].numpy()[...] = dqs[i % n_frames]            # host -> pinned staging (the solver's output)
+        with torch.cuda.stream(stream):
+            steps_obj[slot].run(ios_e2e[slot])
+            slot_done[slot].record()
+        return stats
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, begin=None, end=None):
-        if begin:
-            begin()
+    def timed(step_fn, steps, warmup, src):
+        prime(src)
         for i in range(warmup):
             step_fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         for i in range(warmup, warmup + steps):
             step_fn(i)
-        if end:
-            end()
-        e1.record()
+        e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return ddist.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    # ---- untimed parity check on the hardware (N > 1): slabs gathered over NCCL == a single-volume run on rank 0 ----
+    parity = None
+    if world > 1:
+        parity = parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, stream, comm, rank, world, dev)
+        # fresh state for the timed runs
+        vol.tsdf.fill_(sc.tdist); vol.weight.zero_()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total = timed(step_resident, args.steps, args.warmup, begin(depth_dev))
+    ms_total = timed(step_resident, args.steps, args.warmup, depth_dev)
     # the K timed steps last only a few tens of ms; keep the same step running (untimed, identical count on every rank so
     # that the collectives match) until the 20 ms sampler has seen ~0.4 s of this load
     n_extra = max(0, int(400.0 / max(ms_total / args.steps, 1e-3)) - args.steps)
-    for i in range(min(n_extra, 2000)):
+    for i in range(min(n_extra, 4000)):
         step_resident(i)
-        if i % 32 == 31:
+        if i % 64 == 63:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), begin(depth_host), e2e_end)
+    for e in slot_done:
+        e.record(stream)
+    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), depth_host)
     stats = fus.frame_stats()
+    gstats = steps_obj[0].stats()
 
     # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----
     kk = 4 if args.k <= 4 else 8
-    # production launches per step: nodes_pack, region_bounds_kernel, brick_classify_kernel, brick_update_kernel (CLAMP + MIXED
-    # bricks fused), proj_exact_kernel.  The two halves of the fused pass are also timed alone (profiling modes) for the breakdown.
     prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
             ("proj_exact_kernel<%d>" % kk, _capi.MODE_LIST_ONLY)]
     parts = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
@@ -295,9 +291,8 @@ def run_ours(args):
     names = prod
     # dominant = the slowest kernel that moves volume data (the classifier reads 48 B per brick, no voxels)
     dominant = max([n for n, _ in prod[1:]], key=kms.get)
-    total_vox = nvox_rank * world
-    value = total_vox * args.steps / (ms_total * 1e-3)
-    e2e_value = total_vox * args.steps / (ms_e2e * 1e-3)
+    value = nvox_total * args.steps / (ms_total * 1e-3)
+    e2e_value = nvox_total * args.steps / (ms_e2e * 1e-3)
     peak, peak_src = measured_peaks()
     step_ms = ms_total / args.steps
     kernels = [{"kernel": n, "ms": kms[n], "voxels": int(units[n]),
@@ -308,24 +303,38 @@ def run_ours(args):
                  "frac": ALG_BYTES_PER_VOXEL * punits[n] / (pms[n] * 1e-3) / 1e9 / peak} for n, _ in parts[1:]]
     achieved = ALG_BYTES_PER_VOXEL * units[dominant] / (kms[dominant] * 1e-3) / 1e9
     step_achieved = ALG_BYTES_PER_VOXEL * nvox_rank / (step_ms * 1e-3) / 1e9
+    traffic = measured_traffic(dominant) if world == 1 else None
     out = {
         "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d^3 voxels per GPU (grid %dx%dx%d), warped projective TSDF update (a3), k=%d DQB, %d nodes, "
-                               "%d view(s) 640x480, 15-frame dq sequence" % (per_gpu_res, res_x, res, res, args.k, sc.n_nodes, args.views),
-                   "l2": "inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % (nvox_rank * (8 + 2 * args.k) / 1e6),
-                   "parallelism": "x-slab per GPU, frame broadcast over NCCL" if world > 1 else "single GPU",
+        "config": {"workload": "%d^3 voxels total (one grid, x-slab of %d planes per GPU), warped projective TSDF update (a3), k=%d DQB, "
+                               "%d nodes, %d view(s) 640x480, 15-frame dq sequence" % (res, x1 - x0, args.k, sc.n_nodes, args.views),
+                   "l2": "inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % (nvox_rank * (8 + 2 * args.k) / 1e6)
+                         if nvox_rank * (8 + 2 * args.k) > 2.5e8 else
+                         "slab of %.0f MB (v,w,kNN) per GPU: at N>=4 a 512^3/N slab approaches the 126 MB L2; every step streams the whole slab "
+                         "once, so the working set is re-read from HBM unless it fits" % (nvox_rank * (8 + 2 * args.k) / 1e6),
+                   "parallelism": ("x-slab per GPU (strong scaling of ONE grid); per step ONE CUDA-graph launch per rank: NCCL broadcast of the "
+                                   "node transforms + update kernels, next depth frame broadcast as a concurrent graph branch") if world > 1
+                                  else "single GPU, one CUDA-graph launch per step",
                    "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
         "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(sc.depths.nbytes + dqs[0].nbytes),
                 "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps,
-                "pipeline": "pinned-host depth frame of step t+1 uploaded on a copy stream while step t computes (double-buffered "
-                            "frame packet); node transforms uploaded inside their own step; counters of step t read back while step "
-                            "t+1 is queued; every step's H2D and D2H lie inside the timed region"},
+                "pipeline": "per step: host copies the frame's node transforms into pinned staging, ONE graph launch = [H2D transforms -> "
+                            "(NCCL bcast) -> node records -> classify/update/exact kernels -> D2H of the 8 frame counters] with the H2D (+bcast) "
+                            "of the next frame's pinned depth image as a concurrent branch; the host reads step t-2's counters before "
+                            "re-using its slot; every step's H2D and D2H lie inside the timed region"},
         "gpu_launches": 5 * args.steps,
+        "step_graph": gstats,
         "clocks": clocks,
+        "graph_revision_ms": graph_revision_ms,
+        "value_amortised": {"revision_every_frame": nvox_total / ((step_ms + graph_revision_ms) * 1e-3),
+                            "revision_every_15_frames": nvox_total / ((step_ms + graph_revision_ms / 15.0) * 1e-3),
+                            "note": "the reference rebuilds its KD-tree in update_graph (core/fusion.py:229) and queries it per voxel per frame "
+                                    "(:175); here the voxel kNN table + brick/region sets are rebuilt once per graph revision "
+                                    "(`graph_revision_ms`, full rebuild) and `value` excludes it"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": TRAFFIC_PER_LAUNCH.get(dominant.split("<")[0]),
+                     "frac": achieved / peak, "traffic": traffic,
                      "note": "dominant kernel by time; its units = the voxels that launch processes x 16 B. The step as a whole "
                              "(all voxels of the slab x 16 B / step time) is in `step`.",
                      "algorithmic_bytes_per_voxel": ALG_BYTES_PER_VOXEL,
@@ -333,17 +342,100 @@ def run_ours(args):
                      "kernels": kernels,
                      "bricks": {"total": stats["bricks"], "streamed": stats["bricks_streamed"], "mixed": stats["bricks_mixed"]}},
     }
+    if parity is not None:
+        out["parity_check"] = parity
     if not args.no_gn:
-        out["gn"] = bench_gn(args, dev, rank, world)
+        out["gn"] = bench_gn(args, dev, rank, world, comm)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(sc, (res_x, res, res), budget_s=args.cpu_seconds)
+        out["cpu_baseline"] = cpu_baseline(sc, grid, budget_s=args.cpu_seconds)
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def bench_gn(args, dev, rank, world):
+def measured_traffic(kernel_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full summary of
+    THIS round's kernels (profiles/r2_ncu_full_summary.md, same 512^3 N=1 workload); None when no capture of that kernel is committed."""
+    import re
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_summary.md")
+    if not os.path.isfile(path):
+        return None
+    base = kernel_name.split("<")[0]
+    rd = wr = None
+    active = False
+    for line in open(path):
+        if line.startswith("## "):
+            active = base in line
+        elif active:
+            m = re.match(r"- dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
+            if m:
+                mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                if m.group(1) == "read":
+                    rd = float(m.group(2)) * mult
+                else:
+                    wr = float(m.group(2)) * mult
+    return None if rd is None or wr is None else int(rd + wr)
+
+
+def parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, stream, comm, rank, world, dev):
+    """Three frames on the sharded volume (through the timed path: graph launches + NCCL broadcasts) against the same three
+    frames on a single res^3 volume held by rank 0; slabs are gathered over NCCL.  SURVEY 8e: weights and values must be equal
+    bit for bit."""
+    import torch
+    from dynamicfusion_body_b200 import engine
+    res = args.res
+    vol, wf = fus._vol, fus._wf
+    vol.tsdf.fill_(sc.tdist); vol.weight.zero_()
+    prime(depth_dev)
+    n_chk = 3
+    for i in range(n_chk):
+        with torch.cuda.stream(stream):
+            if rank == 0:
+                wf.node_dq.copy_(dq_dev[i], non_blocking=True)
+            steps_obj[i & 1].run(ios_res[i & 1])
+    stream.synchronize()
+    torch.cuda.synchronize()
+    # gather the slabs on rank 0 (dfb_comm_sendrecv)
+    from dynamicfusion_body_b200 import dist as ddist
+    parts = ddist.slab_partition(res, world)
+    result = None
+    if rank == 0:
+        full_t = torch.empty((res, res, res), dtype=torch.float32, device=dev)
+        full_w = torch.empty_like(full_t)
+        full_t[parts[0][0]:parts[0][1]] = vol.tsdf
+        full_w[parts[0][0]:parts[0][1]] = vol.weight
+        for r in range(1, world):
+            a, b = parts[r]
+            comm.sendrecv(recv=full_t[a:b], recv_peer=r)
+            comm.sendrecv(recv=full_w[a:b], recv_peer=r)
+        torch.cuda.synchronize()
+        # the same frames on one volume
+        wf1 = engine.DeviceWarpField(args.k, dev)
+        wf1.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
+        vol1 = engine.DeviceVolume((res, res, res), device=dev, fill=sc.tdist)
+        for i in range(n_chk):
+            wf1.set_dq(dq_dev[i])
+            engine.update_projective(vol1, wf1, sc.lw, depth_dev, sc.K, sc.Kinv, sc.extrinsics, sc.tdist)
+        torch.cuda.synchronize()
+        w_equal = bool(torch.equal(full_w, vol1.weight))
+        v_equal = bool(torch.equal(full_t, vol1.tsdf))
+        max_diff = float((full_t - vol1.tsdf).abs().max().item())
+        updated = int((vol1.weight > 0).sum().item())
+        result = {"tsdf": "ok" if (w_equal and v_equal) else ("ok_within_1e-6_tdist" if (w_equal and max_diff <= 1e-6 * sc.tdist) else "MISMATCH"),
+                  "frames": n_chk, "weights_bit_equal": w_equal, "values_bit_equal": v_equal, "max_abs_value_diff": max_diff,
+                  "updated_voxels": updated, "how": "slabs gathered on rank 0 over NCCL vs the same frames on one %d^3 volume" % res}
+        del full_t, full_w, vol1, wf1
+        torch.cuda.empty_cache()
+    else:
+        comm.sendrecv(send=vol.tsdf, send_peer=0)
+        comm.sendrecv(send=vol.weight, send_peer=0)
+        torch.cuda.synchronize()
+    return result
+
+
+def bench_gn(args, dev, rank, world, comm=None):
     """Second half of the BASELINE metric: Gauss-Newton ms/iteration (config 3: ~1k nodes, k=4, ~300k data residuals of
     one 640x480 frame, 15 iterations).  N>1: data residuals sharded over ranks, normal equations all-reduced (NCCL)."""
     import torch
@@ -356,7 +448,7 @@ def bench_gn(args, dev, rank, world):
     shard = ddist.residual_partition(len(pd.vertices), world)[rank]
     prob = gn.Problem(wf, pd.vertices, pd.normals, pd.corr, pd.vert_knn, pd.node_vertex_idx, shard=shard, reg_owner=(rank == 0))
     x = torch.from_numpy(pd.x0).to(dev)
-    allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c)) if world > 1 else None
+    allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c, comm=comm)) if world > 1 else None
     prob.pattern()
     res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce)         # warm-up
     torch.cuda.synchronize()

@@ -10,6 +10,7 @@ import os
 DFB_MAX_K = 8
 DFB_MAX_VIEWS = 8
 DFB_NODE_REC_FLOATS = 12
+DFB_COMM_ID_BYTES = 128
 MODE_HYBRID = 0
 MODE_EXACT = 1
 MODE_FAST_ONLY = 2
@@ -64,6 +65,12 @@ class GNProblem(C.Structure):
                 ("rw", C.c_double), ("huber", C.c_int), ("f_scale", C.c_double)]
 
 
+class FrameIO(C.Structure):
+    _fields_ = [("comm", C.c_void_p), ("comm_prefetch", C.c_void_p), ("root", C.c_int), ("dq_src", C.c_void_p),
+                ("prefetch_dst", C.c_void_p), ("prefetch_src", C.c_void_p), ("prefetch_bytes", C.c_int64),
+                ("counters_host", C.c_void_p)]
+
+
 class PointGrid(C.Structure):
     _fields_ = [("pts", C.c_void_p), ("n", C.c_int64), ("origin", C.c_double * 3), ("cell", C.c_double),
                 ("dims", C.c_int * 3), ("cell_start", C.c_void_p), ("order", C.c_void_p)]
@@ -110,6 +117,21 @@ def declare(lib, prefix="dfb_", device=True):
         "mc_count": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp], C.c_int),
         "mc_emit": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp], C.c_int),
         "gn_solve": ([C.c_int, vp, vp, vp, vp, C.c_double, C.c_int, C.c_double, vp, vp, vp, vp, vp], C.c_int),
+        "comm_available": ([], C.c_int),
+        "comm_unique_id": ([vp], C.c_int),
+        "comm_init": ([C.POINTER(vp), vp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "comm_destroy": ([vp], C.c_int),
+        "comm_rank": ([vp], C.c_int),
+        "comm_world": ([vp], C.c_int),
+        "comm_broadcast": ([vp, vp, C.c_int64, C.c_int, vp], C.c_int),
+        "comm_broadcast_frame": ([vp, vp, C.c_int64, vp, C.c_int, vp, C.c_int, vp], C.c_int),
+        "comm_allreduce_f64": ([vp, vp, C.c_int64, C.c_int, vp], C.c_int),
+        "comm_sendrecv": ([vp, vp, C.c_int64, C.c_int, vp, C.c_int64, C.c_int, vp], C.c_int),
+        "frame_step_create": ([C.POINTER(vp)], C.c_int),
+        "frame_step_destroy": ([vp], None),
+        "frame_step_run": ([vp, C.POINTER(Volume), C.POINTER(WarpField), C.POINTER(Views), C.c_double, C.c_double,
+                            C.POINTER(Workspace), C.POINTER(FrameIO), vp], C.c_int),
+        "frame_step_stats": ([vp, C.POINTER(C.c_int64)], C.c_int),
     }
     for name, (argtypes, restype) in sig.items():
         fn = getattr(lib, prefix + name, None)
@@ -152,4 +174,7 @@ EXPORTS = [
     "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",
     "dfb_point_grid_scratch_ints", "dfb_point_grid_build", "dfb_point_grid_knn", "dfb_corr_select", "dfb_graph_unsupported", "dfb_graph_sample_rounds",
     "dfb_mc_level_scratch_floats", "dfb_mc_level", "dfb_mc_rows", "dfb_mc_chunks", "dfb_mc_count", "dfb_mc_emit",
+    "dfb_comm_available", "dfb_comm_unique_id", "dfb_comm_init", "dfb_comm_destroy", "dfb_comm_rank", "dfb_comm_world",
+    "dfb_comm_broadcast", "dfb_comm_broadcast_frame", "dfb_comm_allreduce_f64", "dfb_comm_sendrecv",
+    "dfb_frame_step_create", "dfb_frame_step_destroy", "dfb_frame_step_run", "dfb_frame_step_stats",
 ]

@@ -75,16 +75,37 @@ class FramePacket:
         return self
 
 
-def allreduce_normal_equations(H, g, cost, group=None):
-    """Sum the block-sparse normal equations over ranks (one flat buffer -> one collective)."""
-    if not is_dist():
+def flat_normal_equations(H, g, cost):
+    """The flat [H | g | cost] tensor when the three are adjacent views of one buffer (how gn.Problem.normal_equations
+    allocates them), else None."""
+    try:
+        same = H.untyped_storage().data_ptr() == g.untyped_storage().data_ptr() == cost.untyped_storage().data_ptr()
+    except Exception:
+        return None
+    if (same and H.is_contiguous() and g.is_contiguous() and cost.is_contiguous() and g.storage_offset() == H.storage_offset() + H.numel()
+            and cost.storage_offset() == g.storage_offset() + g.numel()):
+        return torch.as_strided(H, (H.numel() + g.numel() + cost.numel(),), (1,), H.storage_offset())
+    return None
+
+
+def allreduce_normal_equations(H, g, cost, group=None, comm=None):
+    """Sum the block-sparse normal equations over ranks: ONE collective on the flat [H | g | cost] buffer, in place.
+    comm: an engine.Comm (raw NCCL through the C ABI, dfb_comm_allreduce_f64); default: torch.distributed."""
+    if comm is None and not is_dist():
         return H, g, cost
-    flat = torch.cat([H.reshape(-1), g.reshape(-1), cost.reshape(-1)])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    nH, ng = H.numel(), g.numel()
-    H.copy_(flat[:nH].view_as(H))
-    g.copy_(flat[nH:nH + ng].view_as(g))
-    cost.copy_(flat[nH + ng:].view_as(cost))
+    flat = flat_normal_equations(H, g, cost)
+    packed = flat is None
+    if packed:                                            # separate tensors (callers outside gn.Problem): pack once
+        flat = torch.cat([H.reshape(-1), g.reshape(-1), cost.reshape(-1)])
+    if comm is not None:
+        comm.allreduce_f64(flat)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    if packed:
+        nH, ng = H.numel(), g.numel()
+        H.copy_(flat[:nH].view_as(H))
+        g.copy_(flat[nH:nH + ng].view_as(g))
+        cost.copy_(flat[nH + ng:].view_as(cost))
     return H, g, cost
 
 

@@ -143,15 +143,24 @@ class DeviceWarpField:
         self.n_nodes = n
         self._knn = {}
         self._bricks = {}
+        self.node_dq = None
         self.set_dq(node_dq)
 
     def set_dq(self, node_dq):
-        """Only the transforms changed (e.g. after solve): repack records, keep the kNN tables."""
-        self.node_dq = _to_dev(node_dq, torch.float32, self.device).reshape(self.n_nodes, 8)
+        """Only the transforms changed (e.g. after solve): repack records, keep the kNN tables.  The device buffers keep their
+        addresses while the node count stays the same (a captured frame step refers to them)."""
+        if (self.node_dq is not None and tuple(self.node_dq.shape) == (self.n_nodes, 8)
+                and (isinstance(node_dq, torch.Tensor) or isinstance(node_dq, np.ndarray))):
+            src = node_dq if isinstance(node_dq, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(node_dq, dtype=np.float32))
+            if src.data_ptr() != self.node_dq.data_ptr():
+                self.node_dq.copy_(src.reshape(self.n_nodes, 8), non_blocking=True)
+        else:
+            self.node_dq = _to_dev(node_dq, torch.float32, self.device).reshape(self.n_nodes, 8)
         self.repack()
 
     def repack(self):
-        self.node_rec = torch.empty((self.n_nodes, _capi.DFB_NODE_REC_FLOATS), dtype=torch.float32, device=self.device)
+        if self.node_rec is None or self.node_rec.shape[0] != self.n_nodes:
+            self.node_rec = torch.empty((self.n_nodes, _capi.DFB_NODE_REC_FLOATS), dtype=torch.float32, device=self.device)
         _capi.check(_capi.lib().dfb_nodes_pack(_ptr(self.node_pos), _ptr(self.node_dq), _ptr(self.node_w), self.n_nodes,
                                                _ptr(self.node_rec), _stream()))
 
@@ -492,3 +501,114 @@ def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False
             po = offs[:, ::ny].cpu().numpy().astype(np.int64)        # rows are (x, y) pairs: every ny-th entry starts an x-plane; [rows] = total
             out += (po[0], po[1])
         return out
+
+
+# ---- NCCL communicator and the one-launch frame step (csrc/comm.cu, csrc/step.cu) ----------------
+class Comm:
+    """dfb_comm: one NCCL communicator per process / GPU, created from a unique id.  `from_torch` distributes the id with
+    torch.distributed (any backend) -- a host without torch hands the DFB_COMM_ID_BYTES bytes around by its own means."""
+
+    def __init__(self, unique_id, world, rank, device=None):
+        dev = _require_cuda(device)
+        self.device = dev
+        self.world, self.rank = int(world), int(rank)
+        self._h = C.c_void_p()
+        buf = (C.c_char * _capi.DFB_COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _capi.check(_capi.lib().dfb_comm_init(C.byref(self._h), buf, self.world, self.rank, dev.index if dev.index is not None else torch.cuda.current_device()))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_char * _capi.DFB_COMM_ID_BYTES)()
+        _capi.check(_capi.lib().dfb_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, device=None, group=None):
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        return cls(box[0], world, rank, device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def broadcast(self, t, root=0):
+        assert t.is_cuda and t.is_contiguous()
+        _capi.check(_capi.lib().dfb_comm_broadcast(self._h, _ptr(t), t.numel() * t.element_size(), int(root), _stream()))
+        return t
+
+    def broadcast_frame(self, depths=None, node_dq=None, lw=None, root=0):
+        for t, dt in ((depths, torch.float32), (node_dq, torch.float32), (lw, torch.float64)):
+            assert t is None or (t.is_cuda and t.is_contiguous() and t.dtype == dt)
+        _capi.check(_capi.lib().dfb_comm_broadcast_frame(self._h, _ptr(depths), 0 if depths is None else depths.numel(), _ptr(node_dq),
+                                                         0 if node_dq is None else node_dq.shape[0], _ptr(lw), int(root), _stream()))
+
+    def allreduce_f64(self, t, op="sum"):
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float64
+        _capi.check(_capi.lib().dfb_comm_allreduce_f64(self._h, _ptr(t), t.numel(), 0 if op == "sum" else 1, _stream()))
+        return t
+
+    def sendrecv(self, send=None, send_peer=-1, recv=None, recv_peer=-1):
+        _capi.check(_capi.lib().dfb_comm_sendrecv(self._h, _ptr(send), 0 if send is None else send.numel() * send.element_size(), int(send_peer),
+                                                  _ptr(recv), 0 if recv is None else recv.numel() * recv.element_size(), int(recv_peer), _stream()))
+
+    def close(self):
+        if self._h:
+            _capi.lib().dfb_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+class FrameStep:
+    """dfb_frame_step: one frame of the a3 path (transform upload / broadcast -> node records -> warped projective update ->
+    counters read-back, plus the prefetch of the next frame's sensor data as a concurrent branch) as ONE CUDA-graph launch.
+    The argument structs are built once; `run` is a single C call."""
+
+    def __init__(self, vol, wf, lw, views, tdist, wmax=100.0):
+        self._h = C.c_void_p()
+        _capi.check(_capi.lib().dfb_frame_step_create(C.byref(self._h)))
+        self.vol, self.wf, self.views = vol, wf, views
+        knn = wf.knn_table(vol.res, vol.x0, vol.x1)
+        bricks = wf.brick_nodes(vol.res, vol.x0, vol.x1)
+        self._keep = (knn, bricks)
+        self._v = vol.struct()
+        self._w = wf.struct(lw, knn, bricks=bricks)
+        self._ws = vol.workspace.struct(True)
+        self.tdist, self.wmax = float(tdist), float(wmax)
+
+    def set_lw(self, lw):
+        fill_lw(self._w, lw)
+
+    def set_views(self, views):
+        self.views = views
+
+    def io(self, comm=None, comm_prefetch=None, root=0, dq_src=None, prefetch_dst=None, prefetch_src=None, counters_host=None):
+        io = _capi.FrameIO()
+        io.comm = comm.handle if comm is not None else None
+        io.comm_prefetch = comm_prefetch.handle if comm_prefetch is not None else None
+        io.root = int(root)
+        io.dq_src = dq_src.data_ptr() if dq_src is not None else None
+        if prefetch_dst is not None:
+            io.prefetch_dst = prefetch_dst.data_ptr()
+            io.prefetch_bytes = prefetch_dst.numel() * prefetch_dst.element_size()
+            io.prefetch_src = prefetch_src.data_ptr() if prefetch_src is not None else None
+        io.counters_host = counters_host.data_ptr() if counters_host is not None else None
+        io._keep = (comm, comm_prefetch, dq_src, prefetch_dst, prefetch_src, counters_host)
+        return io
+
+    def run(self, io=None):
+        _capi.check(_capi.lib().dfb_frame_step_run(self._h, C.byref(self._v), C.byref(self._w), C.byref(self.views), self.tdist, self.wmax,
+                                                   C.byref(self._ws), C.byref(io) if io is not None else None, _stream()))
+
+    def stats(self):
+        out = (C.c_int64 * 5)()
+        _capi.check(_capi.lib().dfb_frame_step_stats(self._h, out))
+        return {"captures": out[0], "updates": out[1], "replays": out[2], "direct": out[3], "graph_nodes": out[4]}
+
+    def __del__(self):
+        try:
+            if self._h:
+                _capi.lib().dfb_frame_step_destroy(self._h)
+        except Exception:
+            pass

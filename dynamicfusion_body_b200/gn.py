@@ -144,9 +144,10 @@ class Problem:
         """(H [nnzb,8,8], g [8N], cost [2]) float64 CUDA tensors for x (CUDA f64 [8N])."""
         row_ptr, col_idx, nnzb = self.pattern()
         if out is None:
-            H = torch.empty((nnzb, 8, 8), dtype=torch.float64, device=self.device)
-            g = torch.empty(8 * self.n_nodes, dtype=torch.float64, device=self.device)
-            cost = torch.empty(2, dtype=torch.float64, device=self.device)
+            # one flat buffer [H | g | cost]: the sharded solve sums it over ranks with ONE collective, in place (dist.py)
+            nH, ng = nnzb * 64, 8 * self.n_nodes
+            flat = torch.empty(nH + ng + 2, dtype=torch.float64, device=self.device)
+            H, g, cost = flat[:nH].view(nnzb, 8, 8), flat[nH:nH + ng], flat[nH + ng:]
         else:
             H, g, cost = out
         p = self.struct(lw, rw, huber, f_scale, sharded=True)

@@ -262,6 +262,56 @@ int dfb_mc_emit(const float* vol, int rx, int ry, int rz, int step, int x_origin
                 const int32_t* row_voff, const int32_t* row_toff, float* verts, float* normals, float* values, int32_t* faces,
                 dfb_stream_t stream);
 
+/* ---- collectives of the sharded path over NCCL -------------------------------------------
+ * The reference is single-process (SURVEY 5 "Distributed communication backend: none"); these are what the slab-sharded
+ * update and the residual-sharded solve need: per frame a root -> all broadcast of depth view(s) + node transforms +
+ * global rigid dq, per Gauss-Newton iteration one sum of the flat [H | g | cost] buffer, and the neighbour exchange of
+ * halo planes for surface extraction.  NCCL is bound at run time (dlopen libnccl.so.2); one communicator per GPU /
+ * process, created from a unique id that the host distributes by its own means (file, socket, MPI, torch store). */
+#define DFB_COMM_ID_BYTES 128
+#define DFB_COMM_SUM 0
+#define DFB_COMM_MAX 1
+typedef struct dfb_comm dfb_comm;
+int dfb_comm_available(void);                 /* 0 = NCCL could not be loaded, else its version code (or 1) */
+int dfb_comm_unique_id(void* id_out);         /* host buffer of DFB_COMM_ID_BYTES; call on one rank, hand the bytes to all */
+int dfb_comm_init(dfb_comm** out, const void* id, int world, int rank, int device);
+int dfb_comm_destroy(dfb_comm* c);
+int dfb_comm_rank(const dfb_comm* c);
+int dfb_comm_world(const dfb_comm* c);
+int dfb_comm_broadcast(dfb_comm* c, void* buf, int64_t bytes, int root, dfb_stream_t stream);
+/* depths [n_depth] float32, node_dq [n_nodes][8] float32, lw [8] float64 (each optional), one grouped launch */
+int dfb_comm_broadcast_frame(dfb_comm* c, float* depths, int64_t n_depth, float* node_dq, int n_nodes, double* lw, int root,
+                             dfb_stream_t stream);
+/* in-place reduction over ranks of n doubles: the flat normal-equation buffer [H (nnzb*64) | g (8N) | cost (2)] */
+int dfb_comm_allreduce_f64(dfb_comm* c, double* buf, int64_t n, int op, dfb_stream_t stream);
+/* grouped send to send_peer + receive from recv_peer (either side optional: peer < 0 or NULL buffer) */
+int dfb_comm_sendrecv(dfb_comm* c, const void* send_buf, int64_t send_bytes, int send_peer, void* recv_buf, int64_t recv_bytes,
+                      int recv_peer, dfb_stream_t stream);
+
+/* ---- one frame of the a3 path as ONE CUDA-graph launch (the reference's per-frame `updateTSDF` call, test.py:129) ----
+ * dfb_frame_step_run = [root: copy dq_src -> wf->node_dq] -> [broadcast wf->node_dq over io->comm] -> dfb_nodes_pack ->
+ * dfb_tsdf_update_projective(DFB_MODE_HYBRID) -> [copy ws->counters -> counters_host], with the upload + broadcast of the next
+ * frame's sensor data (prefetch_*) as a concurrent branch.  Captured on first use, replayed while the arguments stay
+ * byte-identical, updated in place (cudaGraphExecUpdate) when they change.  `stream` must not be the legacy default
+ * stream (then the launches are issued directly, un-captured).  Every field of dfb_frame_io is optional (NULL / 0). */
+typedef struct dfb_frame_io {
+    dfb_comm* comm;           /* transforms: root -> all at the head of the step */
+    dfb_comm* comm_prefetch;  /* sensor data of the NEXT frame: root -> all, concurrent with the step (its own communicator) */
+    int root;
+    const float* dq_src;      /* root: this frame's node transforms [n_nodes][8] (pinned host or device), NULL = already in wf->node_dq */
+    void* prefetch_dst;       /* device buffer the next frame's sensor data lands in (not the one this step reads) */
+    const void* prefetch_src; /* root: its source (pinned host or device), NULL = already in prefetch_dst */
+    int64_t prefetch_bytes;
+    uint32_t* counters_host;  /* pinned host [8]: ws->counters after the step */
+} dfb_frame_io;
+typedef struct dfb_frame_step dfb_frame_step;
+int dfb_frame_step_create(dfb_frame_step** out);
+void dfb_frame_step_destroy(dfb_frame_step* st);
+int dfb_frame_step_run(dfb_frame_step* st, const dfb_volume* vol, const dfb_warpfield* wf, const dfb_views* views, double tdist,
+                       double wmax, const dfb_workspace* ws, const dfb_frame_io* io, dfb_stream_t stream);
+/* out = {captures, in-place updates, replays, un-captured runs, nodes of the last captured graph} */
+int dfb_frame_step_stats(const dfb_frame_step* st, int64_t out[5]);
+
 #ifdef __cplusplus
 }
 #endif
