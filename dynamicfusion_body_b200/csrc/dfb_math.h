@@ -257,6 +257,42 @@ DFB_HD double dot4_ref(const double* r, double a, double b, double c, double d) 
     return dadd(dadd(dadd(dmul(r[0], a), dmul(r[1], b)), dmul(r[2], c)), dmul(r[3], d));
 }
 
+// fast-tier transcendental / reciprocal: raw MUFU ops on the device (2 ulp; the error margins have > 30 ulp head-room)
+DFB_HD float fast_exp2(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return exp2f(x);
+#endif
+}
+DFB_HD float fast_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// fp32 clamped update of FusionDM.fuseDepths: v' = (scale*v*w + tdist)/(scale*(w+1)); w' = min(w+1, wmax)
+// The quotient uses the MUFU reciprocal (<= 1 ulp): |v'| <= tdist, so the result is within 3 ulp = 4e-7 tdist of the
+// float64 value the reference stores, against the 1e-5 tdist budget.
+// BOTH tiers evaluate a clamped update with this function (the exact tier once its float64 decision is "tl >= tdist"), so a
+// voxel gets the same bits whichever tier resolves it -- slabs / brick grids of any decomposition concatenate to the
+// single-volume result bit for bit.
+DFB_HD void clamp_update(float& v, float& w, float tdist, float wmax, float scale) {
+    // explicit roundings: the compiler must not contract / reassociate this differently at its two call sites
+#if defined(__CUDA_ARCH__)
+    v = __fmul_rn(__fmaf_rn(__fmul_rn(scale, v), w, tdist), fast_rcp(__fmul_rn(scale, __fadd_rn(1.0f, w))));
+#else
+    v = fmul(fmaf(fmul(scale, v), w, tdist), fast_rcp(fmul(scale, fadd(1.0f, w))));
+#endif
+    w = fminf(fadd(1.0f, w), wmax);
+}
+
 // Per-voxel body of FusionDM.fuseDepths from project_to_pixel on (core/fusion_dm.py:194-210,
 // core/util.py:312-320).  v,w: running float64 state (in/out).  Returns bit0 = updated, bit1 = in frustum.
 DFB_HDN int project_fuse_ref(const double* lpos, const float* depth, int rows, int cols, const double* K,
@@ -273,7 +309,15 @@ DFB_HDN int project_fuse_ref(const double* lpos, const float* depth, int rows, i
     const double c2 = dot3_ref(Kinv + 6, dmul(z, u), dmul(z, vv), dmul(z, 1.0));
     const double tl = dsub(c2, lpos[2]);
     if (!(tl > -1.0 * tdist)) return 2;
-    const double m = (tl < tdist) ? tl : tdist;  // python min(tdist, tl)
+    if (!(tl < tdist)) {
+        // min(tdist, tl) = tdist: the clamped running average, evaluated exactly like the fast tier does (see clamp_update)
+        float vf = (float)*v, wf = (float)*w;
+        clamp_update(vf, wf, (float)tdist, (float)wmax, (float)scale);
+        *v = (double)vf;
+        *w = (double)wf;
+        return 3;
+    }
+    const double m = tl;  // python min(tdist, tl)
     const double wt = *w;
     *v = ddiv(dadd(dmul(dmul(scale, *v), wt), dmul(m, 1.0)), dmul(scale, dadd(1.0, wt)));
     const double s = dadd(1.0, wt);

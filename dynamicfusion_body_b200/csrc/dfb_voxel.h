@@ -83,33 +83,30 @@ struct VolParams {
     uint8_t* mask_out;
 };
 
-// fast-tier transcendental / reciprocal: raw MUFU ops on the device (2 ulp; the error margins have > 30 ulp head-room)
-DFB_HD float fast_exp2(float x) {
-#if defined(__CUDA_ARCH__)
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#else
-    return exp2f(x);
+// Where the packed node records are read from: global memory (any caller), or the shared-memory copy of the whole table that
+// the production update kernel keeps (explicit ld.shared: a generic pointer would cost the address-space check on every gather).
+struct RecGlobal {
+    const float4* p;
+    DFB_HD float4 ld(size_t i) const { return p[i]; }
+};
+#if defined(__CUDACC__)
+struct RecShared {
+    uint32_t base;   // shared-window address of record 0
+    __device__ __forceinline__ float4 ld(size_t i) const {
+        float4 r;
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(base + (uint32_t)i * 16u));
+        return r;
+    }
+};
 #endif
-}
-DFB_HD float fast_rcp(float x) {
-#if defined(__CUDA_ARCH__)
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-#else
-    return 1.0f / x;
-#endif
-}
 
 // ---- fast tier: DQB of k nodes in fp32 --------------------------------------------------------
 // rec layout: [pos.xyz, coef][dq0..3][dq4..7], coef = -log2(e)/(4 w^2)  (exp(-(d/2w)^2) = exp2(coef*d^2))
 // Returns false when the fp32 chain cannot be trusted at all (all weights underflow in the reference's
 // float64 exp, or zero blend) -> caller treats the voxel as uncertain.
 // amin_out: most negative exp argument (natural-log units) among the k nodes: scales the error bound.
-template <int KMAX>
-DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, float px, float py, float pz, float* out,
+template <int KMAX, class Rec>
+DFB_HD bool blend_warp_fast(const Rec rec, const uint16_t* ids, int k_rt, float px, float py, float pz, float* out,
                             float* amin_out, bool exact_k = false) {
     const int k = exact_k ? KMAX : k_rt;   // exact_k is a compile-time constant at every call site: predicates fold away
     float a[KMAX];
@@ -117,7 +114,7 @@ DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, fl
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
         if (i < k) {
-            const float4 r0 = rec[3 * (size_t)ids[i]];
+            const float4 r0 = rec.ld(3 * (size_t)ids[i]);
             const float dx = px - r0.x, dy = py - r0.y, dz = pz - r0.z;
             a[i] = (dx * dx + dy * dy + dz * dz) * r0.w;
             amax = fmaxf(amax, a[i]);
@@ -135,8 +132,8 @@ DFB_HD bool blend_warp_fast(const float4* rec, const uint16_t* ids, int k_rt, fl
     for (int i = 0; i < KMAX; ++i) {
         if (i < k) {
             const float w = fast_exp2(a[i] - amax);
-            const float4 r1 = rec[3 * (size_t)ids[i] + 1];
-            const float4 r2 = rec[3 * (size_t)ids[i] + 2];
+            const float4 r1 = rec.ld(3 * (size_t)ids[i] + 1);
+            const float4 r2 = rec.ld(3 * (size_t)ids[i] + 2);
             b[0] += w * r1.x; b[1] += w * r1.y; b[2] += w * r1.z; b[3] += w * r1.w;
             b[4] += w * r2.x; b[5] += w * r2.y; b[6] += w * r2.z; b[7] += w * r2.w;
         }
@@ -198,14 +195,6 @@ DFB_HD int classify_view(float pu, float pv, float pz, float lz, float e, const 
     return CLS_UNCERTAIN;
 }
 
-// fp32 clamped update of FusionDM.fuseDepths: v' = (scale*v*w + tdist)/(scale*(w+1)); w' = min(w+1, wmax)
-// The quotient uses the MUFU reciprocal (<= 1 ulp): |v'| <= tdist, so the result is within 3 ulp = 4e-7 tdist of the
-// float64 value the reference stores, against the 1e-5 tdist budget.
-DFB_HD void clamp_update(float& v, float& w, float tdist, float wmax, float scale) {
-    v = (scale * v * w + tdist) * fast_rcp(scale * (1.0f + w));
-    w = fminf(1.0f + w, wmax);
-}
-
 // ---- exact tier: whole-voxel functions --------------------------------------------------------
 // a3 / a2 for one voxel; v,w in/out (float32 storage, float64 arithmetic).  Returns mask bits in
 // *mask, frustum bits in *frus.
@@ -255,9 +244,9 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
 // ONEVIEW: n_views == 1 known at compile time (the view record is then addressed with immediate offsets)
 // views / m0 / f0: a MIXED brick hands over the views its box test left open (bit mask) and the CLAMP / frustum bits of the
 // views it settled; only the open views are evaluated here.  Defaults = every view open.
-template <int KMAX, bool EXACTK = false, bool ONEVIEW = false>
-DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus,
-                                     int views = 0xff, int m0 = 0, int f0 = 0) {
+template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
+DFB_HD int voxel_projective_classify_rec(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus,
+                                         int views, int m0, int f0, const Rec rec) {
     float pw[3];
     float e;
     if (P.rigid) {
@@ -265,7 +254,7 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
         e = 1.1920929e-7f * P.coord_mag * 32.f;
     } else {
         float amin;
-        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin, EXACTK)) return CLS_UNCERTAIN;
+        if (!blend_warp_fast<KMAX>(rec, ids, P.k, (float)x, (float)y, (float)z, pw, &amin, EXACTK)) return CLS_UNCERTAIN;
         e = pos_err_bound(P.coord_mag, amin);
     }
     int m = m0, f = f0;
@@ -287,6 +276,13 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
     *mask = m;
     *frus = f;
     return m ? CLS_CLAMP : CLS_SKIP;
+}
+
+template <int KMAX, bool EXACTK = false, bool ONEVIEW = false>
+DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, const uint16_t* ids, int* mask, int* frus,
+                                     int views = 0xff, int m0 = 0, int f0 = 0) {
+    const RecGlobal rec = {P.node_rec};
+    return voxel_projective_classify_rec<KMAX, EXACTK, ONEVIEW>(P, x, y, z, ids, mask, frus, views, m0, f0, rec);
 }
 
 // a1 for one voxel, exact tier.
@@ -314,7 +310,8 @@ DFB_HD int voxel_volume_classify(const VolParams& P, int x, int y, int z, const 
     const float px = (float)x, py = (float)y, pz = (float)z;
     if (P.k > 0) {
         float amin;
-        if (!blend_warp_fast<KMAX>(P.node_rec, ids, P.k, px, py, pz, pw, &amin)) return CLS_UNCERTAIN;
+        const RecGlobal rec = {P.node_rec};
+        if (!blend_warp_fast<KMAX>(rec, ids, P.k, px, py, pz, pw, &amin)) return CLS_UNCERTAIN;
         e = pos_err_bound(P.coord_mag, amin);
     } else {
         pw[0] = px; pw[1] = py; pw[2] = pz;

@@ -18,6 +18,33 @@ using namespace dfb;
 
 namespace {
 
+// Volume data (v, w, kNN ids) is touched once per frame: streaming loads / stores (evict-first) keep the L1 / L2 lines for what
+// IS re-used -- node records and depth pixels.  -DDFB_STREAM_HINTS=0 builds the plain variant (A/B in profiles/).
+#ifndef DFB_STREAM_HINTS
+#define DFB_STREAM_HINTS 1
+#endif
+__device__ __forceinline__ float4 ld_stream(const float* p) {
+#if DFB_STREAM_HINTS
+    return __ldcs(reinterpret_cast<const float4*>(p));
+#else
+    return *reinterpret_cast<const float4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_stream(float* p, float4 v) {
+#if DFB_STREAM_HINTS
+    __stcs(reinterpret_cast<float4*>(p), v);
+#else
+    *reinterpret_cast<float4*>(p) = v;
+#endif
+}
+__device__ __forceinline__ uint4 ld_ids(const uint4* p) {
+#if DFB_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return __ldg(p);
+#endif
+}
+
 template <int KMAX>
 __device__ __forceinline__ void load_ids(const uint16_t* knn, size_t i, int k, uint16_t* ids) {
     if (KMAX == 4) {
@@ -426,8 +453,8 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
     const size_t i = ((size_t)xs * P.ry + y) * P.rz + z;
     if (vec) {
         if (m) {
-            float4 v = *reinterpret_cast<const float4*>(P.tsdf + i);
-            float4 w = *reinterpret_cast<const float4*>(P.weight + i);
+            float4 v = ld_stream(P.tsdf + i);
+            float4 w = ld_stream(P.weight + i);
             for (int vi = 0; vi < P.n_views; ++vi)
                 if (m & (1 << vi)) {
                     clamp_update(v.x, w.x, P.tdist_f, P.wmax_f, sc);
@@ -435,8 +462,8 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
                     clamp_update(v.z, w.z, P.tdist_f, P.wmax_f, sc);
                     clamp_update(v.w, w.w, P.tdist_f, P.wmax_f, sc);
                 }
-            *reinterpret_cast<float4*>(P.tsdf + i) = v;
-            *reinterpret_cast<float4*>(P.weight + i) = w;
+            st_stream(P.tsdf + i, v);
+            st_stream(P.weight + i, w);
         }
         if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i) = make_uchar4(m, m, m, m);
         if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i) = make_uchar4(fr, fr, fr, fr);
@@ -457,9 +484,9 @@ __device__ __forceinline__ void stream_brick(const ProjParams& P, int nb, int nb
 
 // MIXED bricks: the per-voxel fast tier (classify, clamped update, defer the rest to the exact pass).
 // Edge bricks (cut by the volume boundary, or rz not a multiple of 4): one guarded voxel at a time.
-template <int KMAX, bool EXACTK, bool ONEVIEW>
+template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
 __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc, int views, int m0,
-                                                 int f0) {
+                                                 int f0, const Rec rec) {
     const bool want_masks = P.mask_out != nullptr || P.frustum_out != nullptr;
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const bool row_in = xs < P.x1 - P.x0 && y < P.ry;
@@ -471,7 +498,7 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
         if (in) {
             uint16_t ids[KMAX];
             if (!P.rigid) load_ids<KMAX>(P.knn, i, EXACTK ? KMAX : P.k, ids);
-            cls = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
+            cls = voxel_projective_classify_rec<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0, rec);
         }
         push_uncertain(in && cls == CLS_UNCERTAIN, (uint32_t)i, P.list, P.capacity, P.counters, P.overflow_bits);
         if (!in || cls == CLS_UNCERTAIN) continue;
@@ -492,18 +519,18 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
 // Interior bricks: the thread's four z-consecutive voxels move as one float4 of v, one of w and (k = 4 / 8) two / four
 // 16-byte kNN loads, all issued before the arithmetic; the four classifications are independent instruction streams
 // for the scheduler, and the warp reserves its work-list slots with one atomic.
-template <int KMAX, bool EXACTK, bool ONEVIEW>
+template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
 __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc, int views, int m0,
-                                                 int f0) {
+                                                 int f0, const Rec rec) {
     const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
     const size_t i0 = ((size_t)xs * P.ry + y) * P.rz + z0;
-    const float4 v4 = *reinterpret_cast<const float4*>(P.tsdf + i0);
-    const float4 w4 = *reinterpret_cast<const float4*>(P.weight + i0);
+    const float4 v4 = ld_stream(P.tsdf + i0);
+    const float4 w4 = ld_stream(P.weight + i0);
     uint16_t ids[4][KMAX];
     if (!P.rigid) {
         if (EXACTK && KMAX == 4) {
             const uint4* src = reinterpret_cast<const uint4*>(P.knn + i0 * 4);
-            const uint4 a = __ldg(src), b = __ldg(src + 1);
+            const uint4 a = ld_ids(src), b = ld_ids(src + 1);
             const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -520,7 +547,7 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         m[q] = 0; f[q] = 0;
-        cls[q] = voxel_projective_classify<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q], views, m0, f0);
+        cls[q] = voxel_projective_classify_rec<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q], views, m0, f0, rec);
     }
     // work list: one reservation per warp for the four voxels of every lane.  (Measured and dropped: CTA-level
     // aggregation through shared memory, and prefetch.global.L2 of the next brick's v / w / kNN lines -- neither the
@@ -561,26 +588,149 @@ __device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, i
         }
     }
     if (changed) {   // deferred voxels get their old value back; the exact pass runs after this kernel
-        *reinterpret_cast<float4*>(P.tsdf + i0) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(P.weight + i0) = make_float4(w[0], w[1], w[2], w[3]);
+        st_stream(P.tsdf + i0, make_float4(v[0], v[1], v[2], v[3]));
+        st_stream(P.weight + i0, make_float4(w[0], w[1], w[2], w[3]));
     }
     if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i0) = make_uchar4(m[0], m[1], m[2], m[3]);
     if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i0) = make_uchar4(f[0], f[1], f[2], f[3]);
 }
 
-template <int KMAX, bool EXACTK, bool ONEVIEW>
-__device__ __forceinline__ void mixed_brick(const ProjParams& P, int nb, int nby, int nbz, const uint8_t* cls, uint32_t entry, int dx, int dy, int dz,
-                                            float sc) {
+// Scratch of one 128-thread group working on one MIXED brick (shared memory).
+struct GroupScratch {
+    uint32_t* res;    // [512] per voxel of the brick: clamp bits | frustum bits << 8 | deferred << 16
+    uint16_t* open;   // [512] voxels (local index = row * 32 + z) left open by the quad pre-test
+    int* n_open;
+    int bar;          // named barrier of the group
+};
+__device__ __forceinline__ void group_sync(int bar) { asm volatile("bar.sync %0, 128;" ::"r"(bar) : "memory"); }
+
+// Interior MIXED bricks, three phases (dfb_brick.h "quads"):
+//  1. every thread runs the quad pre-test on its four z-consecutive voxels (the region's reference map + deviation bound, one or two
+//     depth pixels): settled (SKIP / CLAMP), certainly inside the band (straight to the exact pass' work list), or open;
+//  2. the open voxels, compacted into a list in shared memory, go through the pointwise DQB tier with all four warps busy;
+//  3. the owner of each quad folds the results into (v, w) -- which are only loaded when a voxel of the quad is actually updated.
+template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
+__device__ __forceinline__ void mixed_brick_quads(const ProjParams& P, const float* rr, int bxs, int by, int bz, int t128, float sc, int views, int m0,
+                                                  int f0, const Rec rec, const GroupScratch& S) {
+    int dx, dy, dz;
+    brick_lane(t128, dx, dy, dz);
+    const int lane = threadIdx.x & 31;
+    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
+    const size_t i0 = ((size_t)xs * P.ry + y) * P.rz + z0;
+    if (t128 == 0) *S.n_open = 0;
+    group_sync(S.bar);
+    // ---- phase 1
+    int m = 0, f = 0;
+    const int qs = quad_pretest(P, rr, xs + P.x0, y, z0, 4, ONEVIEW ? 1 : views, m0, f0, &m, &f);
+    {
+        const unsigned bo = __ballot_sync(0xffffffffu, qs == QUAD_OPEN), bb = __ballot_sync(0xffffffffu, qs == QUAD_BAND);
+        if (bo) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(S.n_open, 4 * __popc(bo));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (qs == QUAD_OPEN) {
+                const int pos = base + 4 * __popc(bo & ((1u << lane) - 1u));
+                const int local = (t128 >> 3) * 32 + dz;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) S.open[pos + q] = (uint16_t)(local + q);
+            }
+        }
+        if (bb) {   // certainly inside the band: deferred without a look at the nodes
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(P.counters, 4u * (uint32_t)__popc(bb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (qs == QUAD_BAND) {
+                const uint32_t pos = base + 4u * (uint32_t)__popc(bb & ((1u << lane) - 1u));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) defer_voxel(pos + q, (uint32_t)(i0 + q), P.list, P.capacity, P.overflow_bits);
+            }
+        }
+    }
+    group_sync(S.bar);
+    // ---- phase 2
+    const int n_open = *S.n_open;
+    if (t128 == 0 && n_open) atomicAdd(P.counters + 4, (uint32_t)n_open);   // statistics: voxels that reach the pointwise DQB tier
+    for (int e0 = 0; e0 < n_open; e0 += 128) {
+        const int e = e0 + t128;
+        const bool act = e < n_open;
+        int cls = CLS_SKIP, mv = 0, fv = 0;
+        uint32_t iv = 0;
+        int local = 0;
+        if (act) {
+            local = S.open[e];
+            const int row = local >> 5, zl = local & 31;
+            const int vx = bxs * BRICK_X + (row >> 2), vy = by * BRICK_Y + (row & 3), vz = bz * BRICK_Z + zl;
+            iv = (uint32_t)(((size_t)vx * P.ry + vy) * P.rz + vz);
+            uint16_t ids[KMAX];
+            load_ids<KMAX>(P.knn, iv, EXACTK ? KMAX : P.k, ids);
+            cls = voxel_projective_classify_rec<KMAX, EXACTK, ONEVIEW>(P, vx + P.x0, vy, vz, ids, &mv, &fv, views, m0, f0, rec);
+        }
+        push_uncertain(act && cls == CLS_UNCERTAIN, iv, P.list, P.capacity, P.counters, P.overflow_bits);
+        if (act) S.res[local] = cls == CLS_UNCERTAIN ? (1u << 16) : ((uint32_t)mv | ((uint32_t)fv << 8));
+    }
+    group_sync(S.bar);
+    // ---- phase 3
+    int mq[4], fq[4];
+    if (qs == QUAD_SETTLED) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { mq[q] = m; fq[q] = f; }
+    } else if (qs == QUAD_BAND) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { mq[q] = 0; fq[q] = 0; }
+    } else {
+        const int local = (t128 >> 3) * 32 + dz;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t r = S.res[local + q];
+            mq[q] = (r >> 16) ? 0 : (int)(r & 0xffu);
+            fq[q] = (r >> 16) ? 0 : (int)((r >> 8) & 0xffu);
+        }
+    }
+    if (mq[0] | mq[1] | mq[2] | mq[3]) {   // deferred voxels keep their value; the exact pass runs after this kernel
+        const float4 v4 = ld_stream(P.tsdf + i0), w4 = ld_stream(P.weight + i0);
+        float v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (ONEVIEW) {
+                if (mq[q]) clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
+            } else {
+                for (int vi = 0; vi < P.n_views; ++vi)
+                    if (mq[q] & (1 << vi)) clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
+            }
+        }
+        st_stream(P.tsdf + i0, make_float4(v[0], v[1], v[2], v[3]));
+        st_stream(P.weight + i0, make_float4(w[0], w[1], w[2], w[3]));
+    }
+    if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i0) = make_uchar4(mq[0], mq[1], mq[2], mq[3]);
+    if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i0) = make_uchar4(fq[0], fq[1], fq[2], fq[3]);
+}
+
+// region record of brick (bxs, by, bz) when it carries a valid deviation bound, else nullptr
+__device__ __forceinline__ const float* brick_region_rec(const ProjParams& P, const float* region_rec, int bxs, int by, int bz) {
+    if (!region_rec || P.rigid) return nullptr;
+    const int nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
+    const float* rr = region_rec + (((size_t)(bxs * BRICK_X / REGION_X) * nry + by * BRICK_Y / REGION_Y) * nrz + bz * BRICK_Z / REGION_Z) * REGION_REC_FLOATS;
+    return rr[15] > 0.5f ? rr : nullptr;
+}
+
+// MIXED brick of the production pass: quads when the brick is interior and its region has a deviation bound
+template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
+__device__ __forceinline__ void mixed_brick_v2(const ProjParams& P, const float* region_rec, int nb, int nby, int nbz, const uint8_t* cls, uint32_t entry,
+                                               int t128, float sc, const Rec rec, const GroupScratch& S) {
     int bxs, by, bz;
     brick_unpack(entry, bxs, by, bz);
     int views = 0xff, m0 = 0, f0 = 0;
-    if (!ONEVIEW) {   // with several views the brick's box test has usually settled most of them
+    if (!ONEVIEW) {
         const int b = (bxs * nby + by) * nbz + bz;
         f0 = cls[nb + b]; views = cls[2 * nb + b]; m0 = cls[3 * nb + b];
     }
     const bool full = (P.rz & 3) == 0 && (bxs + 1) * BRICK_X <= P.x1 - P.x0 && (by + 1) * BRICK_Y <= P.ry && (bz + 1) * BRICK_Z <= P.rz;
-    if (full) mixed_brick_full<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0);
-    else mixed_brick_edge<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0);
+    const float* rr = full ? brick_region_rec(P, region_rec, bxs, by, bz) : nullptr;
+    int dx, dy, dz;
+    brick_lane(t128, dx, dy, dz);
+    if (rr) mixed_brick_quads<KMAX, EXACTK, ONEVIEW>(P, rr, bxs, by, bz, t128, sc, views, m0, f0, rec, S);
+    else if (full) mixed_brick_full<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0, rec);
+    else mixed_brick_edge<KMAX, EXACTK, ONEVIEW>(P, bxs, by, bz, dx, dy, dz, sc, views, m0, f0, rec);
 }
 
 __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
@@ -594,11 +744,15 @@ __global__ void __launch_bounds__(128) brick_stream_kernel(const __grid_constant
 
 template <int KMAX, bool EXACTK, bool ONEVIEW>
 __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
-                                                          const uint8_t* cls, const uint32_t* list) {
+                                                          const uint8_t* cls, const uint32_t* list, const float* region_rec) {
+    __shared__ uint32_t s_res[512];
+    __shared__ uint16_t s_open[512];
+    __shared__ int s_n;
+    const GroupScratch S = {s_res, s_open, &s_n, 1};
     const uint32_t count = P.counters[3];
-    int dx, dy, dz;
-    brick_lane(threadIdx.x, dx, dy, dz);
-    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, nbx * nby * nbz, nby, nbz, cls, list[t], dx, dy, dz, (float)P.scale);
+    const RecGlobal rec = {P.node_rec};
+    for (uint32_t t = blockIdx.x; t < count; t += gridDim.x)
+        mixed_brick_v2<KMAX, EXACTK, ONEVIEW>(P, region_rec, nbx * nby * nbz, nby, nbz, cls, list[t], threadIdx.x, (float)P.scale, rec, S);
 }
 
 // Production pass: MIXED and CLAMP bricks in ONE persistent launch.  Every CTA alternates between one MIXED brick
@@ -611,7 +765,12 @@ __global__ void __launch_bounds__(128) brick_mixed_kernel(const __grid_constant_
 #define DFB_UPDATE_BOUNDS __launch_bounds__(128, DFB_UPDATE_MINB)
 template <int KMAX, bool EXACTK, bool ONEVIEW>
 __global__ void DFB_UPDATE_BOUNDS brick_update_kernel(const __grid_constant__ ProjParams P, int nbx, int nby, int nbz,
-                                                           const uint8_t* cls, const uint32_t* stream_list, const uint32_t* mixed_list) {
+                                                           const uint8_t* cls, const uint32_t* stream_list, const uint32_t* mixed_list,
+                                                           const float* region_rec) {
+    __shared__ uint32_t s_res[512];
+    __shared__ uint16_t s_open[512];
+    __shared__ int s_n;
+    const GroupScratch S = {s_res, s_open, &s_n, 1};
     const uint32_t cnt_s = P.counters[2], cnt_m = P.counters[3];
     const uint32_t n_t = cnt_m > gridDim.x ? cnt_m : gridDim.x;
     const uint32_t share = (cnt_s + n_t - 1) / n_t;
@@ -621,7 +780,67 @@ __global__ void DFB_UPDATE_BOUNDS brick_update_kernel(const __grid_constant__ Pr
     const float sc = (float)P.scale;
     const bool vec = (P.rz & 3) == 0;
     for (uint32_t t = blockIdx.x; t < n_t; t += gridDim.x) {
-        if (t < cnt_m) mixed_brick<KMAX, EXACTK, ONEVIEW>(P, nb, nby, nbz, cls, mixed_list[t], dx, dy, dz, sc);
+        if (t < cnt_m) mixed_brick_v2<KMAX, EXACTK, ONEVIEW>(P, region_rec, nb, nby, nbz, cls, mixed_list[t], threadIdx.x, sc, RecGlobal{P.node_rec}, S);
+        const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
+        for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
+    }
+}
+
+// The same pass with the WHOLE node table resident in shared memory (north_star: "node parameters ... staged in shared memory or
+// via TMA"): one persistent CTA of 1024 threads per SM copies the packed records (48 B per node; 191 KB at 3974 nodes) with
+// cp.async.bulk (the TMA unit, one mbarrier) and its eight 128-thread groups then work through the brick lists exactly like the
+// CTAs of brick_update_kernel.  Every node gather of the per-voxel tier becomes an LDS: ncu showed the global variant waiting on
+// the L1-miss share of those gathers (long-scoreboard stalls = 52 % of all samples, L1 hit rate 74 %).
+constexpr int UPDATE_SMEM_THREADS = 1024, UPDATE_SMEM_GROUPS = UPDATE_SMEM_THREADS / 128;
+constexpr size_t UPDATE_SMEM_MAX_BYTES = 220 * 1024;   // of the 227 KB a CTA may own on sm_100
+constexpr size_t UPDATE_SCRATCH_BYTES = 3200;          // per group: res 2048 + open list 1024 + counter (128-byte multiple)
+template <int KMAX, bool EXACTK, bool ONEVIEW>
+__global__ void __launch_bounds__(UPDATE_SMEM_THREADS, 1) brick_update_smem_kernel(const __grid_constant__ ProjParams P, int n_nodes, int nbx, int nby,
+                                                                                    int nbz, const uint8_t* cls, const uint32_t* stream_list,
+                                                                                    const uint32_t* mixed_list, const float* region_rec) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(smem_raw);
+    // behind the table: the quad scratch of the eight groups
+    const int grp = threadIdx.x >> 7;
+    unsigned char* scratch = smem_raw + (((size_t)n_nodes * DFB_NODE_REC_FLOATS * sizeof(float) + 127) & ~(size_t)127) + (size_t)grp * UPDATE_SCRATCH_BYTES;
+    const GroupScratch S = {reinterpret_cast<uint32_t*>(scratch), reinterpret_cast<uint16_t*>(scratch + 2048), reinterpret_cast<int*>(scratch + 3072), 1 + grp};
+    __shared__ __align__(8) unsigned long long bar;
+    const uint32_t bytes = (uint32_t)n_nodes * (uint32_t)(DFB_NODE_REC_FLOATS * sizeof(float));
+    const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        const char* src = reinterpret_cast<const char*>(P.node_rec);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rec);
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+            const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+                         "l"(src + off), "r"(n), "r"(bar_a)
+                         : "memory");
+        }
+    }
+    const uint32_t cnt_s = P.counters[2], cnt_m = P.counters[3];
+    const uint32_t n_groups = gridDim.x * UPDATE_SMEM_GROUPS;
+    const uint32_t n_t = cnt_m > n_groups ? cnt_m : n_groups;
+    const uint32_t share = (cnt_s + n_t - 1) / n_t;
+    const int nb = nbx * nby * nbz;
+    int dx, dy, dz;
+    brick_lane(threadIdx.x & 127, dx, dy, dz);
+    const float sc = (float)P.scale;
+    const bool vec = (P.rz & 3) == 0;
+    const uint32_t rec_a = (uint32_t)__cvta_generic_to_shared(s_rec);
+    {   // wait for the table (phase 0 of the barrier)
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_a) : "memory");
+    }
+    // groups of one CTA take consecutive list entries in turn (neighbouring bricks: the same nodes, the same depth pixels)
+    for (uint32_t t = blockIdx.x * UPDATE_SMEM_GROUPS + (threadIdx.x >> 7); t < n_t; t += n_groups) {
+        if (t < cnt_m) mixed_brick_v2<KMAX, EXACTK, ONEVIEW>(P, region_rec, nb, nby, nbz, cls, mixed_list[t], threadIdx.x & 127, sc, RecShared{rec_a}, S);
         const uint32_t s1 = (t + 1) * share < cnt_s ? (t + 1) * share : cnt_s;
         for (uint32_t s = t * share; s < s1; ++s) stream_brick(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
     }
@@ -876,6 +1095,7 @@ int exact_blocks(size_t nvox) {
 }
 
 struct BrickArgs {
+    int n_nodes;
     const uint16_t* nodes;
     const uint8_t* count;
     const uint32_t* pairs;
@@ -893,6 +1113,10 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
     const bool do_stream = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_STREAM || mode == DFB_MODE_BRICK_UPDATE;
     const bool do_mixed = mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_MIXED || mode == DFB_MODE_BRICK_UPDATE;
     if (mode >= DFB_MODE_BRICK_CLASSIFY) DFB_REQUIRE(bricks, "brick modes need the brick workspace / candidate sets");
+    // Overflow marks are consumed (and cleared) by the exact pass of the SAME call.  The profiling modes that stop before it must
+    // not leave marks behind -- a later hybrid call would send those voxels through the exact tier on top of their fast-tier
+    // update -- so they run without the bitmap (their deferred voxels beyond the list capacity are simply dropped).
+    if (mode != DFB_MODE_HYBRID && mode != DFB_MODE_EXACT) P.overflow_bits = nullptr;
     if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_EXACT || mode == DFB_MODE_FAST_ONLY || mode == DFB_MODE_BRICK_CLASSIFY)
         DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
@@ -940,13 +1164,45 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
         else if (P.k <= 4) { if (one) KERNEL<4, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<4, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
         else { if (one) KERNEL<8, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<8, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
     } while (0)
-                DFB_BRICK_DISPATCH(brick_update_kernel, P, nbx, nby, nbz, B.cls, stream_list, mixed_list);
-                DFB_LAUNCH_CHECK("brick_update_kernel");
+                static int use_smem = -1;
+                if (use_smem < 0) { const char* e = getenv("DFB_UPDATE_SMEM"); use_smem = e ? atoi(e) : 1; }
+                static int use_quads = -1;
+                if (use_quads < 0) { const char* e = getenv("DFB_QUADS"); use_quads = e ? atoi(e) : 0; }
+                const float* qrec = use_quads ? rrec : nullptr;
+                const size_t rec_bytes = (((size_t)B.n_nodes * DFB_NODE_REC_FLOATS * sizeof(float) + 127) & ~(size_t)127) + UPDATE_SMEM_GROUPS * UPDATE_SCRATCH_BYTES;
+                if (use_smem && !P.rigid && B.n_nodes > 0 && rec_bytes <= UPDATE_SMEM_MAX_BYTES) {
+                    // one persistent CTA per SM, the node table in its shared memory
+                    static int n_sm = 0;
+                    if (n_sm == 0) {
+                        int dev = 0;
+                        DFB_CUDA(cudaGetDevice(&dev));
+                        DFB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+                    }
+                    const int sgrid = nb < n_sm * UPDATE_SMEM_GROUPS ? (nb + UPDATE_SMEM_GROUPS - 1) / UPDATE_SMEM_GROUPS : n_sm;
+#define DFB_SMEM_LAUNCH(K_, E_, O_)                                                                                              \
+    do {                                                                                                                         \
+        DFB_CUDA(cudaFuncSetAttribute(brick_update_smem_kernel<K_, E_, O_>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                      (int)UPDATE_SMEM_MAX_BYTES));                                                              \
+        brick_update_smem_kernel<K_, E_, O_><<<sgrid, UPDATE_SMEM_THREADS, rec_bytes, s>>>(P, B.n_nodes, nbx, nby, nbz, B.cls,   \
+                                                                                          stream_list, mixed_list, qrec);      \
+    } while (0)
+                    const bool one = P.n_views == 1;
+                    if (P.k == 4) { if (one) DFB_SMEM_LAUNCH(4, true, true); else DFB_SMEM_LAUNCH(4, true, false); }
+                    else if (P.k == 8) { if (one) DFB_SMEM_LAUNCH(8, true, true); else DFB_SMEM_LAUNCH(8, true, false); }
+                    else if (P.k < 4) { if (one) DFB_SMEM_LAUNCH(4, false, true); else DFB_SMEM_LAUNCH(4, false, false); }
+                    else { if (one) DFB_SMEM_LAUNCH(8, false, true); else DFB_SMEM_LAUNCH(8, false, false); }
+                    DFB_LAUNCH_CHECK("brick_update_smem_kernel");
+                } else {
+                    DFB_BRICK_DISPATCH(brick_update_kernel, P, nbx, nby, nbz, B.cls, stream_list, mixed_list, qrec);
+                    DFB_LAUNCH_CHECK("brick_update_kernel");
+                }
             } else if (do_stream) {
                 brick_stream_kernel<<<grid, 128, 0, s>>>(P, nbx, nby, nbz, B.cls, stream_list);
                 DFB_LAUNCH_CHECK("brick_stream_kernel");
             } else if (do_mixed) {
-                DFB_BRICK_DISPATCH(brick_mixed_kernel, P, nbx, nby, nbz, B.cls, mixed_list);
+                static int use_quads_m = -1;
+                if (use_quads_m < 0) { const char* e = getenv("DFB_QUADS"); use_quads_m = e ? atoi(e) : 0; }
+                DFB_BRICK_DISPATCH(brick_mixed_kernel, P, nbx, nby, nbz, B.cls, mixed_list, use_quads_m ? rrec : nullptr);
                 DFB_LAUNCH_CHECK("brick_mixed_kernel");
             }
         } else {
@@ -986,7 +1242,7 @@ extern "C" int dfb_tsdf_update_projective(const dfb_volume* vol, const dfb_warpf
                                           uint8_t* mask_out, uint8_t* frustum_out, dfb_stream_t stream) {
     ProjParams P;
     if (int r = build_projective(P, vol, wf, views, tdist, wmax, mode, ws, mask_out, frustum_out)) return r;
-    const BrickArgs B = {wf->brick_nodes, wf->brick_count, wf->brick_pairs, wf->region_nodes, wf->region_count, wf->region_pairs, wf->region_rec,
+    const BrickArgs B = {wf->n_nodes, wf->brick_nodes, wf->brick_count, wf->brick_pairs, wf->region_nodes, wf->region_count, wf->region_pairs, wf->region_rec,
                          ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
@@ -1000,7 +1256,7 @@ extern "C" int dfb_fuse_depth_rigid(const dfb_volume* vol, int tsdf_res, const f
     if (int r = build_rigid(P, vol, tsdf_res, depth, rows, cols, lw34, K, Kinv, scale, center, tdist, wmax, mode, ws,
                             mask_out, frustum_out))
         return r;
-    const BrickArgs B = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws->brick_cls, ws->brick_lists};
+    const BrickArgs B = {0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ws->brick_cls, ws->brick_lists};
     return run_projective(P, mode, (cudaStream_t)stream, vol, B);
 }
 
@@ -1010,6 +1266,7 @@ extern "C" int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield
     VolParams P;
     if (int r = build_volume(P, vol, wf, curr, cx, cy, cz, tdist, wmax, mode, ws, mask_out)) return r;
     cudaStream_t s = (cudaStream_t)stream;
+    if (mode != DFB_MODE_HYBRID && mode != DFB_MODE_EXACT) P.overflow_bits = nullptr;   // see run_projective
     if (mode != DFB_MODE_LIST_ONLY) DFB_CUDA(cudaMemsetAsync(P.counters, 0, 8 * sizeof(uint32_t), s));
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     if (mode == DFB_MODE_HYBRID || mode == DFB_MODE_FAST_ONLY) {

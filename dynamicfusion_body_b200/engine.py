@@ -65,7 +65,7 @@ class Workspace:
     def _decode(self, c):
         c = c.astype(np.int64) & 0xffffffff
         return {"deferred": int(c[0]), "exact_processed": int(c[1]), "bricks_streamed": int(c[2]), "bricks_mixed": int(c[3]),
-                "bricks": self.n_bricks}
+                "bricks": self.n_bricks, "dqb_voxels": int(c[4])}
 
     def stats(self):
         return self._decode(self.counters.cpu().numpy())

@@ -160,8 +160,6 @@ class _FusionBase:
     def warp(self, pos, dqs=None, locations=None, normal=None, dmax=None, m_lw=None):
         """Fusion.warp (core/fusion.py:502-520) for one point or an (M,3) batch.  `dqs` given explicitly
         must be the current node transforms of `locations` (the reference always passes those)."""
-        if dmax is not None:
-            raise NotImplementedError("dmax weighting is an unused option of the reference (core/fusion.py:539-541)")
         p = np.asarray(pos, dtype=np.float32)
         single = p.ndim == 1
         p2 = p.reshape(-1, 3)
@@ -172,8 +170,10 @@ class _FusionBase:
             loc = np.asarray(locations, dtype=np.int32).reshape(len(p2), -1)
         wf = self._wf
         if dqs is not None:
-            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(len(p2), -1, 8))
+            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(len(p2), -1, 8), dmax)
             loc = np.arange(loc.size, dtype=np.int32).reshape(loc.shape)
+        elif dmax is not None:
+            wf = self._wf_with_dmax(dmax)
         n2 = None if normal is None else np.asarray(normal, dtype=np.float32).reshape(-1, 3)
         out = engine.warp_points(wf, m_lw, p2, n2, idx=loc, k=loc.shape[1])
         if normal is None:
@@ -182,25 +182,38 @@ class _FusionBase:
         r, rn = out[0].cpu().numpy(), out[1].cpu().numpy()
         return (r[0], rn[0]) if single else (r, rn)
 
-    def _wf_with_dqs(self, loc, dqs):
+    @staticmethod
+    def _dmax_w(dmax, n):
+        """`exp(-(|pos - dg_v| / dmax)^2)` (core/fusion.py:539-541) is the default weight `exp(-(|pos - dg_v| / (2 dg_w))^2)` with
+        2 dg_w replaced by dmax: in the reference both divisors are python floats, i.e. weak operands rounded to float32, and
+        halving / doubling a float32 is exact -- so node weights of float32(dmax) / 2 reproduce the dmax variant bit for bit."""
+        return np.full(n, np.float32(dmax) / np.float32(2.0), dtype=np.float32)
+
+    def _wf_with_dqs(self, loc, dqs, dmax=None):
         """Temporary warp field whose node j is (pos/w of node loc.flat[j], dq = dqs.flat[j]) -- lets
         `warp`/`dq_blend` honour explicitly passed transforms like the reference does."""
         pos = self._wf.node_pos.cpu().numpy()[loc.reshape(-1)]
-        w = self._wf.node_w.cpu().numpy()[loc.reshape(-1)]
+        w = self._wf.node_w.cpu().numpy()[loc.reshape(-1)] if dmax is None else self._dmax_w(dmax, loc.size)
         wf = engine.DeviceWarpField(loc.shape[1], self._device)
         wf.set_nodes(pos, dqs.reshape(-1, 8), w)
         return wf
 
+    def _wf_with_dmax(self, dmax):
+        """The current graph with every node weight replaced by dmax / 2 (see _dmax_w)."""
+        wf = engine.DeviceWarpField(self._wf.k, self._device)
+        wf.set_nodes(self._wf.node_pos, self._wf.node_dq, self._dmax_w(dmax, self._wf.n_nodes))
+        return wf
+
     def dq_blend(self, pos, dqs=None, locations=None, dmax=None):
         """Fusion.dq_blend (core/fusion.py:527-551): blended, 8-norm-normalised dual quaternion (Q2)."""
-        if dmax is not None:
-            raise NotImplementedError("dmax weighting is an unused option of the reference")
         p = np.asarray(pos, dtype=np.float32).reshape(1, 3)
         loc = self._lookup(p, self._knn) if locations is None else np.asarray(locations, dtype=np.int32).reshape(1, -1)
         wf = self._wf
         if dqs is not None:
-            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(1, -1, 8))
+            wf = self._wf_with_dqs(loc, np.asarray(dqs, dtype=np.float32).reshape(1, -1, 8), dmax)
             loc = np.arange(loc.size, dtype=np.int32).reshape(loc.shape)
+        elif dmax is not None:
+            wf = self._wf_with_dmax(dmax)
         return _gn.dq_blend_points(wf, p, loc)[0]
 
     def write_warp_field(self, path, filename):
@@ -235,17 +248,17 @@ class _FusionBase:
         if self._verbose:
             print("Marching Cubes result: number of extracted vertices is %d" % (len(self._vertices)))
 
-    def _device_surface(self, step_size):
-        """Surface of the resident canonical volume.  A rank that holds an x-slab of a volume sharded over the process group
+    def _device_surface(self, step_size, level=None):
+        """Surface of the resident canonical volume (level None = 0.5 * (min + max) like skimage's default).  A rank that holds an x-slab of a volume sharded over the process group
          extracts its share with three halo planes per boundary and every rank receives the whole mesh, identical to the
         single-GPU one (dist.extract_surface_slab); a lone slab is extracted as is, in whole-grid coordinates."""
         vol = self._vol
         rx = int(vol.res[0])
         if ddist.is_dist() and (vol.x0 > 0 or vol.x1 < rx):
-            return ddist.allgather_mesh(ddist.extract_surface_slab(vol.tsdf, vol.x0, vol.x1, rx, step_size))
+            return ddist.allgather_mesh(ddist.extract_surface_slab(vol.tsdf, vol.x0, vol.x1, rx, step_size, level=level))
         if vol.x0 % step_size == 0:
-            return engine.marching_cubes(vol.tsdf, step_size, x_origin=vol.x0 // step_size)
-        v, f, n, val = engine.marching_cubes(vol.tsdf, step_size)
+            return engine.marching_cubes(vol.tsdf, step_size, level, x_origin=vol.x0 // step_size)
+        v, f, n, val = engine.marching_cubes(vol.tsdf, step_size, level)
         v[:, 0] += np.float32(vol.x0)
         return v, f, n, val
 
@@ -261,13 +274,20 @@ class _FusionBase:
     def write_canonical_mesh(self, path, filename):
         """core/fusion.py:577-586 / core/fusion_dm.py:339-354: extract the canonical surface (step size 1) and write it as OBJ; FusionDM maps vertices and normals to world coordinates with `_IND` first."""
         from . import io
+        ind = getattr(self, "_IND", None)
+        # FusionDM extracts the ZERO level set (`level=0`, core/fusion_dm.py:341-342); Fusion passes no level (core/fusion.py:579),
+        # i.e. skimage's default 0.5 * (min + max)
+        level = 0.0 if ind is not None else None
         if self.surface_extractor == "device":
-            verts, faces, normals, _ = self._device_surface(1)
+            verts, faces, normals, _ = self._device_surface(1, level)
         else:
-            verts, faces, normals, _ = self.marching_cubes(self._tsdf, step_size=1)
+            ext = self.surface_extractor
+            try:
+                verts, faces, normals, _ = ext(_as_np(self._tsdf), 1, level) if level is not None else ext(_as_np(self._tsdf), 1)
+            except TypeError:
+                verts, faces, normals, _ = ext(_as_np(self._tsdf), 1)
             if self._vol.x0:
                 verts = np.array(verts); verts[:, 0] += self._vol.x0
-        ind = getattr(self, "_IND", None)
         if ind is not None:
             rot, trans = ind[:3, :3], ind[:3, 3]
             verts = np.asarray(verts, dtype=np.float64) @ rot.T + trans
@@ -493,7 +513,7 @@ class Fusion(_FusionBase):
         prob = self._problem()
         if precompute_lw:
             self._lw = prob.solve_lw(np.asarray(self._lw, dtype=np.float64), max_iter=opts.get("lw_iterations", 20), verbose=self._verbose)
-            if method == 'clpts' and correspondences is None:
+            if method == 'clpts':                                   # unconditional, as in the reference (core/fusion.py:363-364)
                 self.setupCorrespondences(self._curr_tsdf, method='clpts')
                 prob = self._problem()
         rw = regularization_weight
@@ -504,9 +524,12 @@ class Fusion(_FusionBase):
             x0 = self._wf.node_dq.double().reshape(-1)
             res = prob.gauss_newton(x0, self._lw, rw, max_iter=gn_iterations, huber=opts.get("huber", True),
                                     f_scale=opts.get("f_scale", 1.0), verbose=self._verbose, **opts.get("gn", {}))
-            self._wf.set_dq(res.x.reshape(-1, 8).float())        # written back un-normalised (core/fusion.py:400-403)
+            # written back un-normalised (core/fusion.py:400-403); the device node table is float32 (the reference keeps the
+            # float64 `opt_result.x`, which also switches its dtype flow from then on -- stated deviation)
+            self._wf.set_dq(res.x.reshape(-1, 8).float())
             self.last_solve = res
-            reduct_rate = (res.cost0 - res.cost) / res.cost0 if res.cost0 > 0 else 0.0
+            # core/fusion.py:376,405: plain 0.5 |f|^2 before, the optimiser's robust cost after
+            reduct_rate = (res.cost0_l2 - res.cost) / res.cost0_l2 if res.cost0_l2 > 0 else 0.0
             if 0.05 < reduct_rate < 0.9:
                 rw /= 8
             else:
@@ -556,12 +579,19 @@ class FusionDM(_FusionBase):
             return (tsdf, tsdf_w)
         return (out_t, out_w)
 
-    def compute_live_tsdf(self, depths, lws, UseAutoAlignment=False, useICP=False, outputMesh=False):
-        """core/fusion_dm.py:95-178, plain multi-view branch: the volume stays on the device across views."""
+    def marching_cubes(self, tsdf=None, step_size=1):
+        """core/fusion_dm.py:319-331: same as Fusion.marching_cubes but the step size defaults to 1 (the reference's FusionDM also
+        leaves skimage's allow_degenerate at its default True here; the device extractor always drops degenerate triangles)."""
+        return super().marching_cubes(tsdf, step_size)
+
+    def compute_live_tsdf(self, depths, lws, UseAutoAlignment=False, useICP=False, outputMesh=False, *, mesh_path=None):
+        """core/fusion_dm.py:95-178, plain multi-view branch: the volume stays on the device across views.  outputMesh=True
+        saves the volume as `tsdf_temp.npy` and writes the zero level set to `test.obj` (core/fusion_dm.py:174-176) under
+        `mesh_path` (default: $DFB_DATA_PATH or the working directory -- the reference's DATA_PATH is a checkout-relative constant)."""
         if len(depths) != len(lws):
             raise ValueError('length of camera matrix array Ks must equal that of depth maps')
-        if UseAutoAlignment or useICP or outputMesh:
-            raise NotImplementedError("auto-alignment / ICP / mesh output are outside the hot path (SURVEY 2 row 2)")
+        if UseAutoAlignment or useICP:
+            raise NotImplementedError("auto-alignment / ICP are outside the hot path (SURVEY 2 row 2)")
         avg = np.array([-0.03, -0.43, -5.6], dtype='float32')       # core/fusion_dm.py:106-107
         std = 1.3
         scale = 8 * std / self._tsdf_res
@@ -575,7 +605,12 @@ class FusionDM(_FusionBase):
             d = engine._to_dev(depths[idx], torch.float32, self._device)
             engine.fuse_depth_rigid(self._vol, self._tsdf_res, d, lws[idx], self._K, self._Kinv, 12 * std / self._tsdf_res, avg,
                                     self._tdist, 100.0, mode=self._mode)
-        return (self._tsdf, self._tsdfw)
+        tsdf, tsdfw = self._tsdf, self._tsdfw
+        if outputMesh:
+            out_dir = mesh_path if mesh_path is not None else os.environ.get("DFB_DATA_PATH", ".")
+            np.save(os.path.join(out_dir, 'tsdf_temp'), tsdf)
+            self.write_canonical_mesh(out_dir, 'test.obj')
+        return (tsdf, tsdfw)
 
     def updateTSDF(self, curr_tsdf, wmax=100.0):
         """core/fusion_dm.py:300-316: rigid volume->volume fusion with the global dq `_lw`."""

@@ -52,6 +52,7 @@ class GNResult:
     iterations: int
     accepted: int
     history: list            # per iteration dicts (cost, lambda, accepted, pcg_iterations)
+    cost0_l2: float = 0.0    # 0.5 |f(x0)|^2 -- the reference's `cost_before` (core/fusion.py:376)
 
 
 class Problem:
@@ -183,7 +184,8 @@ class Problem:
             return H, g, c
 
         H, g, c = assemble(x)
-        cost = float(c[0].item())
+        c_host = c.tolist()
+        cost, cost0_l2 = float(c_host[0]), float(c_host[1])
         cost0 = cost
         lam = lam0
         hist = []
@@ -213,7 +215,7 @@ class Problem:
             its = torch.cat([h["pcg_iterations"] for h in hist]).cpu().numpy()
             for h, n_it in zip(hist, its):
                 h["pcg_iterations"] = int(n_it)
-        return GNResult(x=x, cost0=cost0, cost=cost, iterations=it, accepted=accepted, history=hist)
+        return GNResult(x=x, cost0=cost0, cost=cost, iterations=it, accepted=accepted, history=hist, cost0_l2=cost0_l2)
 
     # -- rigid fit of the global dq (core/fusion.py:350-362) -----------------------------------------------------------
     def lw_normal_equations(self, lw, huber=False, f_scale=1.0):

@@ -88,7 +88,8 @@ typedef struct dfb_workspace {
     uint32_t capacity;
     uint32_t* counters; /* device [8]; counters[0] = voxels deferred to the exact pass by the last call,
                            counters[1] = voxels the exact pass processed, counters[2] = bricks streamed (CLAMP),
-                           counters[3] = bricks evaluated per voxel (MIXED) */
+                           counters[3] = bricks evaluated per voxel (MIXED), counters[4] = voxels of MIXED bricks the quad
+                           pre-test left to the pointwise DQB tier */
     /* optional (NULL = no brick culling), n_bricks = dfb_brick_count(x1-x0, ry, rz): */
     uint8_t* brick_cls;    /* device [4*n_bricks]: class (0xFF = MIXED), frustum bits, open views, settled CLAMP bits */
     uint32_t* brick_lists; /* device [2*n_bricks] */

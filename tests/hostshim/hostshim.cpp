@@ -84,6 +84,14 @@ static int g_use_regions = 0;
 static float g_region_dmax = 0.f;   // largest deviation bound among valid regions of the last call (diagnostic)
 static float g_region_valid = 0.f;  // fraction of valid regions
 static int g_region_resolved = 0;   // regions classified as a whole in the last call
+static float* g_dev_log = nullptr;
+static long g_dev_n = 0;
+extern "C" void hs_set_dev_log(float* p) { g_dev_log = p; g_dev_n = 0; }
+extern "C" long hs_dev_log_n() { return g_dev_n; }
+static int g_use_quads = 1;
+static long g_quad_settled = 0, g_quad_band = 0, g_quad_open = 0;
+extern "C" void hs_set_quads(int on) { g_use_quads = on; g_quad_settled = g_quad_band = g_quad_open = 0; }
+extern "C" void hs_quad_stats(long* out) { out[0] = g_quad_settled; out[1] = g_quad_band; out[2] = g_quad_open; }
 extern "C" void hs_set_bricks(const uint16_t* nodes, const uint8_t* count, const uint32_t* pairs, uint8_t* cls_vox, int use_regions) {
     g_brick_nodes = nodes; g_brick_count = count; g_brick_pairs = pairs; g_brick_cls_vox = cls_vox; g_use_regions = use_regions;
 }
@@ -154,6 +162,7 @@ static std::vector<float> build_region_records(const ProjParams& P) {
                 }
                 out[15] = region_code(!bad, rc);
                 if (!bad && !rc.mixed) ++g_region_resolved;
+                if (!bad && rc.mixed && g_dev_log) { g_dev_log[g_dev_n++] = dev[0]; g_dev_log[g_dev_n++] = dev[1]; g_dev_log[g_dev_n++] = dev[2]; }
                 if (!bad) { ++nvalid; g_region_dmax = std::max(g_region_dmax, std::max(dev[0], std::max(dev[1], dev[2]))); }
             }
     g_region_valid = (float)nvalid / (float)((size_t)nrx * nry * nrz);
@@ -199,7 +208,20 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                 uint16_t ids[KMAX] = {0};
                 for (int j = 0; j < P.k; ++j) ids[j] = P.knn[i * P.k + j];
                 int m = 0, f = 0, cls = CLS_UNCERTAIN;
-                if (mode == DFB_MODE_HYBRID) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
+                bool pretested = false;
+                if (bricks && rrec && g_use_quads && mode == DFB_MODE_HYBRID) {
+                    // the quad pre-test of the update kernel (dfb_brick.h quad_pretest), on the quad this voxel belongs to
+                    const int nry = (P.ry + REGION_Y - 1) / REGION_Y, nrz = (P.rz + REGION_Z - 1) / REGION_Z;
+                    const float* rr = rrec + (((size_t)(xs / REGION_X) * nry + y / REGION_Y) * nrz + z / REGION_Z) * REGION_REC_FLOATS;
+                    if (rr[15] > 0.5f) {
+                        const int zq = z & ~3, nz = std::min(4, P.rz - zq);
+                        const int qs = quad_pretest(P, rr, xs + P.x0, y, zq, nz, views, m0, f0, &m, &f);
+                        if (qs == QUAD_SETTLED) { cls = m ? CLS_CLAMP : CLS_SKIP; pretested = true; ++g_quad_settled; }
+                        else if (qs == QUAD_BAND) { cls = CLS_UNCERTAIN; m = f = 0; pretested = true; ++g_quad_band; }
+                        else ++g_quad_open;
+                    }
+                }
+                if (mode == DFB_MODE_HYBRID && !pretested) cls = voxel_projective_classify<KMAX>(P, xs + P.x0, y, z, ids, &m, &f, views, m0, f0);
                 if (cls_out) cls_out[i] = (uint8_t)cls;
                 float v = P.tsdf[i], w = P.weight[i];
                 if (cls == CLS_UNCERTAIN) {

@@ -66,10 +66,10 @@ def test_full_size_projective(R, N, k, views):
         res[name] = (vol.tsdf, vol.weight, m, f)
         if mode == 0:
             print("R=%d views=%d" % (R, views), vol.workspace.stats())
-    # the classification tiers never change a decision; clamped updates differ only by fp32-vs-fp64 evaluation of the average
+    # the classification tiers never change a decision, and a clamped update is the same float32 expression in both tiers
     assert torch.equal(res["hybrid"][2], res["exact"][2]) and torch.equal(res["hybrid"][3], res["exact"][3])
     assert torch.equal(res["hybrid"][1], res["exact"][1])
-    assert (res["hybrid"][0] - res["exact"][0]).abs().max().item() <= 1e-6 * sc.tdist * max(1, views)
+    assert torch.equal(res["hybrid"][0], res["exact"][0])
     # untouched voxels are bit-identical to the input (idempotence of SKIP)
     untouched = res["hybrid"][2] == 0
     assert torch.equal(res["hybrid"][0][untouched.view(R, R, R)], t0.view(R, R, R)[untouched.view(R, R, R)])
@@ -89,6 +89,6 @@ def test_full_size_projective(R, N, k, views):
         s = engine.DeviceVolume((R, R, R), x0, x1, tsdf=t0.view(R, R, R)[x0:x1].clone(), weight=w0.view(R, R, R)[x0:x1].clone())
         engine.update_projective(s, wf, sc.lw, depths, sc.K, sc.Kinv, sc.extrinsics, sc.tdist)
         parts.append((s.tsdf, s.weight))
-    # weights identical; values may differ by a few fp32 ulp where the brick grid of a slab resolves a voxel in another tier
+    # bit for bit, whichever tier the brick grid of a slab routes a voxel through
     assert torch.equal(torch.cat([p[1] for p in parts]), res["hybrid"][1])
-    assert (torch.cat([p[0] for p in parts]) - res["hybrid"][0]).abs().max().item() <= 1e-6 * sc.tdist * max(1, views)
+    assert torch.equal(torch.cat([p[0] for p in parts]), res["hybrid"][0])

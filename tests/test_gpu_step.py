@@ -67,7 +67,7 @@ def test_frame_step_graph_equals_direct_calls():
         step.run(step.io(dq_src=stage, counters_host=counters))
         s.synchronize()
         st = step.stats()
-        assert st["captures"] == 3 and st["updates"] == 2, st
+        assert st["captures"] == 3 and st["updates"] == 1, st   # the upload node changed the topology (re-instantiated), the new lw only parameters
     assert torch.equal(vol.weight, vol0.weight)
     assert torch.equal(vol.tsdf, vol0.tsdf)
     # the legacy default stream cannot be captured: the step then issues its launches directly

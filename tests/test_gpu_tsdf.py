@@ -122,8 +122,8 @@ def test_projective_hybrid_equals_exact_bitwise(small_scene):
         out.append((vol.tsdf.cpu().numpy(), vol.weight.cpu().numpy(), m.cpu().numpy(), f.cpu().numpy()))
     assert np.array_equal(out[0][2], out[1][2]) and np.array_equal(out[0][3], out[1][3])
     assert np.array_equal(out[0][1], out[1][1])
-    # clamped updates are evaluated in float32 in the fast tier and float64 in the exact tier
-    assert np.abs(out[0][0] - out[1][0]).max() <= 2e-7 * sc.tdist * 4
+    # a clamped update is the same float32 expression in both tiers
+    assert np.array_equal(out[0][0], out[1][0])
 
 
 def test_brick_culling_is_invisible():
@@ -146,8 +146,7 @@ def test_brick_culling_is_invisible():
     print("brick stats", st)
     for a, b in zip(out[0][1:], out[1][1:]):
         assert np.array_equal(a, b)
-    # values: a few fp32 ulp where a voxel the per-voxel tier defers to float64 sits in a brick clamped in fp32
-    assert np.abs(out[0][0] - out[1][0]).max() <= 1e-6 * sc.tdist
+    assert np.array_equal(out[0][0], out[1][0])
     assert st["bricks_mixed"] < 0.6 * st["bricks"]
 
 
@@ -179,7 +178,8 @@ def test_projective_multi_view_k8():
 
 
 def test_projective_slabs_equal_full_volume(small_scene):
-    """x-slab sharding: concatenated slabs == single-volume result (weights bit for bit, values to an fp32 ulp or two)."""
+    """x-slab sharding: concatenated slabs == single-volume result, bit for bit (both tiers evaluate a clamped
+    update with the same float32 expression, so it does not matter which tier a brick grid routes a voxel through)."""
     torch, engine, _ = _engine()
     import scenes
     sc = small_scene
@@ -195,7 +195,7 @@ def test_projective_slabs_equal_full_volume(small_scene):
         s = engine.DeviceVolume((R, R, R), x0, x1, tsdf=t3[x0:x1], weight=w3[x0:x1])
         engine.update_projective(s, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist)
         parts_v.append(s.tsdf.cpu().numpy()); parts_w.append(s.weight.cpu().numpy())
-    assert np.abs(np.concatenate(parts_v) - full.tsdf.cpu().numpy()).max() <= 1e-6 * sc.tdist
+    assert np.array_equal(np.concatenate(parts_v), full.tsdf.cpu().numpy())
     assert np.array_equal(np.concatenate(parts_w), full.weight.cpu().numpy())
 
 

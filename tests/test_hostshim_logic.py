@@ -165,7 +165,7 @@ def test_brick_culling_is_conservative():
     # tier and the other in the float64 tier
     for a, b in zip(res[0][1:], res[1][1:]):
         assert np.array_equal(a, b)
-    assert np.abs(res[0][0] - res[1][0]).max() <= 1e-6 * s.tdist
+    assert np.array_equal(res[0][0], res[1][0])
     assert (cv != 255).mean() > 0.3                      # a sizeable part of the volume never needs the per-voxel tier
     assert not (om[0] & (cv == 0)).any()                 # SKIP bricks contain no updated voxel
     assert om[0][(cv != 0) & (cv != 255)].all()          # CLAMP bricks contain only updated voxels
