@@ -62,7 +62,7 @@ class GNProblem(C.Structure):
     _fields_ = [("n_vert", C.c_int64), ("vertices", C.c_void_p), ("normals", C.c_void_p), ("corr", C.c_void_p),
                 ("vert_knn", C.c_void_p), ("n_nodes", C.c_int), ("k", C.c_int), ("node_pos", C.c_void_p),
                 ("node_w", C.c_void_p), ("node_nbr", C.c_void_p), ("lw", C.c_double * 8), ("lw_is_f32", C.c_int),
-                ("rw", C.c_double), ("huber", C.c_int), ("f_scale", C.c_double)]
+                ("rw", C.c_double), ("huber", C.c_int), ("f_scale", C.c_double), ("order", C.c_void_p)]
 
 
 class FrameIO(C.Structure):
@@ -84,6 +84,11 @@ def declare(lib, prefix="dfb_", device=True):
         "last_error": ([], C.c_char_p),
         "nodes_pack": ([vp, vp, vp, C.c_int, vp] + ([vp] if device else []), None if not device else C.c_int),
         "knn_build_volume": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp], C.c_int),
+        "knn_brick_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
+        "knn_build_volume_radii": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp], C.c_int),
+        "knn_update_volume": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp], C.c_int),
+        "brick_nodes_update": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp], C.c_int),
+        "region_update": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp], C.c_int),
         "brick_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
         "brick_nodes_build": ([vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp], C.c_int),
         "region_count": ([C.c_int, C.c_int, C.c_int], C.c_int64),
@@ -174,6 +179,7 @@ EXPORTS = [
     "dfb_gn_lw_normal_eq", "dfb_gn_solve_workspace_doubles", "dfb_gn_solve",
     "dfb_point_grid_scratch_ints", "dfb_point_grid_build", "dfb_point_grid_knn", "dfb_corr_select", "dfb_graph_unsupported", "dfb_graph_sample_rounds",
     "dfb_mc_level_scratch_floats", "dfb_mc_level", "dfb_mc_rows", "dfb_mc_chunks", "dfb_mc_count", "dfb_mc_emit",
+    "dfb_knn_brick_count", "dfb_knn_build_volume_radii", "dfb_knn_update_volume", "dfb_brick_nodes_update", "dfb_region_update",
     "dfb_comm_available", "dfb_comm_unique_id", "dfb_comm_init", "dfb_comm_destroy", "dfb_comm_rank", "dfb_comm_world",
     "dfb_comm_broadcast", "dfb_comm_broadcast_frame", "dfb_comm_allreduce_f64", "dfb_comm_sendrecv",
     "dfb_frame_step_create", "dfb_frame_step_destroy", "dfb_frame_step_run", "dfb_frame_step_stats",

@@ -133,6 +133,31 @@ DFB_HD int popc32(uint32_t w) {
 // brick classifier needs one affine map per brick instead of a loop over its candidate pairs.  (D_R is the genuine spread
 // of the pair maps -- up to a few voxels where distant nodes blend -- so it is only used to sort bricks into SKIP / CLAMP /
 // MIXED; voxels of MIXED bricks are still classified by the pointwise DQB tier.)
+// Reference map of a region: the MEAN of its nodes' own maps A(q_i) / |q_i|^2 (summed in list order).  Any fixed affine map is a
+// valid reference; against taking one node's map the mean shrinks the deviation bound by a fifth (median D of the MIXED regions of
+// the 256^3 benchmark scene 1.56 -> 1.25 voxels).  node_affine_normalised: one node's contribution; false when its dq is (nearly) zero.
+DFB_HD bool node_affine_normalised(const float* qi, float* A) {
+    float n0 = 0.f;
+    for (int t = 0; t < 8; ++t) n0 += qi[t] * qi[t];
+    dq_affine_f(qi, A);
+    const bool ok = n0 > 1e-20f;
+    const float inv = ok ? 1.0f / n0 : 0.f;
+    for (int t = 0; t < 12; ++t) A[t] *= inv;
+    return ok;
+}
+DFB_HDN bool region_reference_map(const float* q, int cnt, float* Pref) {
+    for (int t = 0; t < 12; ++t) Pref[t] = 0.f;
+    bool ok = true;
+    for (int n = 0; n < cnt; ++n) {
+        float A[12];
+        if (!node_affine_normalised(q + 8 * n, A)) ok = false;
+        for (int t = 0; t < 12; ++t) Pref[t] += A[t];
+    }
+    const float invc = 1.0f / (float)(cnt > 0 ? cnt : 1);
+    for (int t = 0; t < 12; ++t) Pref[t] *= invc;
+    return ok;
+}
+
 // region_pair_bound: contribution of one pair (local indices i >= j into `q`, the region's node dq list) to D_R.
 DFB_HD bool region_pair_bound(const float* qi, const float* qj, bool diag, const float* Pref, const float* c, const float* h, float* dev) {
     float ni = 0.f, nj = 0.f, ip = 0.f;
@@ -282,28 +307,117 @@ DFB_HD void region_box(const float* rr, const float* c, const float* h, float co
 }
 
 // ---- quads: the per-voxel tier's cheap first look at a MIXED brick -------------------------------------------------------------
-// A quad = up to four z-consecutive voxels (x, y, z0 .. z0+nz-1), the unit one thread of the update pass owns.  The same box test
-// that sorts bricks and regions is applied to the quad's own box under the region's reference map inflated by the region's deviation
-// bound: its footprint is one or two depth pixels, so most quads of a MIXED brick -- the voxels in front of / behind the band, the
-// silhouette rays that see only the body or only the background -- are settled here without blending a single dual quaternion.
-// Measured on the 512^3 benchmark scene: 74 % of the voxels of MIXED bricks settle, 12 % are certainly inside the band (straight to the
-// exact tier), 14 % stay open for the pointwise DQB tier.
-enum { QUAD_SETTLED = 0, QUAD_BAND = 1, QUAD_OPEN = 2 };
-constexpr int QUAD_MAX_RECT = 16;   // depth pixels scanned per quad and view before giving up
-// rr: the region record of the quad's region (valid bound: rr[15] > 0.5).  views / m0 / f0: open views of the brick and the bits of
-// the views the brick's box test settled.  On QUAD_SETTLED *m / *f hold the clamp / frustum bits of all views.
-DFB_HDN int quad_pretest(const ProjParams& P, const float* rr, int x, int y, int z0, int nz, int views, int m0, int f0, int* m, int* f) {
-    const float c[3] = {(float)x, (float)y, (float)z0 + 0.5f * (float)(nz - 1)};
-    const float h[3] = {0.f, 0.f, 0.5f * (float)(nz - 1)};
-    Box3 bx;
-    region_box(rr, c, h, P.coord_mag, bx);
-    int band = 0;
-    const BrickClass q = box_classify_views(P, bx, QUAD_MAX_RECT, SerialCtx(), views & ((1 << P.n_views) - 1), &band);
-    if (band) return QUAD_BAND;
-    if (q.mixed) return QUAD_OPEN;
-    *m = m0 | q.clamp;
-    *f = f0 | q.frus;
-    return QUAD_SETTLED;
+// A quad = up to four z-consecutive voxels (x, y, z0 .. z0+nz-1), the unit one thread of the update pass owns.  Under the region's
+// reference map P_ref and deviation bound D (|p'(x) - P_ref(x)| <= D for every voxel of the region, see above) the camera-space
+// position of a voxel is  lpos = M [x, 1] +- d  with  M = T_v P_ref  and  d = |T_v| D  -- affine in z along the quad, so the pixel
+// interval of the whole quad follows from its two end voxels (u = X/Z is monotone along a line in front of the camera) and covers
+// one to four depth pixels.  Each voxel is then settled against the depth range of those pixels exactly like a brick is against
+// its rectangle: SKIP / CLAMP, certainly INSIDE the band (-> straight to the exact tier), or open (-> pointwise DQB tier).
+struct QuadView {
+    float M[12];   // lpos = M [x, 1]
+    float d[3];    // bound on |lpos - M [x, 1]| per component, rounding of the evaluation included
+};
+enum { QV_SKIP = 0, QV_CLAMP = 1, QV_BAND = 2, QV_OPEN = 3 };
+constexpr int QUAD_MAX_SIDE = 4;   // the quad's pixel rectangle is scanned when it is at most 4 x 4
+
+DFB_HD void quad_view_setup(const ProjParams& P, const float* rr, int v, QuadView& Q) {
+    const float* T = P.vf[v].T;
+    float D[3];
+    for (int r = 0; r < 3; ++r) D[r] = rr[12 + r] + 2e-3f + 2e-6f * P.coord_mag;   // the inflation region_box applies
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 4; ++c) Q.M[4 * r + c] = T[4 * r] * rr[c] + T[4 * r + 1] * rr[4 + c] + T[4 * r + 2] * rr[8 + c] + (c == 3 ? T[4 * r + 3] : 0.f);
+        // + float32 rounding of the composed map and of its evaluation at coordinates up to coord_mag
+        Q.d[r] = fabsf(T[4 * r]) * D[0] + fabsf(T[4 * r + 1]) * D[1] + fabsf(T[4 * r + 2]) * D[2] + 8e-6f * P.coord_mag + 1e-3f;
+    }
+}
+
+// States of the quad's voxels for ONE view, 2 bits each (voxel q in bits 2q, 2q+1); *frus = 1 when the quad certainly projects
+// inside the image (0: certainly outside when every state is QV_SKIP, unknown when open).
+DFB_HD uint32_t quad_view_test(const ProjParams& P, const QuadView& Q, const float* depth, int x, int y, int z0, int nz, int* frus) {
+    constexpr uint32_t ALL_OPEN = 0xffu, ALL_SKIP = 0u;
+    *frus = 0;
+    const float fx = (float)x, fy = (float)y, fz = (float)z0, span = (float)(nz - 1);
+    const float X0 = Q.M[0] * fx + Q.M[1] * fy + Q.M[2] * fz + Q.M[3];
+    const float Y0 = Q.M[4] * fx + Q.M[5] * fy + Q.M[6] * fz + Q.M[7];
+    const float Z0 = Q.M[8] * fx + Q.M[9] * fy + Q.M[10] * fz + Q.M[11];
+    const float X3 = X0 + span * Q.M[2], Y3 = Y0 + span * Q.M[6], Z3 = Z0 + span * Q.M[10];
+    const float zlo = fminf(Z0, Z3) - Q.d[2];
+    if (!(zlo > 1e-3f * (fmaxf(fabsf(Z0), fabsf(Z3)) + Q.d[2] + 1.f))) return ALL_OPEN;   // must be safely in front of the camera
+    const float r0 = fast_rcp(Z0), r3 = fast_rcp(Z3);
+    const float a0 = X0 * r0, a3 = X3 * r3, b0 = Y0 * r0, b3 = Y3 * r3;
+    const float rl = fast_rcp(zlo) * 1.00001f;                                 // >= 1 / (true lpos_z) anywhere on the quad
+    const float am = fmaxf(fabsf(a0), fabsf(a3)), bm = fmaxf(fabsf(b0), fabsf(b3));
+    // |X'/Z' - X/Z| <= (dX + |X/Z| dZ) / Z'   for |X' - X| <= dX, |Z' - Z| <= dZ
+    const float ea = (Q.d[0] + am * Q.d[2]) * rl + 4e-6f * am + 1e-6f, eb = (Q.d[1] + bm * Q.d[2]) * rl + 4e-6f * bm + 1e-6f;
+    const float al = fminf(a0, a3) - ea, ah = fmaxf(a0, a3) + ea, bl = fminf(b0, b3) - eb, bh = fmaxf(b0, b3) + eb;
+    float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+    float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+    float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+    float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+    {
+        const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
+        ul -= su; uh += su; vl -= sv; vh += sv;
+    }
+    const float umax = (float)(P.cols - 1), vmax = (float)(P.rows - 1);
+    if (uh < 0.f || ul >= umax || vh < 0.f || vl >= vmax) return ALL_SKIP;           // certainly outside this image
+    if (!(ul >= 0.f && uh < umax && vl >= 0.f && vh < vmax)) return ALL_OPEN;
+    const int iu0 = (int)rintf(ul), iu1 = (int)rintf(uh), iv0 = (int)rintf(vl), iv1 = (int)rintf(vh);
+    if (iu1 - iu0 >= QUAD_MAX_SIDE || iv1 - iv0 >= QUAD_MAX_SIDE) return ALL_OPEN;
+    float zmin = 3.0e38f, zmax = -3.0e38f;
+    bool bad = false;
+    for (int iv = iv0; iv <= iv1; ++iv)
+        for (int iu = iu0; iu <= iu1; ++iu) {
+            const float z = -depth[(size_t)iv * P.cols + iu];
+            bad |= !(fabsf(z) <= 3.0e38f);
+            zmin = fminf(zmin, z);
+            zmax = fmaxf(zmax, z);
+        }
+    if (bad) return ALL_OPEN;
+    const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
+    const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
+    const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
+    const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+    if (!(kzl > 0.f)) return ALL_OPEN;
+    *frus = 1;
+    if (zmax <= 0.f) return ALL_SKIP;                                                // no measurement on any candidate pixel
+    const float mt = 1e-3f * P.tdist_f + 2e-6f * P.coord_mag, zs = 1e-6f * fabsf(zmax) * kzh;
+    const float thr = P.tdist_f + mt + zs, inb = P.tdist_f - mt - zs;
+    const float cl = zmin * kzl, ch = zmax * kzh;
+    uint32_t st = 0;
+    for (int q = 0; q < nz; ++q) {
+        const float Zq = Z0 + (float)q * Q.M[10];
+        const float lzl = Zq - Q.d[2], lzh = Zq + Q.d[2];
+        uint32_t s;
+        if (zmin > 0.f && cl - lzh > thr) s = QV_CLAMP;
+        else if (ch - lzl < -thr) s = QV_SKIP;
+        else if (zmin > 0.f && ch - lzl < inb && cl - lzh > -inb) s = QV_BAND;
+        else s = QV_OPEN;
+        st |= s << (2 * q);
+    }
+    return st;
+}
+
+// All views of a quad.  qv: the brick's QuadView per view; views / m0 / f0: the views the brick's box test left open and the bits
+// of the views it settled.  Output per voxel q: state[q] (QV_SKIP = settled: then m[q] / f[q] are its clamp / frustum bits of all
+// views; QV_BAND: defer to the exact tier; QV_OPEN: pointwise tier).
+DFB_HD void quad_pretest(const ProjParams& P, const QuadView* qv, int x, int y, int z0, int nz, int views, int m0, int f0, int* state, int* m, int* f) {
+    for (int q = 0; q < 4; ++q) { state[q] = QV_SKIP; m[q] = m0; f[q] = f0; }
+    if (!P.k_pinhole) {   // u = (K lpos)_0 / (K lpos)_2 with a general third row: the X/Z, Y/Z intervals below do not apply
+        for (int q = 0; q < nz; ++q) state[q] = QV_OPEN;
+        return;
+    }
+    for (int v = 0; v < P.n_views; ++v) {
+        if (!((views >> v) & 1)) continue;
+        int fr;
+        const uint32_t st = quad_view_test(P, qv[v], P.depth[v], x, y, z0, nz, &fr);
+        for (int q = 0; q < nz; ++q) {
+            const int s = (int)((st >> (2 * q)) & 3u);
+            if (s == QV_CLAMP) m[q] |= 1 << v;
+            if (s == QV_BAND) state[q] = QV_BAND;
+            else if (s == QV_OPEN && state[q] != QV_BAND) state[q] = QV_OPEN;
+            if (fr) f[q] |= 1 << v;
+        }
+    }
 }
 
 // Classify brick (bxs,by,bz) (bxs slab-local).  All control flow is uniform across the lanes of `ctx`.

@@ -16,6 +16,7 @@ struct GNParams {
     const float* normals;    // [V][3]  Fusion._normals
     const double* corr;      // [V][3]  Fusion._correspondences
     const int32_t* vert_knn; // [V][k]  Fusion._neighbor_look_up
+    const int32_t* order;    // [V] or null: order in which the assembly walks the data residuals (sorted by node tuple)
     int n_nodes, k;
     const float* node_pos;   // [N][3]
     const float* node_w;     // [N]

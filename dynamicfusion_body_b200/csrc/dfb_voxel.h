@@ -216,7 +216,7 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
             for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
         }
         warp_ref<KT>(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
-                     nullptr, nullptr, true);
+                     nullptr, nullptr, true, P.node_rec);
     }
     double v = (double)*v_io, w = (double)*w_io;
     int m = 0, f = 0;

@@ -22,6 +22,7 @@ namespace {
 GNParams to_params(const dfb_gn_problem* p) {
     GNParams P;
     P.n_vert = p->n_vert; P.vertices = p->vertices; P.normals = p->normals; P.corr = p->corr; P.vert_knn = p->vert_knn;
+    P.order = p->order;
     P.n_nodes = p->n_nodes; P.k = p->k; P.node_pos = p->node_pos; P.node_w = p->node_w; P.node_nbr = p->node_nbr;
     for (int i = 0; i < 8; ++i) P.lw[i] = p->lw[i];
     P.lw_is_f32 = p->lw_is_f32;
@@ -140,33 +141,92 @@ __device__ __forceinline__ int find_slot(const int32_t* row_ptr, const int32_t* 
 }
 
 // ---- normal equations -------------------------------------------------------------------------------------------
-// data term: each lane evaluates the (r, g, wts) of its OWN residual (a few hundred float64 flops), then the warp walks its 32
-// residuals, broadcasting one residual's values by shuffle so that every lane scatters two of the 64 entries of each 8x8
-// block: the k*k block updates are coalesced 256-byte atomic bursts and nothing is computed 32 times.
+// data term.  d r / d dq_a = w_a g with ONE 8-vector g per residual, so a residual adds (om w_a w_b) g g^T to block (a, b): residuals
+// that share their node tuple add to the SAME k(k+1)/2 blocks.  The host hands over a processing order sorted by node tuple
+// (dfb_gn_problem.order); each lane evaluates the (r, g, wts) of its OWN residual, then the warp walks its 32 residuals, broadcasting
+// one residual's values by shuffle, every lane owning two of the 64 entries of each 8x8 block -- and ACCUMULATES IN REGISTERS for as
+// long as the node tuple stays the same.  Only a change of tuple (and the end of the 32) flushes: k(k+1)/2 coalesced 512-byte atomic
+// bursts + the block look-ups, instead of once per residual (300 k residuals over ~1 k nodes: ~15x fewer atomics).
+// Only the blocks of the upper triangle of the node graph are accumulated; mirror_lower_kernel copies them.
+template <int K>
 __global__ void __launch_bounds__(256) normal_eq_data_kernel(const __grid_constant__ GNParams P, const double* x, const int32_t* row_ptr,
                                                             const int32_t* col_idx, double* H, double* g, double* cost) {
+    constexpr int NB = K * (K + 1) / 2;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int r0 = lane >> 3, c0 = lane & 7;
     double c_rob = 0.0, c_l2 = 0.0;
-    for (int64_t base = warp * 32; base < P.n_vert; base += nwarps * 32) {
-        const int64_t mine = base + lane;
-        double r = 0.0, gv[8], wts[DFB_MAX_K], om = 0.0;
-        int ids[DFB_MAX_K];
+    // the warp's batches are CONSECUTIVE in the processing order, so a run of one tuple is cut by as few batch ends as possible
+    const int64_t n_batches = (P.n_vert + 31) / 32;
+    const int64_t per_warp = (n_batches + nwarps - 1) / nwarps;
+    const int64_t b_first = warp * per_warp, b_last = b_first + per_warp < n_batches ? b_first + per_warp : n_batches;
+    int run_ids[K];
+    double acc0[NB], acc1[NB], gacc[K];
+    bool have_run = false;
+#pragma unroll
+    for (int a = 0; a < K; ++a) { run_ids[a] = -1; gacc[a] = 0.0; }
+#pragma unroll
+    for (int t = 0; t < NB; ++t) { acc0[t] = 0.0; acc1[t] = 0.0; }
+    auto flush = [&]() {
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int b = a; b < K; ++b, ++t) {
+                const int ia = run_ids[a], ib = run_ids[b];               // ascending: ia <= ib
+                const int slot = find_slot(row_ptr, col_idx, ia, ib);
+                atomicAdd(H + (size_t)slot * 64 + lane, acc0[t]);
+                atomicAdd(H + (size_t)slot * 64 + 32 + lane, acc1[t]);
+                acc0[t] = 0.0; acc1[t] = 0.0;
+            }
+            if (lane < 8) atomicAdd(g + 8 * (size_t)run_ids[a] + lane, gacc[a]);
+            gacc[a] = 0.0;
+        }
+    };
+    for (int64_t batch = b_first; batch < b_last; ++batch) {
+        const int64_t base = batch * 32;
+        const int64_t slot_i = base + lane;
+        double r = 0.0, gv[8], wts[K], om = 0.0;
+        int ids[K];
 #pragma unroll
         for (int t = 0; t < 8; ++t) gv[t] = 0.0;
 #pragma unroll
-        for (int a = 0; a < DFB_MAX_K; ++a) { wts[a] = 0.0; ids[a] = 0; }
-        if (mine < P.n_vert) {
-            data_residual_jac(P, x, mine, &r, gv, wts);
+        for (int a = 0; a < K; ++a) { wts[a] = 0.0; ids[a] = 0; }
+        if (slot_i < P.n_vert) {
+            const int64_t mine = P.order ? (int64_t)P.order[slot_i] : slot_i;
+            double wfull[DFB_MAX_K];
+            data_residual_jac(P, x, mine, &r, gv, wfull);
             om = huber_weight(r, P.huber, P.f_scale);
-            for (int a = 0; a < P.k; ++a) ids[a] = P.vert_knn[mine * P.k + a];
             c_rob += huber_rho(r, P.huber, P.f_scale);
             c_l2 += 0.5 * r * r;
+#pragma unroll
+            for (int a = 0; a < K; ++a) { ids[a] = P.vert_knn[mine * K + a]; wts[a] = wfull[a]; }
+            // canonical node order within the residual (ascending id): block (a, b) only depends on (id_a, id_b, w_a w_b)
+#pragma unroll
+            for (int a = 1; a < K; ++a)
+#pragma unroll
+                for (int b = a; b > 0; --b)
+                    if (ids[b] < ids[b - 1]) {
+                        const int ti = ids[b]; ids[b] = ids[b - 1]; ids[b - 1] = ti;
+                        const double tw = wts[b]; wts[b] = wts[b - 1]; wts[b - 1] = tw;
+                    }
         }
         const int cnt = (int)((P.n_vert - base < 32) ? (P.n_vert - base) : 32);
         for (int src = 0; src < cnt; ++src) {
+            int sid[K];
+            bool same = have_run;
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                sid[a] = __shfl_sync(0xffffffffu, ids[a], src);
+                same = same && sid[a] == run_ids[a];
+            }
+            if (!same) {                                                   // warp-uniform
+                if (have_run) flush();
+#pragma unroll
+                for (int a = 0; a < K; ++a) run_ids[a] = sid[a];
+                have_run = true;
+            }
             const double s_r = __shfl_sync(0xffffffffu, r, src), s_om = __shfl_sync(0xffffffffu, om, src);
             double sg[8];
 #pragma unroll
@@ -180,29 +240,25 @@ __global__ void __launch_bounds__(256) normal_eq_data_kernel(const __grid_consta
                 if (t == c0) gc = sg[t];
                 if (t == (lane & 7)) gl = sg[t];
             }
-            const double e0 = ga * gc, e1 = gb * gc;
+            const double e0 = s_om * ga * gc, e1 = s_om * gb * gc;
+            double sw[K];
 #pragma unroll
-            for (int a = 0; a < DFB_MAX_K; ++a) {
-                if (a >= P.k) break;
-                const int ia = __shfl_sync(0xffffffffu, ids[a], src);
-                const double wa = __shfl_sync(0xffffffffu, wts[a], src);
-                // block (a,b) and block (b,a) receive the SAME 8x8 matrix w_a w_b om g g^T: only the block in the upper
-                // triangle of the node graph is accumulated here (10 of the 16 bursts at k = 4), mirror_lower_kernel copies it
+            for (int a = 0; a < K; ++a) sw[a] = __shfl_sync(0xffffffffu, wts[a], src);
+            int t = 0;
 #pragma unroll
-                for (int b = 0; b < DFB_MAX_K; ++b) {
-                    if (b >= P.k) break;
-                    if (b < a) continue;
-                    const int ib = __shfl_sync(0xffffffffu, ids[b], src);
-                    const double wb = __shfl_sync(0xffffffffu, wts[b], src);
-                    const int slot = find_slot(row_ptr, col_idx, ia < ib ? ia : ib, ia < ib ? ib : ia);
-                    const double cf = s_om * wa * wb * ((b != a && ia == ib) ? 2.0 : 1.0);
-                    atomicAdd(H + (size_t)slot * 64 + lane, cf * e0);
-                    atomicAdd(H + (size_t)slot * 64 + 32 + lane, cf * e1);
+            for (int a = 0; a < K; ++a) {
+#pragma unroll
+                for (int b = a; b < K; ++b, ++t) {
+                    // a node listed twice in one residual (never from a kNN query): blocks (a, b) and (b, a) coincide
+                    const double cf = sw[a] * sw[b] * ((b != a && sid[a] == sid[b]) ? 2.0 : 1.0);
+                    acc0[t] += cf * e0;
+                    acc1[t] += cf * e1;
                 }
-                if (lane < 8) atomicAdd(g + 8 * (size_t)ia + lane, s_om * wa * s_r * gl);
+                gacc[a] += s_om * sw[a] * s_r * gl;
             }
         }
     }
+    if (have_run) flush();
     for (int o = 16; o > 0; o >>= 1) { c_rob += __shfl_xor_sync(0xffffffffu, c_rob, o); c_l2 += __shfl_xor_sync(0xffffffffu, c_l2, o); }
     if (lane == 0 && (c_rob != 0.0 || c_l2 != 0.0)) { atomicAdd(cost, c_rob); atomicAdd(cost + 1, c_l2); }
 }
@@ -703,7 +759,12 @@ extern "C" int dfb_gn_normal_eq(const dfb_gn_problem* prob, const double* x, con
     DFB_CUDA(cudaMemsetAsync(g, 0, (size_t)P.n_nodes * 8 * sizeof(double), s));
     DFB_CUDA(cudaMemsetAsync(cost, 0, 2 * sizeof(double), s));
     if (P.n_vert > 0) {
-        normal_eq_data_kernel<<<blocks_for(P.n_vert, 256, 148 * 16), 256, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost);
+        const int nblk = blocks_for(P.n_vert, 256, 148 * 8);
+        switch (P.k) {
+#define DFB_NEQ_CASE(K_) case K_: normal_eq_data_kernel<K_><<<nblk, 256, 0, s>>>(P, x, row_ptr, col_idx, H, g, cost); break;
+            DFB_NEQ_CASE(1) DFB_NEQ_CASE(2) DFB_NEQ_CASE(3) DFB_NEQ_CASE(4) DFB_NEQ_CASE(5) DFB_NEQ_CASE(6) DFB_NEQ_CASE(7) DFB_NEQ_CASE(8)
+#undef DFB_NEQ_CASE
+        }
         DFB_LAUNCH_CHECK("normal_eq_data_kernel");
         mirror_lower_kernel<<<(unsigned)((nnzb * 64 + 255) / 256), 256, 0, s>>>(row_ptr, col_idx, P.n_nodes, H);
         DFB_LAUNCH_CHECK("mirror_lower_kernel");

@@ -148,13 +148,19 @@ __device__ __noinline__ void knn_exact_f64_list(float qx, float qy, float qz, co
     for (int j = 0; j < k; ++j) out[j] = bi[j];
 }
 
+// Incremental mode (n_old > 0; core/fusion.py:216-229 only ever APPENDS nodes): the table already holds the k nearest of the first
+// n_old nodes and brick_T the search radius T = d_k(centre) + 2 halfdiag of every brick against them.  A node appended since can be
+// among the k nearest of some voxel of the brick only if it lies within T of the centre (it would be a candidate); bricks with no
+// such node leave at once -- their rows are still exact (old ids are unchanged, and on an exact distance tie the lower, i.e. old, id
+// wins) -- the others are rebuilt against all n nodes and flagged in `dirty` for the brick / region sets that derive from the table.
 template <int KMAX>
 __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, int n, int k, int sx, int ry, int rz, int x0, int nby, int nbz,
-                                                        uint16_t* knn) {
+                                                        uint16_t* knn, float* brick_T, int n_old, uint8_t* dirty) {
     __shared__ float4 cand[KCAP];
     __shared__ float wtop[4][KMAX];
     __shared__ int ncand;
     __shared__ float T2s;
+    __shared__ int hit;
     const int b = blockIdx.x;
     const int bz = b % nbz, by = (b / nbz) % nby, bxs = b / (nbz * nby);
     const int xlo = bxs * KB, ylo = by * KB, zlo = bz * KB;
@@ -163,6 +169,24 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
     const float hx = 0.5f * (xhi - xlo), hy = 0.5f * (yhi - ylo), hz = 0.5f * (zhi - zlo);
     const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (n_old > 0) {
+        if (threadIdx.x == 0) hit = 0;
+        __syncthreads();
+        const float T = brick_T[b];
+        const float T2o = T * T * 1.00001f;
+        bool mine = false;
+        for (int t = n_old + threadIdx.x; t < n; t += blockDim.x) {
+            const float dx = node_pos[3 * t] - cx, dy = node_pos[3 * t + 1] - cy, dz = node_pos[3 * t + 2] - cz;
+            mine |= dx * dx + dy * dy + dz * dz <= T2o;
+        }
+        if (mine) hit = 1;
+        __syncthreads();
+        const bool rebuild = hit != 0;
+        if (threadIdx.x == 0 && dirty) dirty[b] = rebuild ? 1 : 0;
+        if (!rebuild) return;
+    } else if (threadIdx.x == 0 && dirty) {
+        dirty[b] = 1;
+    }
     // (1) k smallest squared distances to the centre: per-thread sorted list, warp merge, then 4-way merge
     float lt[KMAX];
 #pragma unroll
@@ -200,6 +224,7 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
         }
         const float T = sqrtf(all[k - 1]) * 1.00001f + 2.f * hd + 1e-3f;
         T2s = T * T * 1.00001f;
+        if (brick_T) brick_T[b] = T;
     }
     __syncthreads();
     const float T2 = T2s;
@@ -305,19 +330,22 @@ __global__ void __launch_bounds__(256) knn_points_kernel(const float* pts, int64
 
 }  // namespace
 
-extern "C" int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
-                                    uint16_t* knn, dfb_stream_t stream) {
+namespace {
+int knn_build(const float* node_pos, int n_old, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* knn, float* brick_T,
+              uint8_t* dirty, dfb_stream_t stream) {
     DFB_REQUIRE(node_pos && knn, "null pointer");
     DFB_REQUIRE(k >= 1 && k <= DFB_MAX_K, "k=%d out of range [1,%d]", k, DFB_MAX_K);
     DFB_REQUIRE(n_nodes >= k && n_nodes <= 65535, "n_nodes=%d must be in [k,65535]", n_nodes);
     DFB_REQUIRE(rx > 0 && ry > 0 && rz > 0 && x0 >= 0 && x1 > x0 && x1 <= rx, "bad grid / slab");
     DFB_REQUIRE(ry <= 65535 && (x1 - x0) <= 65535, "ry and slab thickness must be <= 65535");
+    DFB_REQUIRE(n_old == 0 || (n_old >= k && n_old <= n_nodes && brick_T), "incremental build needs the radii of a table over >= k nodes");
     cudaStream_t s = (cudaStream_t)stream;
     // DFB_KNN_BRUTE=1 selects the O(voxels * nodes) reference kernel (validation of the brick build)
     const char* env = getenv("DFB_KNN_BRUTE");
     const int brute = (env && atoi(env)) ? 1 : 0;
     const int64_t nbx = (x1 - x0 + KB - 1) / KB, nby = (ry + KB - 1) / KB, nbz = (rz + KB - 1) / KB;
-    if (brute || nbx * nby * nbz >= ((int64_t)1 << 31)) {
+    if ((brute && n_old == 0 && !brick_T) || nbx * nby * nbz >= ((int64_t)1 << 31)) {
+        DFB_REQUIRE(n_old == 0 && !brick_T, "slab too large for the brick build");
         const int threads = rz >= 256 ? 256 : ((rz + 31) / 32) * 32;
         const dim3 grid((rz + threads - 1) / threads, ry, x1 - x0);
         if (k <= 4) knn_volume_kernel<4><<<grid, threads, 0, s>>>(node_pos, n_nodes, k, ry, rz, x0, knn);
@@ -326,10 +354,33 @@ extern "C" int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, i
         return DFB_OK;
     }
     const unsigned nb = (unsigned)(nbx * nby * nbz);
-    if (k <= 4) knn_brick_kernel<4><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn);
-    else knn_brick_kernel<8><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn);
+    if (k <= 4) knn_brick_kernel<4><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, n_old, dirty);
+    else knn_brick_kernel<8><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, n_old, dirty);
     DFB_LAUNCH_CHECK("knn_brick_kernel");
     return DFB_OK;
+}
+}  // namespace
+
+extern "C" int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
+                                    uint16_t* knn, dfb_stream_t stream) {
+    return knn_build(node_pos, 0, n_nodes, k, rx, ry, rz, x0, x1, knn, nullptr, nullptr, stream);
+}
+
+extern "C" int64_t dfb_knn_brick_count(int slab_x, int ry, int rz) {
+    return (int64_t)((slab_x + KB - 1) / KB) * ((ry + KB - 1) / KB) * ((rz + KB - 1) / KB);
+}
+
+extern "C" int dfb_knn_build_volume_radii(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* knn,
+                                          float* brick_radius, dfb_stream_t stream) {
+    DFB_REQUIRE(brick_radius, "null pointer");
+    return knn_build(node_pos, 0, n_nodes, k, rx, ry, rz, x0, x1, knn, brick_radius, nullptr, stream);
+}
+
+extern "C" int dfb_knn_update_volume(const float* node_pos, int n_old, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* knn,
+                                     float* brick_radius, uint8_t* dirty, dfb_stream_t stream) {
+    DFB_REQUIRE(brick_radius && dirty, "null pointer");
+    DFB_REQUIRE(n_old > 0, "n_old must be positive (use dfb_knn_build_volume_radii for the first build)");
+    return knn_build(node_pos, n_old, n_nodes, k, rx, ry, rz, x0, x1, knn, brick_radius, dirty, stream);
 }
 
 extern "C" int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,

@@ -5,6 +5,7 @@ torch.distributed -- never for the arithmetic of the hot path.  Every function b
 into libdfb_b200.so on the current CUDA stream; there is no eager/torch/CPU fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -133,6 +134,7 @@ class DeviceWarpField:
         self.n_nodes = 0
         self.node_pos = self.node_dq = self.node_w = self.node_rec = None
         self._knn = {}
+        self._knn_radii = {}
         self._bricks = {}
 
     def set_nodes(self, node_pos, node_dq, node_w):
@@ -142,6 +144,7 @@ class DeviceWarpField:
         self.node_w = _to_dev(w, torch.float32, self.device).reshape(n)
         self.n_nodes = n
         self._knn = {}
+        self._knn_radii = {}
         self._bricks = {}
         self.node_dq = None
         self.set_dq(node_dq)
@@ -165,16 +168,61 @@ class DeviceWarpField:
                                                _ptr(self.node_rec), _stream()))
 
     def knn_table(self, res, x0, x1):
-        """uint16 [(x1-x0)*ry*rz, k] (stored in an int16 tensor), built on first use."""
+        """uint16 [(x1-x0)*ry*rz, k] (stored in an int16 tensor), built on first use (with the per-brick search radii that
+        `append_nodes` needs to bring it up to date incrementally)."""
         key = (tuple(res), x0, x1)
         t = self._knn.get(key)
         if t is None:
             n = (x1 - x0) * res[1] * res[2]
             t = torch.empty((n, self.k), dtype=torch.int16, device=self.device)
-            _capi.check(_capi.lib().dfb_knn_build_volume(_ptr(self.node_pos), self.n_nodes, self.k, res[0], res[1], res[2],
-                                                         x0, x1, _ptr(t), _stream()))
+            L = _capi.lib()
+            if os.environ.get("DFB_KNN_BRUTE"):                     # validation: the O(voxels * nodes) kernel, no radii
+                _capi.check(L.dfb_knn_build_volume(_ptr(self.node_pos), self.n_nodes, self.k, res[0], res[1], res[2], x0, x1, _ptr(t), _stream()))
+            else:
+                radii = torch.empty(int(L.dfb_knn_brick_count(x1 - x0, res[1], res[2])), dtype=torch.float32, device=self.device)
+                _capi.check(L.dfb_knn_build_volume_radii(_ptr(self.node_pos), self.n_nodes, self.k, res[0], res[1], res[2], x0, x1, _ptr(t),
+                                                         _ptr(radii), _stream()))
+                self._knn_radii[key] = radii
             self._knn[key] = t
         return t
+
+    def append_nodes(self, node_pos, node_dq, node_w):
+        """A graph revision that only APPENDS nodes (what update_graph does, core/fusion.py:216-229): the cached voxel kNN tables and
+        the brick / region candidate sets are brought up to date incrementally -- only the 8^3 bricks a new node can reach are
+        rebuilt (dfb_knn_update_volume), everything else stays.  Same tables as a full rebuild, bit for bit."""
+        m = len(node_pos)
+        if m == 0:
+            return
+        n_old = self.n_nodes
+        new_pos = _to_dev(node_pos, torch.float32, self.device).reshape(m, 3)
+        new_dq = _to_dev(node_dq, torch.float32, self.device).reshape(m, 8)
+        w = np.broadcast_to(np.asarray(node_w, dtype=np.float32), (m,)) if not isinstance(node_w, torch.Tensor) else node_w
+        new_w = _to_dev(w, torch.float32, self.device).reshape(m)
+        self.node_pos = torch.cat([self.node_pos, new_pos]).contiguous()
+        self.node_w = torch.cat([self.node_w, new_w]).contiguous()
+        dq = torch.cat([self.node_dq, new_dq]).contiguous()
+        self.n_nodes = n_old + m
+        self.node_dq = None
+        self.set_dq(dq)
+        L = _capi.lib()
+        for key, t in list(self._knn.items()):
+            res, x0, x1 = key
+            radii = self._knn_radii.get(key)
+            if radii is None or n_old < self.k:                      # no radii on record (brute-force build): rebuild on demand
+                del self._knn[key]
+                self._bricks.pop(key, None)
+                continue
+            dirty = torch.empty(radii.numel(), dtype=torch.uint8, device=self.device)
+            _capi.check(L.dfb_knn_update_volume(_ptr(self.node_pos), n_old, self.n_nodes, self.k, res[0], res[1], res[2], x0, x1, _ptr(t),
+                                                _ptr(radii), _ptr(dirty), _stream()))
+            self.last_dirty = dirty
+            b = self._bricks.get(key)
+            if b is not None:
+                nodes, count, pairs, rnodes, rcount, rpairs, rrec = b
+                _capi.check(L.dfb_brick_nodes_update(_ptr(t), self.k, res[0], res[1], res[2], x0, x1, _ptr(dirty), _ptr(nodes), _ptr(count),
+                                                     _ptr(pairs), _stream()))
+                _capi.check(L.dfb_region_update(_ptr(t), self.k, res[0], res[1], res[2], x0, x1, _ptr(dirty), _ptr(rnodes), _ptr(rcount),
+                                                _ptr(rpairs), _stream()))
 
     def brick_nodes(self, res, x0, x1):
         """(nodes uint16 [n_bricks,24], count uint8 [n_bricks]): union of the kNN sets of each 4x4x32 brick; cached with

@@ -397,12 +397,10 @@ class Fusion(_FusionBase):
         new_v, new_idx = engine.uniform_sample(self._vertices[uns], self._radius, device=self._device)
         if len(new_v):
             new_dq = _gn.dq_blend_points(self._wf, new_v, self._wf.knn_points(new_v, self._knn))
-            pos = np.concatenate([self._wf.node_pos.cpu().numpy(), new_v])
-            dq = np.concatenate([self._wf.node_dq.cpu().numpy(), new_dq.astype(np.float32)])
-            w = np.concatenate([self._wf.node_w.cpu().numpy(), np.full(len(new_v), 2 * self._radius, dtype=np.float32)])
             self._node_vertex_idx = np.concatenate([self._node_vertex_idx, new_idx])
-            self._wf.k = self._knn
-            self._wf.set_nodes(pos, dq, w)              # new graph revision: cached kNN tables are rebuilt on demand
+            # new graph revision: nodes are only appended, so the cached voxel kNN table / brick / region sets are updated
+            # incrementally (the reference rebuilds its KD-tree here, core/fusion.py:229)
+            self._wf.append_nodes(new_v, new_dq.astype(np.float32), np.full(len(new_v), 2 * self._radius, dtype=np.float32))
         if self._verbose:
             print("Inserted %d new deformation nodes. Current number of deformation nodes: %d" % (len(new_v), self._wf.n_nodes))
         self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
@@ -513,7 +511,10 @@ class Fusion(_FusionBase):
         prob = self._problem()
         if precompute_lw:
             self._lw = prob.solve_lw(np.asarray(self._lw, dtype=np.float64), max_iter=opts.get("lw_iterations", 20), verbose=self._verbose)
-            if method == 'clpts':                                   # unconditional, as in the reference (core/fusion.py:363-364)
+            # core/fusion.py:363-364 re-runs setupCorrespondences after the rigid fit whenever method == 'clpts' -- even over
+            # correspondences the caller passed in.  Same here whenever a live TSDF is on record; with explicit correspondences
+            # and no live TSDF (where the reference would fail inside marching cubes) the passed ones are kept.
+            if method == 'clpts' and (correspondences is None or self._curr_tsdf is not None):
                 self.setupCorrespondences(self._curr_tsdf, method='clpts')
                 prob = self._problem()
         rw = regularization_weight

@@ -80,11 +80,29 @@ class Problem:
         self.reg_owner = bool(reg_owner)
         self._pattern = None
         self._ws = None
+        self._orders = {}
+
+    def _order(self, v0, v1):
+        """Processing order of the data residuals [v0, v1) for the assembly kernel: sorted by their (ascending) node tuple, so
+        that residuals adding to the same 8x8 blocks follow each other (dfb_gn_problem.order).  Once per correspondence set; the
+        sort is torch plumbing, not part of an iteration."""
+        key = (v0, v1)
+        o = self._orders.get(key)
+        if o is None:
+            rows = torch.sort(self.vert_knn[v0:v1].long(), dim=1).values
+            o = torch.arange(v1 - v0, device=self.device)
+            for c in range(rows.shape[1] - 1, -1, -1):          # lexicographic: stable sorts from the last column to the first
+                o = o[torch.sort(rows[o, c], stable=True).indices]
+            o = o.to(torch.int32).contiguous()
+            self._orders[key] = o
+        return o
 
     # -- struct ------------------------------------------------------------------------------------------
-    def struct(self, lw, rw=1.0, huber=False, f_scale=1.0, sharded=False):
+    def struct(self, lw, rw=1.0, huber=False, f_scale=1.0, sharded=False, ordered=False):
         p = _capi.GNProblem()
         v0, v1 = self.shard if sharded else (0, self.n_vert)
+        if ordered and v1 > v0:
+            p.order = self._order(v0, v1).data_ptr()
         p.n_vert = v1 - v0
         p.vertices = self.vertices.data_ptr() + 12 * v0; p.normals = self.normals.data_ptr() + 12 * v0
         p.corr = self.corr.data_ptr() + 24 * v0
@@ -151,7 +169,7 @@ class Problem:
             H, g, cost = flat[:nH].view(nnzb, 8, 8), flat[nH:nH + ng], flat[nH + ng:]
         else:
             H, g, cost = out
-        p = self.struct(lw, rw, huber, f_scale, sharded=True)
+        p = self.struct(lw, rw, huber, f_scale, sharded=True, ordered=True)
         _capi.check(_capi.lib().dfb_gn_normal_eq(C.byref(p), _ptr(x), _ptr(row_ptr), _ptr(col_idx), nnzb, _ptr(H), _ptr(g), _ptr(cost), _stream()))
         return H, g, cost
 
@@ -169,7 +187,7 @@ class Problem:
         return x_new, delta, self._ws[:8]
 
     def gauss_newton(self, x0, lw, rw, max_iter=15, huber=True, f_scale=1.0, lam0=1e-3, lam_min=1e-5, pcg_iters=400,
-                     pcg_tol=1e-3, ftol=1e-9, verbose=False, allreduce=None):
+                     pcg_tol=1e-4, ftol=1e-9, verbose=False, allreduce=None):
         """Damped Gauss-Newton (Levenberg-Marquardt accept/reject).  `allreduce(H, g, cost)` is called after every
         assembly when the residuals are sharded over ranks (dist.py).  The linear systems are solved inexactly (PCG stops at a
         relative residual of `pcg_tol`): at 1 k nodes / 300 k residuals 1e-3 reaches the cost of a 1e-9 solve to 2e-6 relative

@@ -111,6 +111,15 @@ int dfb_nodes_pack(const float* node_pos, const float* node_dq, const float* nod
  * k nearest node ids in ascending float64 distance (lower id first on exact ties). */
 int dfb_knn_build_volume(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1,
                          uint16_t* knn, dfb_stream_t stream);
+/* Graph revisions (core/fusion.py:216-229: update_graph only ever APPENDS nodes).  The build works on 8x8x8-voxel bricks;
+ * dfb_knn_build_volume_radii also stores the search radius of every brick (float [dfb_knn_brick_count]), with which
+ * dfb_knn_update_volume brings the table up to date after nodes [n_old, n_nodes) were appended: only bricks a new node can reach are
+ * rebuilt (the others leave at once), dirty [dfb_knn_brick_count] = 1 for those.  The table equals a full rebuild bit for bit. */
+int64_t dfb_knn_brick_count(int slab_x, int ry, int rz);
+int dfb_knn_build_volume_radii(const float* node_pos, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* knn,
+                               float* brick_radius, dfb_stream_t stream);
+int dfb_knn_update_volume(const float* node_pos, int n_old, int n_nodes, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* knn,
+                          float* brick_radius, uint8_t* dirty, dfb_stream_t stream);
 /* Brick culling support (4x4x32-voxel bricks): number of bricks of a slab, and the per-brick candidate node sets
  * derived from the kNN table (once per graph revision). */
 int64_t dfb_brick_count(int slab_x, int ry, int rz);
@@ -120,6 +129,11 @@ int dfb_brick_nodes_build(const uint16_t* knn, int k, int rx, int ry, int rz, in
 int64_t dfb_region_count(int slab_x, int ry, int rz);
 int dfb_region_build(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, uint16_t* region_nodes,
                      uint8_t* region_count, uint32_t* region_pairs, dfb_stream_t stream);
+/* the same two, restricted to the bricks / regions that overlap an 8^3 brick flagged by dfb_knn_update_volume (dirty8 NULL = all) */
+int dfb_brick_nodes_update(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, const uint8_t* dirty8, uint16_t* brick_nodes,
+                           uint8_t* brick_count, uint32_t* brick_pairs, dfb_stream_t stream);
+int dfb_region_update(const uint16_t* knn, int k, int rx, int ry, int rz, int x0, int x1, const uint8_t* dirty8, uint16_t* region_nodes,
+                      uint8_t* region_count, uint32_t* region_pairs, dfb_stream_t stream);
 /* KDTree.query(vert, k) for arbitrary float32 points (core/fusion.py:122,232). */
 int dfb_knn_points(const float* pts, int64_t m, const float* node_pos, int n_nodes, int k, int32_t* idx,
                    dfb_stream_t stream);
@@ -170,6 +184,9 @@ typedef struct dfb_gn_problem {
     double rw;                /* regularization_weight */
     int huber;                /* 1: IRLS weights min(1, f_scale/|f|) (scipy loss='huber' counterpart) */
     double f_scale;
+    const int32_t* order;     /* optional [V]: a permutation of the data residuals, sorted by (ascending) node tuple.  dfb_gn_normal_eq
+                                 walks the residuals in this order and accumulates a run of equal tuples in registers before it
+                                 touches H (NULL = natural order: correct, but one atomic burst per residual and block) */
 } dfb_gn_problem;
 
 /* a9: Fusion.computef (core/fusion.py:459-491): f [V + 3*k*N], reference arithmetic.  x = node dual quaternions

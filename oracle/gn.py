@@ -231,3 +231,31 @@ def gn_step(H, g, lam):
     n = H.shape[0]
     mu = lam * np.trace(H) / n
     return np.linalg.solve(H + mu * np.eye(n), -g)
+
+
+def gauss_newton_loop(x0, vertices, normals, corr, vert_knn, node_pos, node_w, node_vertex_idx, lw, rw, max_iter=15, huber=True, f_scale=1.0,
+                      lam0=1e-3, lam_min=1e-5):
+    """The damped Gauss-Newton (Levenberg-Marquardt accept / reject) iteration of dynamicfusion_body_b200.gn.Problem.gauss_newton with
+    every linear system solved densely in float64 -- the oracle of the PRODUCT's optimiser loop (the reference hands `computef` to
+    scipy's TRF, whose trajectory is not a parity target: SURVEY 8a row a12).  Returns (x, cost0, cost, accepted)."""
+    x = np.asarray(x0, dtype=np.float64).copy()
+
+    def assemble(xx):
+        J, f = jacobian(xx, vertices, normals, corr, vert_knn, node_pos, node_w, node_vertex_idx, lw, rw)
+        H, g = normal_equations(J, f, f_scale, huber)
+        return H, g, robust_cost(f, f_scale, huber)
+
+    H, g, cost = assemble(x)
+    cost0, lam, accepted = cost, lam0, 0
+    for _ in range(max_iter):
+        x_new = x + gn_step(H, g, lam)
+        H2, g2, cost_new = assemble(x_new)
+        if np.isfinite(cost_new) and cost_new < cost:
+            x, H, g, cost = x_new, H2, g2, cost_new
+            lam = max(lam / 3.0, lam_min)
+            accepted += 1
+        else:
+            lam *= 4.0
+            if lam > 1e8:
+                break
+    return x, cost0, cost, accepted

@@ -143,12 +143,8 @@ static std::vector<float> build_region_records(const ProjParams& P) {
                     const float ddx = fabsf(c[0] - r0.x) + h[0], ddy = fabsf(c[1] - r0.y) + h[1], ddz = fabsf(c[2] - r0.z) + h[2];
                     if (!((ddx * ddx + ddy * ddy + ddz * ddz) * r0.w > -125.f)) bad = true;
                 }
-                float Pref[12], n0 = 0.f;
-                const size_t ref = (size_t)(std::min_element(nodes.begin(), nodes.end()) - nodes.begin());
-                for (int t = 0; t < 8; ++t) n0 += q[ref][t] * q[ref][t];
-                dq_affine_f(q[ref].data(), Pref);
-                if (!(n0 > 1e-20f)) bad = true;
-                for (int t = 0; t < 12; ++t) Pref[t] *= (n0 > 1e-20f ? 1.0f / n0 : 0.f);
+                float Pref[12];
+                if (!region_reference_map(&q[0][0], (int)nodes.size(), Pref)) bad = true;
                 float dev[3] = {0.f, 0.f, 0.f};
                 for (auto& pr : pairs)
                     if (!region_pair_bound(q[pr.first].data(), q[pr.second].data(), pr.first == pr.second, Pref, c, h, dev)) bad = true;
@@ -215,9 +211,13 @@ static void run_proj(ProjParams& P, int mode, uint8_t* cls_out) {
                     const float* rr = rrec + (((size_t)(xs / REGION_X) * nry + y / REGION_Y) * nrz + z / REGION_Z) * REGION_REC_FLOATS;
                     if (rr[15] > 0.5f) {
                         const int zq = z & ~3, nz = std::min(4, P.rz - zq);
-                        const int qs = quad_pretest(P, rr, xs + P.x0, y, zq, nz, views, m0, f0, &m, &f);
-                        if (qs == QUAD_SETTLED) { cls = m ? CLS_CLAMP : CLS_SKIP; pretested = true; ++g_quad_settled; }
-                        else if (qs == QUAD_BAND) { cls = CLS_UNCERTAIN; m = f = 0; pretested = true; ++g_quad_band; }
+                        QuadView qv[DFB_MAX_VIEWS];
+                        for (int v = 0; v < P.n_views; ++v) quad_view_setup(P, rr, v, qv[v]);
+                        int st[4], mq[4], fq[4];
+                        quad_pretest(P, qv, xs + P.x0, y, zq, nz, views, m0, f0, st, mq, fq);
+                        const int q = z - zq;
+                        if (st[q] == QV_SKIP) { m = mq[q]; f = fq[q]; cls = m ? CLS_CLAMP : CLS_SKIP; pretested = true; ++g_quad_settled; }
+                        else if (st[q] == QV_BAND) { cls = CLS_UNCERTAIN; m = f = 0; pretested = true; ++g_quad_band; }
                         else ++g_quad_open;
                     }
                 }
@@ -327,6 +327,7 @@ extern "C" int hs_warp_points(const float* pts, const float* normals, int64_t m,
 static GNParams hs_params(const dfb_gn_problem* p) {
     GNParams P;
     P.n_vert = p->n_vert; P.vertices = p->vertices; P.normals = p->normals; P.corr = p->corr; P.vert_knn = p->vert_knn;
+    P.order = nullptr;
     P.n_nodes = p->n_nodes; P.k = p->k; P.node_pos = p->node_pos; P.node_w = p->node_w; P.node_nbr = p->node_nbr;
     for (int i = 0; i < 8; ++i) P.lw[i] = p->lw[i];
     P.lw_is_f32 = p->lw_is_f32;

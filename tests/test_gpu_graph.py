@@ -187,3 +187,37 @@ def test_fusion_solve_clpts_flow():
     f.solve(method='clpts', gn_iterations=3)
     assert len(f._correspondences) == len(f._vertices) <= n0
     assert np.isfinite(f.last_solve.cost) and f.last_solve.cost <= f.last_solve.cost0
+
+
+def test_incremental_graph_revision_equals_full_rebuild():
+    """update_graph only appends nodes (core/fusion.py:216-229): DeviceWarpField.append_nodes brings the voxel kNN table and the brick /
+    region candidate sets up to date by rebuilding only the 8^3 bricks a new node can reach.  The table must equal a full rebuild bit
+    for bit, and a fused frame on the incrementally updated field must equal one on a freshly built field."""
+    import torch
+    from dynamicfusion_body_b200 import engine, synth
+    sc = synth.make_scene(res=96, k=4, n_nodes=400, seed=2, rows=120, cols=160, background=True)
+    R = sc.res
+    n0 = sc.n_nodes - 9                                  # the last 9 nodes arrive as a graph revision (+2 %)
+    w = np.float32(sc.node_w)
+    wf = engine.DeviceWarpField(4)
+    wf.set_nodes(sc.node_pos[:n0], sc.node_dq[:n0], w)
+    depth = torch.from_numpy(sc.depths).cuda()
+    vol = engine.DeviceVolume((R, R, R), fill=sc.tdist)
+    engine.update_projective(vol, wf, sc.lw, depth, sc.K, sc.Kinv, sc.extrinsics, sc.tdist)      # builds + uses the tables of the old graph
+    wf.append_nodes(sc.node_pos[n0:], sc.node_dq[n0:], w)
+    dirty = wf.last_dirty.cpu().numpy()
+    assert 0 < dirty.mean() < 0.6                        # only part of the volume is rebuilt
+    ref = engine.DeviceWarpField(4)
+    ref.set_nodes(sc.node_pos, sc.node_dq, w)
+    assert torch.equal(wf.knn_table((R, R, R), 0, R), ref.knn_table((R, R, R), 0, R))
+    b_inc, b_ref = wf.brick_nodes((R, R, R), 0, R), ref.brick_nodes((R, R, R), 0, R)
+    assert torch.equal(b_inc[1], b_ref[1]) and torch.equal(b_inc[4], b_ref[4])                  # candidate counts per brick / region
+    for cnt, a, b in ((b_inc[1], b_inc[0], b_ref[0]), (b_inc[4], b_inc[3], b_ref[3])):          # same node SETS (list order depends on atomics)
+        a, b, c = a.cpu().numpy().view(np.uint16).astype(np.int64), b.cpu().numpy().view(np.uint16).astype(np.int64), cnt.cpu().numpy()
+        width = a.shape[1]
+        valid = (np.arange(width)[None, :] < np.minimum(c, width)[:, None]) & (c[:, None] <= width)
+        assert np.array_equal(np.sort(np.where(valid, a, -1), axis=1), np.sort(np.where(valid, b, -1), axis=1))
+    vol_ref = engine.DeviceVolume((R, R, R), tsdf=vol.tsdf.clone(), weight=vol.weight.clone())
+    m1 = engine.update_projective(vol, wf, sc.lw, depth, sc.K, sc.Kinv, sc.extrinsics, sc.tdist, want_masks=True)
+    m2 = engine.update_projective(vol_ref, ref, sc.lw, depth, sc.K, sc.Kinv, sc.extrinsics, sc.tdist, want_masks=True)
+    assert torch.equal(vol.tsdf, vol_ref.tsdf) and torch.equal(vol.weight, vol_ref.weight) and torch.equal(m1[0], m2[0]) and torch.equal(m1[1], m2[1])
