@@ -120,12 +120,103 @@ def frame_dqs(sc, n_frames, seed=1):
 
 
 # ------------------------------------------------------------------------------------------------------
+class RankState:
+    """Everything one rank needs to step its x-slab [x0, x1) of the grid: the drop-in Fusion object, the double-buffered frame
+    packets, and one captured frame step (CUDA graph) per packet with its resident / end-to-end I/O descriptors."""
+
+    def __init__(self, args, sc, grid, x0, x1, dev, rank, comm, comm_pre, frames):
+        import torch
+        from dynamicfusion_body_b200 import engine
+        from dynamicfusion_body_b200 import dist as ddist
+        from dynamicfusion_body_b200.fusion import Fusion
+        self.x0, self.x1, self.rank, self.dev, self.sc, self.comm_pre = x0, x1, rank, dev, sc, comm_pre
+        self.nvox = (x1 - x0) * grid[1] * grid[2]
+        fus = Fusion(sc.tdist, knn=args.k, device=dev, use_cnn=False, write_warpfield=False)
+        fus.InitializeCanonicalSpace(tsdf_shape=grid, slab=(x0, x1), K=sc.K, vertices=sc.vertices, normals=sc.normals,
+                                     nodes=sc.nodes_as_reference_tuples())
+        fus._lw = sc.lw
+        self.fus, self.vol, self.wf = fus, fus._vol, fus._wf
+        # graph revision: voxel kNN table + brick / region candidate sets (once per update_graph, core/fusion.py:229)
+        torch.cuda.synchronize()
+        rev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        rev[0].record()
+        fus.build_knn()
+        rev[1].record()
+        torch.cuda.synchronize()
+        self.graph_revision_ms = ddist.max_over_ranks(rev[0].elapsed_time(rev[1]), dev)
+        self.stream = torch.cuda.Stream(device=dev)      # a capturable (non-default) stream: the step is one CUDA-graph launch
+        shape = sc.depths.shape
+        self.frames = frames
+        self.packets = [torch.zeros(shape, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.dq_stage = [torch.zeros((sc.n_nodes, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.counters_host = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self.slot_done = [torch.cuda.Event(), torch.cuda.Event()]
+        self.steps, self.ios_res, self.ios_e2e = [], [], []
+        for slot in range(2):
+            views = engine.make_views(self.packets[slot], sc.K, sc.Kinv, sc.extrinsics)
+            st = engine.FrameStep(self.vol, self.wf, sc.lw, views, sc.tdist)
+            self.steps.append(st)
+            # resident frame: the transforms are already in wf.node_dq on the root, the next depth frame is a device buffer
+            self.ios_res.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, prefetch_dst=self.packets[slot ^ 1], prefetch_src=frames["depth_dev"]))
+            # end to end: transforms and depth come from pinned host memory, the counters go back to pinned host memory
+            self.ios_e2e.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, dq_src=self.dq_stage[slot], prefetch_dst=self.packets[slot ^ 1],
+                                      prefetch_src=frames["depth_host"], counters_host=self.counters_host[slot]))
+
+    def reset(self):
+        self.vol.tsdf.fill_(self.sc.tdist)
+        self.vol.weight.zero_()
+
+    def prime(self, src):
+        """frame 0's sensor data into packet 0 (every later frame arrives through the prefetch branch of the step before it)"""
+        import torch
+        with torch.cuda.stream(self.stream):
+            if self.rank == 0:
+                self.packets[0].copy_(src, non_blocking=True)
+            if self.comm_pre is not None:
+                self.comm_pre.broadcast(self.packets[0])
+        self.stream.synchronize()
+
+    def step_resident(self, i):
+        import torch
+        slot = i & 1
+        with torch.cuda.stream(self.stream):
+            if self.rank == 0:
+                self.wf.node_dq.copy_(self.frames["dq_dev"][i % len(self.frames["dq_dev"])], non_blocking=True)
+            self.steps[slot].run(self.ios_res[slot])
+
+    def step_e2e(self, i):
+        import torch
+        slot = i & 1
+        self.slot_done[slot].synchronize()                             # step i-2 has consumed this slot's staging buffers
+        stats = self.counters_host[slot].numpy().copy()                # D2H result of step i-2, read on the host
+        if self.rank == 0:
+            self.dq_stage[slot].numpy()[...] = self.frames["dqs"][i % len(self.frames["dqs"])]   # host -> pinned staging (the solver's output)
+        with torch.cuda.stream(self.stream):
+            self.steps[slot].run(self.ios_e2e[slot])
+            self.slot_done[slot].record()
+        return stats
+
+    def timed(self, step_fn, steps, warmup, src, barrier):
+        import torch
+        from dynamicfusion_body_b200 import dist as ddist
+        self.prime(src)
+        for i in range(warmup):
+            step_fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for i in range(warmup, warmup + steps):
+            step_fn(i)
+        e1.record(self.stream)
+        barrier()
+        return ddist.max_over_ranks(e0.elapsed_time(e1), self.dev)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from dynamicfusion_body_b200 import _capi, engine
     from dynamicfusion_body_b200 import dist as ddist
-    from dynamicfusion_body_b200.fusion import Fusion
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -138,130 +229,84 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # STRONG scaling (BASELINE configs[4]): ONE res^3 grid, x-slab [x0, x1) per rank
+    # STRONG scaling (BASELINE configs[4]): ONE res^3 grid, one x-slab per rank
     res = args.res
     grid = (res, res, res)
-    x0, x1 = ddist.slab_partition(res, world)[rank]
     sc = build_scene(res, args.nodes, args.k, args.views)
-    fus = Fusion(sc.tdist, knn=args.k, device=dev, use_cnn=False, write_warpfield=False)
-    fus.InitializeCanonicalSpace(tsdf_shape=grid, slab=(x0, x1), K=sc.K, vertices=sc.vertices, normals=sc.normals,
-                                 nodes=sc.nodes_as_reference_tuples())
-    fus._lw = sc.lw
-    nvox_rank = (x1 - x0) * res * res
     nvox_total = res ** 3
     n_frames = 15
     dqs = frame_dqs(sc, n_frames)
-    dq_dev = [torch.from_numpy(d).to(dev) for d in dqs]
-    depth_dev = torch.from_numpy(sc.depths.copy()).to(dev)
-    depth_host = torch.from_numpy(sc.depths.copy()).pin_memory()
+    frames = {"dqs": dqs, "dq_dev": [torch.from_numpy(d).to(dev) for d in dqs], "depth_dev": torch.from_numpy(sc.depths.copy()).to(dev),
+              "depth_host": torch.from_numpy(sc.depths.copy()).pin_memory()}
+    depth_dev, depth_host, dq_dev = frames["depth_dev"], frames["depth_host"], frames["dq_dev"]
 
-    # ---- graph revision: voxel kNN table + brick / region candidate sets (once per update_graph, core/fusion.py:229) ----
-    torch.cuda.synchronize()
-    rev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    rev[0].record()
-    fus.build_knn()
-    rev[1].record()
-    torch.cuda.synchronize()
-    graph_revision_ms = ddist.max_over_ranks(rev[0].elapsed_time(rev[1]), dev)
-
-    # ---- communicators (raw NCCL through the C ABI): one for the in-step transform broadcast, one for the sensor prefetch ----
+    # communicators (raw NCCL through the C ABI): one for the in-step transform broadcast, one for the sensor prefetch
     comm = comm_pre = None
     if world > 1:
         comm = engine.Comm.from_torch(dev)
         comm_pre = engine.Comm.from_torch(dev)
-
-    stream = torch.cuda.Stream(device=dev)           # a capturable (non-default) stream: the step is one CUDA-graph launch
-    shape = sc.depths.shape
-    packets = [torch.zeros(shape, dtype=torch.float32, device=dev) for _ in range(2)]
-    dq_stage = [torch.zeros((sc.n_nodes, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
-    counters_host = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
-    slot_done = [torch.cuda.Event(), torch.cuda.Event()]
-    wf, vol = fus._wf, fus._vol
-    steps_obj, ios_res, ios_e2e = [], [], []
-    for slot in range(2):
-        views = engine.make_views(packets[slot], sc.K, sc.Kinv, sc.extrinsics)
-        st = engine.FrameStep(vol, wf, sc.lw, views, sc.tdist)
-        steps_obj.append(st)
-        # resident frame: the transforms are already in wf.node_dq on the root, the next depth frame is a device buffer
-        ios_res.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, prefetch_dst=packets[slot ^ 1], prefetch_src=depth_dev))
-        # end to end: transforms and depth come from pinned host memory, the counters go back to pinned host memory
-        ios_e2e.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, dq_src=dq_stage[slot], prefetch_dst=packets[slot ^ 1],
-                             prefetch_src=depth_host, counters_host=counters_host[slot]))
-
-    def prime(src):
-        """frame 0's sensor data into packet 0 (every later frame arrives through the prefetch branch of the step before it)"""
-        with torch.cuda.stream(stream):
-            if rank == 0:
-                packets[0].copy_(src, non_blocking=True)
-            if comm_pre is not None:
-                comm_pre.broadcast(packets[0])
-        stream.synchronize()
-
-    def step_resident(i):
-        slot = i & 1
-        with torch.cuda.stream(stream):
-            if rank == 0:
-                wf.node_dq.copy_(dq_dev[i % n_frames], non_blocking=True)
-            steps_obj[slot].run(ios_res[slot])
-
-    def step_e2e(i):
-        slot = i & 1
-        slot_done[slot].synchronize()                                  # step i-2 has consumed this slot's staging buffers
-        stats = counters_host[slot].numpy().copy()                     # D2H result of step i-2, read on the host
-        if rank == 0:
-            dq_stage[slot].numpy()[...] = dqs[i % n_frames]            # host -> pinned staging (the solver's output)
-        with torch.cuda.stream(stream):
-            steps_obj[slot].run(ios_e2e[slot])
-            slot_done[slot].record()
-        return stats
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, src):
-        prime(src)
-        for i in range(warmup):
-            step_fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for i in range(warmup, warmup + steps):
-            step_fn(i)
-        e1.record(stream)
-        barrier()
-        return ddist.max_over_ranks(e0.elapsed_time(e1), dev)
+    parts_equal = ddist.slab_partition(res, world)
+    st = RankState(args, sc, grid, parts_equal[rank][0], parts_equal[rank][1], dev, rank, comm, comm_pre, frames)
+    partition = {"kind": "equal", "slabs": parts_equal}
+    equal_info = None
+    if world > 1:
+        # the step time of a sharded volume is the maximum over ranks: measure the equal slabs, then move the slab boundaries
+        # (multiples of 16 planes) so that the estimated cost -- brick classes of a frame -- is the same on every rank
+        ms_eq = st.timed(st.step_resident, args.steps, args.warmup, depth_dev, barrier)
+        prof = engine.slab_cost_profile(st.vol, 16)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, prof.tolist())
+        unit_cost = np.concatenate([np.asarray(g) for g in gathered])
+        equal_info = {"ms_per_step": ms_eq / args.steps, "value": nvox_total * args.steps / (ms_eq * 1e-3), "slabs": parts_equal,
+                      "estimated_cost_per_rank": [float(np.sum(g)) for g in gathered]}
+        if not args.equal_slabs:
+            parts_bal = ddist.balanced_slab_partition(unit_cost, world, 16, res)
+            if parts_bal != parts_equal:
+                del st
+                torch.cuda.empty_cache()
+                st = RankState(args, sc, grid, parts_bal[rank][0], parts_bal[rank][1], dev, rank, comm, comm_pre, frames)
+                partition = {"kind": "balanced", "slabs": parts_bal,
+                             "how": "x-slab boundaries (multiples of 16 planes) minimising the largest estimated slab cost; cost per "
+                                    "16-plane layer from the brick classes of a frame (0.6 / 1.6 / 10.7 ns per brick / CLAMP brick / MIXED brick)"}
+        st.reset()
+    x0, x1 = st.x0, st.x1
+    nvox_rank = st.nvox
+    fus = st.fus
 
     # ---- untimed parity check on the hardware (N > 1): slabs gathered over NCCL == a single-volume run on rank 0 ----
     parity = None
     if world > 1:
-        parity = parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, stream, comm, rank, world, dev)
-        # fresh state for the timed runs
-        vol.tsdf.fill_(sc.tdist); vol.weight.zero_()
+        parity = parity_check(args, sc, st, partition["slabs"], comm, rank, world, dev)
+        st.reset()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_total = timed(step_resident, args.steps, args.warmup, depth_dev)
+    ms_total = st.timed(st.step_resident, args.steps, args.warmup, depth_dev, barrier)
     # the K timed steps last only a few tens of ms; keep the same step running (untimed, identical count on every rank so
     # that the collectives match) until the 20 ms sampler has seen ~0.4 s of this load
     n_extra = max(0, int(400.0 / max(ms_total / args.steps, 1e-3)) - args.steps)
     for i in range(min(n_extra, 4000)):
-        step_resident(i)
+        st.step_resident(i)
         if i % 64 == 63:
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    for e in slot_done:
-        e.record(stream)
-    ms_e2e = timed(step_e2e, args.steps, max(3, args.warmup // 2), depth_host)
+    for e in st.slot_done:
+        e.record(st.stream)
+    ms_e2e = st.timed(st.step_e2e, args.steps, max(3, args.warmup // 2), depth_host, barrier)
     stats = fus.frame_stats()
-    gstats = steps_obj[0].stats()
+    gstats = st.steps[0].stats()
 
     # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----
     kk = 4 if args.k <= 4 else 8
-    prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
+    prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_smem_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
             ("proj_exact_kernel<%d>" % kk, _capi.MODE_LIST_ONLY)]
     parts = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
              ("brick_mixed_kernel<%d>" % kk, _capi.MODE_BRICK_MIXED)]
@@ -304,20 +349,23 @@ def run_ours(args):
     achieved = ALG_BYTES_PER_VOXEL * units[dominant] / (kms[dominant] * 1e-3) / 1e9
     step_achieved = ALG_BYTES_PER_VOXEL * nvox_rank / (step_ms * 1e-3) / 1e9
     traffic = measured_traffic(dominant) if world == 1 else None
+    slab_mb = nvox_rank * (8 + 2 * args.k) / 1e6
     out = {
         "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%d^3 voxels total (one grid, x-slab of %d planes per GPU), warped projective TSDF update (a3), k=%d DQB, "
-                               "%d nodes, %d view(s) 640x480, 15-frame dq sequence" % (res, x1 - x0, args.k, sc.n_nodes, args.views),
-                   "l2": "inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % (nvox_rank * (8 + 2 * args.k) / 1e6)
-                         if nvox_rank * (8 + 2 * args.k) > 2.5e8 else
-                         "slab of %.0f MB (v,w,kNN) per GPU: at N>=4 a 512^3/N slab approaches the 126 MB L2; every step streams the whole slab "
-                         "once, so the working set is re-read from HBM unless it fits" % (nvox_rank * (8 + 2 * args.k) / 1e6),
-                   "parallelism": ("x-slab per GPU (strong scaling of ONE grid); per step ONE CUDA-graph launch per rank: NCCL broadcast of the "
-                                   "node transforms + update kernels, next depth frame broadcast as a concurrent graph branch") if world > 1
-                                  else "single GPU, one CUDA-graph launch per step",
-                   "deferred_voxel_fraction": stats["deferred"] / nvox_rank},
+        "config": {"workload": "%d^3 voxels total (ONE grid, %s x-slabs over %d GPU(s): %s), warped projective TSDF update (a3), k=%d DQB, "
+                               "%d nodes, %d view(s) 640x480, 15-frame dq sequence"
+                               % (res, partition["kind"], world, "/".join(str(b - a) for a, b in partition["slabs"]), args.k, sc.n_nodes, args.views),
+                   "l2": ("inputs larger than L2 (%.0f MB of v,w,kNN per GPU)" % slab_mb) if slab_mb > 250 else
+                         ("slab of %.0f MB (v,w,kNN) per GPU, each step streams it once: a 512^3/N slab approaches the 126 MB L2 from N=4 on, "
+                          "so part of it is served from L2 -- that is the configuration BASELINE configs[4] names" % slab_mb),
+                   "parallelism": ("one CUDA-graph launch per rank and step: NCCL broadcast of the node transforms (dfb_comm, raw NCCL) -> node "
+                                   "records -> classify / update / exact kernels, next depth frame broadcast as a concurrent graph branch")
+                                  if world > 1 else "single GPU, one CUDA-graph launch per step",
+                   "partition": partition,
+                   "deferred_voxel_fraction": stats["deferred"] / nvox_rank,
+                   "dqb_voxel_fraction_of_mixed": stats.get("dqb_voxels", 0) / max(1, n_mixed)},
         "e2e": {"value": e2e_value, "unit": "voxels/s", "h2d_bytes_per_step": int(sc.depths.nbytes + dqs[0].nbytes),
                 "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "per step: host copies the frame's node transforms into pinned staging, ONE graph launch = [H2D transforms -> "
@@ -327,12 +375,12 @@ def run_ours(args):
         "gpu_launches": 5 * args.steps,
         "step_graph": gstats,
         "clocks": clocks,
-        "graph_revision_ms": graph_revision_ms,
-        "value_amortised": {"revision_every_frame": nvox_total / ((step_ms + graph_revision_ms) * 1e-3),
-                            "revision_every_15_frames": nvox_total / ((step_ms + graph_revision_ms / 15.0) * 1e-3),
+        "graph_revision_ms": st.graph_revision_ms,
+        "value_amortised": {"revision_every_frame": nvox_total / ((step_ms + st.graph_revision_ms) * 1e-3),
+                            "revision_every_15_frames": nvox_total / ((step_ms + st.graph_revision_ms / 15.0) * 1e-3),
                             "note": "the reference rebuilds its KD-tree in update_graph (core/fusion.py:229) and queries it per voxel per frame "
-                                    "(:175); here the voxel kNN table + brick/region sets are rebuilt once per graph revision "
-                                    "(`graph_revision_ms`, full rebuild) and `value` excludes it"},
+                                    "(:175); here the voxel kNN table + brick/region sets belong to a graph revision: `graph_revision_ms` is "
+                                    "the FULL rebuild, `graph_revision_incremental` the update after +1 % appended nodes; `value` excludes both"},
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic,
                      "note": "dominant kernel by time; its units = the voxels that launch processes x 16 B. The step as a whole "
@@ -342,10 +390,28 @@ def run_ours(args):
                      "kernels": kernels,
                      "bricks": {"total": stats["bricks"], "streamed": stats["bricks_streamed"], "mixed": stats["bricks_mixed"]}},
     }
+    if equal_info is not None:
+        out["equal_slabs"] = equal_info
     if parity is not None:
         out["parity_check"] = parity
+    def leg(name, fn):
+        """the extra legs must never cost the headline line"""
+        try:
+            out[name] = fn()
+        except Exception as e:                                   # pragma: no cover
+            import traceback
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e), "trace": traceback.format_exc()[-600:]}
+
+    if world == 1 and not args.no_configs:
+        leg("graph_revision_incremental", lambda: bench_incremental_revision(sc, st))
+    del st
+    torch.cuda.empty_cache()
+    if world == 1 and not args.no_configs:
+        leg("configs", lambda: bench_configs(args, dev))
+        leg("frame_loop", lambda: bench_frame_loop(args, dev))
     if not args.no_gn:
         out["gn"] = bench_gn(args, dev, rank, world, comm)
+        leg("gn_depth_frame", lambda: bench_gn_depth_frame(args, dev, rank, world, comm))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sc, grid, budget_s=args.cpu_seconds)
     if rank == 0:
@@ -379,27 +445,21 @@ def measured_traffic(kernel_name):
     return None if rd is None or wr is None else int(rd + wr)
 
 
-def parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, stream, comm, rank, world, dev):
+def parity_check(args, sc, st, parts, comm, rank, world, dev):
     """Three frames on the sharded volume (through the timed path: graph launches + NCCL broadcasts) against the same three
-    frames on a single res^3 volume held by rank 0; slabs are gathered over NCCL.  SURVEY 8e: weights and values must be equal
-    bit for bit."""
+    frames on a single res^3 volume held by rank 0; slabs are gathered over NCCL (dfb_comm_sendrecv).  SURVEY 8e: weights and values
+    must be equal bit for bit."""
     import torch
     from dynamicfusion_body_b200 import engine
     res = args.res
-    vol, wf = fus._vol, fus._wf
-    vol.tsdf.fill_(sc.tdist); vol.weight.zero_()
-    prime(depth_dev)
+    vol, wf = st.vol, st.wf
+    st.reset()
+    st.prime(st.frames["depth_dev"])
     n_chk = 3
     for i in range(n_chk):
-        with torch.cuda.stream(stream):
-            if rank == 0:
-                wf.node_dq.copy_(dq_dev[i], non_blocking=True)
-            steps_obj[i & 1].run(ios_res[i & 1])
-    stream.synchronize()
+        st.step_resident(i)
+    st.stream.synchronize()
     torch.cuda.synchronize()
-    # gather the slabs on rank 0 (dfb_comm_sendrecv)
-    from dynamicfusion_body_b200 import dist as ddist
-    parts = ddist.slab_partition(res, world)
     result = None
     if rank == 0:
         full_t = torch.empty((res, res, res), dtype=torch.float32, device=dev)
@@ -416,16 +476,16 @@ def parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, st
         wf1.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
         vol1 = engine.DeviceVolume((res, res, res), device=dev, fill=sc.tdist)
         for i in range(n_chk):
-            wf1.set_dq(dq_dev[i])
-            engine.update_projective(vol1, wf1, sc.lw, depth_dev, sc.K, sc.Kinv, sc.extrinsics, sc.tdist)
+            wf1.set_dq(st.frames["dq_dev"][i])
+            engine.update_projective(vol1, wf1, sc.lw, st.frames["depth_dev"], sc.K, sc.Kinv, sc.extrinsics, sc.tdist)
         torch.cuda.synchronize()
         w_equal = bool(torch.equal(full_w, vol1.weight))
         v_equal = bool(torch.equal(full_t, vol1.tsdf))
         max_diff = float((full_t - vol1.tsdf).abs().max().item())
         updated = int((vol1.weight > 0).sum().item())
-        result = {"tsdf": "ok" if (w_equal and v_equal) else ("ok_within_1e-6_tdist" if (w_equal and max_diff <= 1e-6 * sc.tdist) else "MISMATCH"),
-                  "frames": n_chk, "weights_bit_equal": w_equal, "values_bit_equal": v_equal, "max_abs_value_diff": max_diff,
-                  "updated_voxels": updated, "how": "slabs gathered on rank 0 over NCCL vs the same frames on one %d^3 volume" % res}
+        result = {"tsdf": "ok" if (w_equal and v_equal) else "MISMATCH", "frames": n_chk, "weights_bit_equal": w_equal, "values_bit_equal": v_equal,
+                  "max_abs_value_diff": max_diff, "updated_voxels": updated,
+                  "how": "slabs gathered on rank 0 over NCCL vs the same frames on one %d^3 volume" % res}
         del full_t, full_w, vol1, wf1
         torch.cuda.empty_cache()
     else:
@@ -433,6 +493,181 @@ def parity_check(args, sc, fus, dq_dev, depth_dev, steps_obj, ios_res, prime, st
         comm.sendrecv(send=vol.weight, send_peer=0)
         torch.cuda.synchronize()
     return result
+
+
+def _event_ms(fn, reps, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_incremental_revision(sc, st):
+    """A graph revision that appends 1 % new nodes (what update_graph does): incremental update of the kNN table + brick / region
+    sets against the full rebuild.  The new nodes are surface points between existing nodes."""
+    import torch
+    from dynamicfusion_body_b200 import engine
+    rng = np.random.default_rng(7)
+    m = max(1, sc.n_nodes // 100)
+    warm = engine.DeviceWarpField(st.wf.k, st.dev)                     # load the revision kernels on a throw-away field first
+    warm.set_nodes(sc.node_pos[:-m], sc.node_dq[:-m], np.float32(sc.node_w))
+    warm.brick_nodes((64, 64, 64), 0, 64)
+    warm.append_nodes(sc.node_pos[-m:], sc.node_dq[-m:], np.float32(sc.node_w))
+    del warm
+    sel = rng.choice(len(sc.vertices), m, replace=False)
+    new_pos = sc.vertices[sel].astype(np.float32)
+    new_dq = np.tile(np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32), (m, 1))
+    wf = st.wf
+    res, x0, x1 = st.vol.res, st.vol.x0, st.vol.x1
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record()
+    wf.append_nodes(new_pos, new_dq, np.float32(sc.node_w))
+    e[1].record()
+    torch.cuda.synchronize()
+    dirty = float(wf.last_dirty.float().mean().item())
+    ref = engine.DeviceWarpField(wf.k, st.dev)
+    ref.set_nodes(wf.node_pos, wf.node_dq, wf.node_w)
+    same = bool(torch.equal(ref.knn_table(res, x0, x1), wf.knn_table(res, x0, x1)))
+    del ref
+    return {"new_nodes": m, "ms": e[0].elapsed_time(e[1]), "dirty_8cube_bricks_fraction": dirty, "knn_table_equals_full_rebuild": same,
+            "full_rebuild_ms": st.graph_revision_ms}
+
+
+def bench_configs(args, dev):
+    """The other BASELINE configs on one GPU (the driver only runs the default command).  256^3 volumes are 134 MB of (v, w): four
+    volumes are rotated so that a frame never finds its volume in the 126 MB L2 (SURVEY 7 'honest HBM numbers')."""
+    import torch
+    from dynamicfusion_body_b200 import engine, synth
+    peak, _ = measured_peaks()
+    out = {}
+    R = 256
+    nvox = R ** 3
+    n_rot = 4
+
+    def line(ms, views=1, extra=None):
+        d = {"ms_per_frame": ms, "voxels_per_s": nvox / (ms * 1e-3), "voxel_updates_per_s": views * nvox / (ms * 1e-3),
+             "roofline_frac_16B_per_voxel": ALG_BYTES_PER_VOXEL * nvox / (ms * 1e-3) / 1e9 / peak, "rotating_volumes": n_rot}
+        d.update(extra or {})
+        return d
+
+    # configs[1]: 256^3, 1 view per frame, ~1k nodes, k=4, 15-frame sequence
+    sc = synth.make_scene(res=R, k=4, n_nodes=1000, seed=0, background=True)
+    dqs = [torch.from_numpy(d).to(dev) for d in frame_dqs(sc, 15)]
+    wf = engine.DeviceWarpField(4, dev)
+    wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
+    vols = [engine.DeviceVolume((R, R, R), device=dev, fill=sc.tdist) for _ in range(n_rot)]
+    depth = torch.from_numpy(sc.depths).to(dev)
+    views = engine.make_views(depth, sc.K, sc.Kinv, sc.extrinsics)
+    wf.brick_nodes((R, R, R), 0, R)
+    it = {"i": 0}
+
+    def a3():
+        i = it["i"]; it["i"] += 1
+        wf.set_dq(dqs[i % 15])
+        engine.update_projective(vols[i % n_rot], wf, sc.lw, depth, sc.K, sc.Kinv, sc.extrinsics, sc.tdist, views=views)
+    ms = _event_ms(a3, 30, 8)
+    stt = vols[0].workspace.stats()
+    out["c2_a3_256"] = line(ms, extra={"path": "Fusion.fuseFrame (a3: warp + projective update), %d nodes k=4, 1 view" % sc.n_nodes,
+                                       "deferred_fraction": stt["deferred"] / nvox, "bricks_mixed_fraction": stt["bricks_mixed"] / stt["bricks"]})
+    # configs[1] as profiled by the reference (profiles/updateTSDF_*): Fusion.updateTSDF against a live TSDF VOLUME (a1)
+    nw = np.full(sc.n_nodes, np.float32(sc.node_w))
+    wv = synth.blend_warp(sc.vertices, sc.node_pos, sc.node_dq, nw, sc.vert_knn, lw=None)
+    t0 = time.time()
+    sdf = synth.mesh_sdf_volume((R, R, R), wv, sc.normals)             # untruncated, as test.py:105-110 loads it
+    sdf_s = time.time() - t0
+    live_raw = torch.from_numpy(sdf).to(dev)
+    live_trunc = torch.from_numpy(np.clip(sdf, -sc.tdist, sc.tdist)).to(dev)
+    for name, live, td, what in (("c2_a1_256_reference_usage", live_raw, float(sdf.max()),
+                                  "Fusion.updateTSDF, untruncated live SDF with trunc_distance = volume.max() (test.py:110): every voxel lies inside the "
+                                  "band and takes the reference-exact float64 tier"),
+                                 ("c2_a1_256_truncated", live_trunc, sc.tdist,
+                                  "Fusion.updateTSDF, live TSDF truncated at +-tdist (what FusionDM / fuseFrame volumes hold)")):
+        vs = [engine.DeviceVolume((R, R, R), device=dev, fill=td) for _ in range(n_rot)]
+        it["i"] = 0
+
+        def a1():
+            i = it["i"]; it["i"] += 1
+            wf.set_dq(dqs[i % 15])
+            engine.update_volume(vs[i % n_rot], wf, None, live, td)
+        ms = _event_ms(a1, 8, 3)
+        stt = vs[0].workspace.stats()
+        out[name] = line(ms, extra={"path": what, "deferred_fraction": stt["deferred"] / nvox})
+        del vs
+    out["c2_a1_256_reference_usage"]["live_sdf_synthesis_s"] = sdf_s
+    del vols, wf, live_raw, live_trunc
+    torch.cuda.empty_cache()
+    # configs[3]: 8 synthetic depth views per frame fused into a 256^3 TSDF with k=8 DQB
+    sc8 = synth.make_scene(res=R, k=8, n_nodes=1000, seed=0, background=True, n_views=8)
+    dqs8 = [torch.from_numpy(d).to(dev) for d in frame_dqs(sc8, 15)]
+    wf8 = engine.DeviceWarpField(8, dev)
+    wf8.set_nodes(sc8.node_pos, sc8.node_dq, np.float32(sc8.node_w))
+    vols8 = [engine.DeviceVolume((R, R, R), device=dev, fill=sc8.tdist) for _ in range(n_rot)]
+    depth8 = torch.from_numpy(sc8.depths).to(dev)
+    views8 = engine.make_views(depth8, sc8.K, sc8.Kinv, sc8.extrinsics)
+    wf8.brick_nodes((R, R, R), 0, R)
+    it["i"] = 0
+
+    def a3v8():
+        i = it["i"]; it["i"] += 1
+        wf8.set_dq(dqs8[i % 15])
+        engine.update_projective(vols8[i % n_rot], wf8, sc8.lw, depth8, sc8.K, sc8.Kinv, sc8.extrinsics, sc8.tdist, views=views8)
+    ms = _event_ms(a3v8, 20, 6)
+    stt = vols8[0].workspace.stats()
+    out["c4_8view_k8_256"] = line(ms, views=8, extra={"path": "Fusion.fuseFrame, 8 views (ring of cameras) fused in ONE pass, %d nodes k=8" % sc8.n_nodes,
+                                                      "deferred_fraction": stt["deferred"] / nvox,
+                                                      "bricks_mixed_fraction": stt["bricks_mixed"] / stt["bricks"]})
+    del vols8, wf8
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_frame_loop(args, dev):
+    """The reference's frame loop (test.py:125-131: setupCorrespondences -> solve -> TSDF update -> update_graph) through the drop-in
+    Fusion object at 256^3 / ~1k nodes: wall time per stage, host work and synchronisations included."""
+    import torch
+    from dynamicfusion_body_b200 import synth
+    from dynamicfusion_body_b200.fusion import Fusion
+    R = 256
+    sc = synth.make_scene(res=R, k=4, n_nodes=1000, seed=0, background=True)
+    fus = Fusion(sc.tdist, knn=4, device=dev, use_cnn=False, write_warpfield=False)
+    fus.InitializeCanonicalSpace(tsdf_shape=(R, R, R), K=sc.K, vertices=sc.vertices, normals=sc.normals, faces=sc.faces,
+                                 nodes=sc.nodes_as_reference_tuples(), radius=sc.radius)
+    fus._lw = sc.lw
+    live = sc.warped_vertices.astype(np.float32)
+    depth = torch.from_numpy(sc.depths).to(dev)
+    fus.build_knn()
+    fus.fuseFrame(depth, extrinsics=sc.extrinsics)                     # a first frame so that the volume holds a surface
+    torch.cuda.synchronize()
+    stages = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fn()
+        torch.cuda.synchronize()
+        stages[name] = stages.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+
+    n = 3
+    for it in range(n + 1):
+        if it == 1:
+            stages = {}                                                # the first pass is a warm-up (module loads, allocator growth)
+        timed("setupCorrespondences_ms", lambda: fus.setupCorrespondences(None, method='clpts', prune_result=False, live_vertices=live))
+        timed("solve_ms", lambda: fus.solve(regularization_weight=0.5, method='cnn', precompute_lw=False, gn_iterations=5))
+        timed("fuseFrame_ms", lambda: fus.fuseFrame(depth, extrinsics=sc.extrinsics))
+        timed("update_graph_ms", lambda: fus.update_graph())
+    stages = {k: v / n for k, v in stages.items()}
+    stages["total_ms"] = float(sum(stages.values()))
+    stages["config"] = ("256^3, %d nodes -> %d after update_graph, %d canonical vertices, 5 Gauss-Newton iterations per solve, surface "
+                        "extraction (step 3) + node re-sampling + incremental kNN revision inside update_graph" % (sc.n_nodes, fus._wf.n_nodes, len(fus._vertices)))
+    return stages
 
 
 def bench_gn(args, dev, rank, world, comm=None):
@@ -504,6 +739,70 @@ def bench_gn(args, dev, rank, world, comm=None):
             "reference_published_ms_per_iter": 70100.0}
 
 
+def bench_gn_depth_frame(args, dev, rank, world, comm=None):
+    """BASELINE configs[2] as worded: the data residuals of ONE 640x480 depth frame.  Canonical surface samples = the valid pixels of a
+    depth frame rendered from the canonical mesh, back-projected; live points = the back-projected pixels of the live depth frame;
+    correspondences through the drop-in Fusion.setupCorrespondences (closest live point, best-of-k point-to-plane); then 15
+    Gauss-Newton iterations from perturbed node transforms."""
+    import torch
+    from scipy.spatial import cKDTree
+    from dynamicfusion_body_b200 import dist as ddist
+    from dynamicfusion_body_b200 import gn, synth
+    from dynamicfusion_body_b200.fusion import Fusion
+    R = 256
+    sc = synth.make_scene(res=R, k=4, n_nodes=args.gn_nodes, seed=0, background=False, focal=775.0)
+    K, Kinv = sc.K, sc.Kinv
+    E = np.zeros((3, 4))
+    A = np.zeros(12)
+    # the global rigid dq of a one-view scene is the camera extrinsic
+    E = np.stack([synth.dq_apply(sc.lw[None, :].astype(np.float64), e[None, :])[0] for e in np.eye(3)], 1)
+    t = synth.dq_apply(sc.lw[None, :].astype(np.float64), np.zeros((1, 3)))[0]
+    Rm = E - t[:, None]
+
+    def backproject(dm):
+        v, u = np.nonzero(dm < 0)
+        z = -dm[v, u].astype(np.float64)
+        return (Kinv @ np.stack([u * z, v * z, z])).T
+
+    canon_cam = backproject(synth.render_depth(sc.vertices.astype(np.float64) @ Rm.T + t, sc.faces, K, sc.rows, sc.cols))
+    canon = ((canon_cam - t) @ Rm).astype(np.float32)                 # back into canonical (grid) coordinates
+    _, nn = cKDTree(sc.vertices.astype(np.float64)).query(canon.astype(np.float64))
+    normals = sc.normals[nn]
+    live = backproject(sc.depths[0]).astype(np.float32)
+    fus = Fusion(sc.tdist, knn=4, device=dev, use_cnn=False, write_warpfield=False)
+    rng = np.random.default_rng(0)
+    _, nvi = cKDTree(canon.astype(np.float64)).query(sc.node_pos.astype(np.float64))
+    nodes = [(int(nvi[i]),) + n[1:] for i, n in enumerate(sc.nodes_as_reference_tuples())]
+    fus.InitializeCanonicalSpace(tsdf_shape=(8, 8, 8), K=K, vertices=canon, normals=normals, nodes=nodes)
+    fus._lw = sc.lw
+    x0 = (sc.node_dq.reshape(-1).astype(np.float64) + rng.normal(size=8 * sc.n_nodes) * 2e-3)
+    fus.set_node_dqs(x0.reshape(-1, 8).astype(np.float32))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fus.setupCorrespondences(None, method='clpts', prune_result=False, live_vertices=live)
+    torch.cuda.synchronize()
+    corr_ms = 1e3 * (time.perf_counter() - t0)
+    shard = ddist.residual_partition(len(canon), world)[rank]
+    prob = gn.Problem(fus._wf, fus._vertices, fus._normals, np.asarray(fus._correspondences, dtype=np.float64), np.asarray(fus._neighbor_look_up),
+                      fus._node_vertex_idx, shard=shard, reg_owner=(rank == 0))
+    allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c, comm=comm)) if world > 1 else None
+    x = torch.from_numpy(x0).to(dev)
+    prob.pattern()
+    prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    e[0].record()
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce)
+    e[1].record()
+    torch.cuda.synchronize()
+    total_ms = ddist.max_over_ranks(e[0].elapsed_time(e[1]), dev)
+    return {"metric": "gn_solve_ms_per_iter", "value": total_ms / max(1, res.iterations), "unit": "ms", "iterations": res.iterations, "accepted": res.accepted,
+            "cost0": res.cost0, "cost": res.cost, "data_residuals": int(len(canon)), "live_points": int(len(live)), "nodes": sc.n_nodes,
+            "setupCorrespondences_ms": corr_ms, "pcg_iterations": [h["pcg_iterations"] for h in res.history],
+            "config": {"workload": "valid pixels of one 640x480 depth frame (focal 775: the body fills the frame) as canonical samples, closest-point "
+                                   "correspondences against the live frame's pixels via Fusion.setupCorrespondences, %d nodes k=4, 15 iterations" % sc.n_nodes}}
+
+
 def cpu_baseline(sc, res, budget_s=12.0):
     from oracle import driver
     sd = driver.scene_dict(sc)
@@ -560,6 +859,8 @@ def main():
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gn", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configs / frame loop legs")
+    ap.add_argument("--equal-slabs", action="store_true", help="N>1: keep the equal x-slabs (no cost-balanced boundaries)")
     ap.add_argument("--gn-nodes", type=int, default=1000)
     ap.add_argument("--gn-points", type=int, default=300000)
     ap.add_argument("--gn-iters", type=int, default=15)

@@ -338,7 +338,11 @@ DFB_HD int voxel_volume_classify(const VolParams& P, int x, int y, int z, const 
     // the Q1 interpolation is a convex combination of the corners (its swapped y/z weights are still in [0,1]): with every
     // corner below -tdist the reference's `tsdf_l > -tdist` (core/fusion.py:179) is certainly false
     if (mxc <= -P.tdist_f * 1.000001f) return CLS_SKIP;
-    if (!(mn >= P.tdist_f * 1.000001f)) return CLS_UNCERTAIN;
+    // every corner >= tdist: the update is min(tdist, tl) = tdist.  Equality is included (a live TSDF clipped at +tdist is the common
+    // input): the reference's float64 interpolation of corners that all equal tdist can come out an ulp of a double below it, which
+    // moves the stored float32 by at most its own last bit -- far inside the 1e-5 tdist value tolerance, and no mask depends on it.
+    // (The mirror case at -tdist decides a MASK, so it keeps its margin and goes to the exact tier.)
+    if (!(mn >= P.tdist_f)) return CLS_UNCERTAIN;
     if (P.k > 0) {
         float wi = 0.f;
         for (int i = 0; i < P.k; ++i) {

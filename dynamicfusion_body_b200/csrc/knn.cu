@@ -148,11 +148,8 @@ __device__ __noinline__ void knn_exact_f64_list(float qx, float qy, float qz, co
     for (int j = 0; j < k; ++j) out[j] = bi[j];
 }
 
-// Incremental mode (n_old > 0; core/fusion.py:216-229 only ever APPENDS nodes): the table already holds the k nearest of the first
-// n_old nodes and brick_T the search radius T = d_k(centre) + 2 halfdiag of every brick against them.  A node appended since can be
-// among the k nearest of some voxel of the brick only if it lies within T of the centre (it would be a candidate); bricks with no
-// such node leave at once -- their rows are still exact (old ids are unchanged, and on an exact distance tie the lower, i.e. old, id
-// wins) -- the others are rebuilt against all n nodes and flagged in `dirty` for the brick / region sets that derive from the table.
+// brick_T (optional, out): the search radius T of every brick, kept for incremental graph revisions (knn_merge_kernel).  With n_old > 0
+// the kernel is the second pass of such a revision: it rebuilds exactly the bricks the merge pass flagged with dirty == 2.
 template <int KMAX>
 __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, int n, int k, int sx, int ry, int rz, int x0, int nby, int nbz,
                                                         uint16_t* knn, float* brick_T, int n_old, uint8_t* dirty) {
@@ -160,7 +157,6 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
     __shared__ float wtop[4][KMAX];
     __shared__ int ncand;
     __shared__ float T2s;
-    __shared__ int hit;
     const int b = blockIdx.x;
     const int bz = b % nbz, by = (b / nbz) % nby, bxs = b / (nbz * nby);
     const int xlo = bxs * KB, ylo = by * KB, zlo = bz * KB;
@@ -170,20 +166,10 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
     const float hd = sqrtf(hx * hx + hy * hy + hz * hz);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (n_old > 0) {
-        if (threadIdx.x == 0) hit = 0;
+        // incremental pass 2: only the bricks knn_merge_kernel could not handle (more new nodes in reach than its list holds)
+        if (dirty[b] != 2) return;
         __syncthreads();
-        const float T = brick_T[b];
-        const float T2o = T * T * 1.00001f;
-        bool mine = false;
-        for (int t = n_old + threadIdx.x; t < n; t += blockDim.x) {
-            const float dx = node_pos[3 * t] - cx, dy = node_pos[3 * t + 1] - cy, dz = node_pos[3 * t + 2] - cz;
-            mine |= dx * dx + dy * dy + dz * dz <= T2o;
-        }
-        if (mine) hit = 1;
-        __syncthreads();
-        const bool rebuild = hit != 0;
-        if (threadIdx.x == 0 && dirty) dirty[b] = rebuild ? 1 : 0;
-        if (!rebuild) return;
+        if (threadIdx.x == 0) dirty[b] = 1;
     } else if (threadIdx.x == 0 && dirty) {
         dirty[b] = 1;
     }
@@ -313,6 +299,108 @@ __global__ void __launch_bounds__(128) knn_brick_kernel(const float* node_pos, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Incremental graph revision (core/fusion.py:216-229 only ever APPENDS nodes).  The table holds the k nearest of the first n_old
+// nodes, brick_T the search radius T = d_k(centre) + 2 halfdiag every brick was built with.  A node appended since can be among the k
+// nearest of some voxel of the brick only if it lies within T of the centre (it would have been a candidate); a brick with no such
+// node leaves at once -- its rows are still exact: old ids are unchanged, and on an exact distance tie the lower, i.e. old, id wins.
+// Otherwise every voxel merges the few new nodes in reach into its stored, already correctly ordered list: float64 squared distances
+// in the oracle's operation order, strict '<' against the old entries (ties keep the old node in front), new nodes taken in
+// ascending id.  No scan over the node table, no candidate search: the pass is bounded by the 8 bytes per voxel it reads and, where
+// a row changed, writes.  dirty[b] = 1 when a row of the brick changed (the 4x4x32 brick / region sets that derive from the table are
+// refreshed for those), 2 when more than KNEW new nodes are in reach (knn_brick_kernel rebuilds such a brick from scratch).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int KNEW = 48;
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_merge_kernel(const float* node_pos, int n_old, int n, int k, int sx, int ry, int rz, int x0, int nby, int nbz,
+                                                        uint16_t* knn, const float* brick_T, uint8_t* dirty) {
+    __shared__ float4 newc[KNEW];
+    __shared__ int n_new_s, changed_s;
+    const int b = blockIdx.x;
+    const int bz = b % nbz, by = (b / nbz) % nby, bxs = b / (nbz * nby);
+    const int xlo = bxs * KB, ylo = by * KB, zlo = bz * KB;
+    const int xhi = min(xlo + KB, sx) - 1, yhi = min(ylo + KB, ry) - 1, zhi = min(zlo + KB, rz) - 1;
+    const float cx = 0.5f * (xlo + xhi) + (float)x0, cy = 0.5f * (ylo + yhi), cz = 0.5f * (zlo + zhi);
+    if (threadIdx.x == 0) { n_new_s = 0; changed_s = 0; }
+    __syncthreads();
+    const float T = brick_T[b];
+    const float T2 = T * T * 1.00001f;
+    for (int t = n_old + threadIdx.x; t < n; t += blockDim.x) {
+        const float px = node_pos[3 * t], py = node_pos[3 * t + 1], pz = node_pos[3 * t + 2];
+        const float dx = px - cx, dy = py - cy, dz = pz - cz;
+        if (dx * dx + dy * dy + dz * dz <= T2) {
+            const int pos = atomicAdd(&n_new_s, 1);
+            if (pos < KNEW) newc[pos] = make_float4(px, py, pz, __int_as_float(t));
+        }
+    }
+    __syncthreads();
+    const int m = n_new_s;
+    if (m == 0 || m > KNEW) {
+        if (threadIdx.x == 0) dirty[b] = m == 0 ? 0 : 2;
+        return;
+    }
+    if (threadIdx.x == 0) {   // ascending id (the appends raced): insertion sort of <= KNEW entries
+        for (int a = 1; a < m; ++a) {
+            const float4 v = newc[a];
+            int q = a - 1;
+            while (q >= 0 && __float_as_int(newc[q].w) > __float_as_int(v.w)) { newc[q + 1] = newc[q]; --q; }
+            newc[q + 1] = v;
+        }
+    }
+    __syncthreads();
+    bool changed = false;
+    for (int q = 0; q < 4; ++q) {
+        const int j = threadIdx.x * 4 + q;
+        const int z = zlo + (j & 7), y = ylo + ((j >> 3) & 7), xs = xlo + (j >> 6);
+        if (!(xs < sx && y < ry && z < rz)) continue;
+        const size_t i = ((size_t)xs * ry + y) * rz + z;
+        const double qx = (double)(float)(xs + x0), qy = (double)y, qz = (double)z;
+        int id[KMAX];
+        double d[KMAX];
+#pragma unroll
+        for (int a = 0; a < KMAX; ++a) {
+            id[a] = 0; d[a] = 1.0e300;
+            if (a < k) {
+                id[a] = knn[i * (size_t)k + a];
+                const float* np_ = node_pos + 3 * (size_t)id[a];
+                const double dx = dfb::dsub(qx, (double)np_[0]), dy = dfb::dsub(qy, (double)np_[1]), dz = dfb::dsub(qz, (double)np_[2]);
+                d[a] = dfb::dadd(dfb::dadd(dfb::dmul(dx, dx), dfb::dmul(dy, dy)), dfb::dmul(dz, dz));
+            }
+        }
+        bool ch = false;
+        for (int t = 0; t < m; ++t) {
+            const float4 p = newc[t];
+            const double dx = dfb::dsub(qx, (double)p.x), dy = dfb::dsub(qy, (double)p.y), dz = dfb::dsub(qz, (double)p.z);
+            const double dn = dfb::dadd(dfb::dadd(dfb::dmul(dx, dx), dfb::dmul(dy, dy)), dfb::dmul(dz, dz));
+            if (!(dn < d[k - 1])) continue;          // not strictly closer than the current k-th: stays out (ties keep the lower id)
+            // insert before the first entry that is strictly farther; entries at the same distance (lower ids) stay in front
+            int idn = __float_as_int(p.w);
+            double dcur = dn;
+            bool ins = false;
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a) {
+                if (a < k) {
+                    if (!ins && dcur < d[a]) ins = true;
+                    if (ins) {                       // from the insertion point on everything moves down one slot (order of ties kept)
+                        const double td = d[a]; d[a] = dcur; dcur = td;
+                        const int ti = id[a]; id[a] = idn; idn = ti;
+                    }
+                }
+            }
+            ch = true;
+        }
+        if (ch) {
+#pragma unroll
+            for (int a = 0; a < KMAX; ++a)
+                if (a < k) knn[i * (size_t)k + a] = (uint16_t)id[a];
+            changed = true;
+        }
+    }
+    if (changed) changed_s = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) dirty[b] = changed_s ? 1 : 0;
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(256) knn_points_kernel(const float* pts, int64_t m, const float* node_pos, int n, int k,
                                                          int32_t* idx) {
@@ -354,6 +442,12 @@ int knn_build(const float* node_pos, int n_old, int n_nodes, int k, int rx, int 
         return DFB_OK;
     }
     const unsigned nb = (unsigned)(nbx * nby * nbz);
+    if (n_old > 0) {
+        if (k <= 4) knn_merge_kernel<4><<<nb, 128, 0, s>>>(node_pos, n_old, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, dirty);
+        else knn_merge_kernel<8><<<nb, 128, 0, s>>>(node_pos, n_old, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, dirty);
+        DFB_LAUNCH_CHECK("knn_merge_kernel");
+        if (n_nodes - n_old <= KNEW) return DFB_OK;      // no brick can have overflowed: the rebuild pass would find nothing to do
+    }
     if (k <= 4) knn_brick_kernel<4><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, n_old, dirty);
     else knn_brick_kernel<8><<<nb, 128, 0, s>>>(node_pos, n_nodes, k, x1 - x0, ry, rz, x0, (int)nby, (int)nbz, knn, brick_T, n_old, dirty);
     DFB_LAUNCH_CHECK("knn_brick_kernel");

@@ -22,6 +22,45 @@ def slab_partition(rx, world):
     return out
 
 
+def balanced_slab_partition(unit_cost, world, unit_planes=16, rx=None):
+    """Contiguous x-slabs whose boundaries are multiples of `unit_planes`, chosen so that the LARGEST slab cost is as small as
+    possible (the step time of a sharded volume is the maximum over ranks).  unit_cost[i] = estimated cost of planes
+    [i * unit_planes, (i + 1) * unit_planes) -- e.g. from the brick classes of a frame (engine.slab_cost_profile).  Every slab gets
+    at least one unit.  Returns [(x0, x1)] * world like slab_partition; rx clips the last boundary."""
+    c = np.asarray(unit_cost, dtype=np.float64)
+    n, world = len(c), int(world)
+    if n < world:
+        raise ValueError("fewer units (%d) than ranks (%d)" % (n, world))
+
+    def cuts_for(cap):
+        """greedy fill under capacity `cap`; None if more than `world` slabs would be needed"""
+        cuts, acc, used = [], 0.0, 1
+        for i in range(n):
+            remaining_units, remaining_slabs = n - i, world - used
+            if acc > 0 and (acc + c[i] > cap or remaining_units == remaining_slabs):
+                cuts.append(i); acc = 0.0; used += 1
+                if used > world:
+                    return None
+            acc += c[i]
+        return cuts
+
+    lo, hi = float(c.max()), float(c.sum())
+    for _ in range(60):
+        mid = 0.5 * (lo + hi)
+        if cuts_for(mid) is None:
+            lo = mid
+        else:
+            hi = mid
+    cuts = cuts_for(hi) or []
+    while len(cuts) < world - 1:                     # fewer slabs than ranks: split the widest slab
+        b = [0] + cuts + [n]
+        w = int(np.argmax(np.diff(b)))
+        cuts = sorted(cuts + [b[w] + (b[w + 1] - b[w]) // 2])
+    b = [0] + cuts + [n]
+    total = n * unit_planes if rx is None else int(rx)
+    return [(b[r] * unit_planes, min(b[r + 1] * unit_planes, total) if r < world - 1 else total) for r in range(world)]
+
+
 def residual_partition(n_vert, world):
     """Contiguous ranges of data residuals per rank."""
     return slab_partition(n_vert, world)

@@ -500,7 +500,7 @@ def uniform_sample(pts, radius, device=None, rounds_per_call=16):
     return p[idx].cpu().numpy(), idx.cpu().numpy().astype(np.int64)
 
 
-def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False):
+def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False, keep_on_device=False):
     """Surface extraction on the device (include/dfb.h `dfb_mc_*`): the call the reference makes as
     measure.marching_cubes_lewiner(volume, step_size=..., allow_degenerate=False) (core/fusion.py:554-568, 579).
     vol: (rx, ry, rz) CUDA tensor or host array; level None = 0.5 * (min + max) like skimage.  Returns host arrays
@@ -508,7 +508,7 @@ def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False
     x_origin: sample index (voxel x / step) of vol[0] in the whole grid when `vol` is an x-slab -- coordinates and degenerate-triangle
     decisions are then those of the whole grid.  plane_offsets=True appends (plane_voff, plane_toff), int64 [nx + 1]: first vertex /
     triangle of every sample x-plane (vertices are ordered by owning sample, triangles by cell, x slowest) -- what
-    dist.extract_surface_slab cuts the halo planes off with."""
+    dist.extract_surface_slab cuts the halo planes off with.  keep_on_device=True returns CUDA tensors instead of host arrays."""
     if not isinstance(vol, torch.Tensor):
         vol = _to_dev(np.asarray(vol), torch.float32, _require_cuda(None))
     if vol.dim() != 3:
@@ -543,7 +543,10 @@ def marching_cubes(vol, step_size=1, level=None, x_origin=0, plane_offsets=False
         if nv or nt:
             _capi.check(L.dfb_mc_emit(_ptr(vol), rx, ry, rz, step, int(x_origin), _ptr(lv), _ptr(chunks), _ptr(offs[0]), _ptr(offs[1]),
                                       _ptr(verts), _ptr(normals), _ptr(values), _ptr(faces), _stream()))
-        out = (verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy())
+        if keep_on_device:      # CUDA tensors: the mesh stays where update_graph / setupCorrespondences / solve consume it
+            out = (verts, faces, normals, values)
+        else:
+            out = (verts.cpu().numpy(), faces.cpu().numpy(), normals.cpu().numpy(), values.cpu().numpy())
         if plane_offsets:
             ny = (ry - 1) // step + 1
             po = offs[:, ::ny].cpu().numpy().astype(np.int64)        # rows are (x, y) pairs: every ny-th entry starts an x-plane; [rows] = total
@@ -660,3 +663,22 @@ class FrameStep:
                 _capi.lib().dfb_frame_step_destroy(self._h)
         except Exception:
             pass
+
+
+def slab_cost_profile(vol, unit_planes=16):
+    """Estimated cost of every `unit_planes`-thick x-layer of the slab from the brick classes of the LAST projective update
+    (Workspace.brick_cls: 0 = SKIP, 0xFF = MIXED, else CLAMP): cost = 0.6 per brick (classification) + 1.6 per CLAMP brick
+    (streaming) + 10.7 per MIXED brick (per-voxel tier + its share of the exact pass), in ns on one B200 -- the weights are the
+    measured per-brick times of the 512^3 benchmark step.  Feeds dist.balanced_slab_partition.  numpy float64 [n_units]."""
+    sx, ry, rz = vol.x1 - vol.x0, vol.res[1], vol.res[2]
+    nbx, nby, nbz = (sx + 3) // 4, (ry + 3) // 4, (rz + 31) // 32
+    nb = nbx * nby * nbz
+    cls = vol.workspace.brick_cls[:nb].view(nbx, nby * nbz)
+    mixed = (cls == 0xFF).sum(1).double()
+    clamp = ((cls != 0xFF) & (cls != 0)).sum(1).double()
+    layer = (0.6 * nby * nbz + 1.6 * clamp + 10.7 * mixed).cpu().numpy()          # per 4-plane brick layer
+    per_unit = unit_planes // 4
+    n_units = (nbx + per_unit - 1) // per_unit
+    pad = np.zeros(n_units * per_unit)
+    pad[:nbx] = layer
+    return pad.reshape(n_units, per_unit).sum(1)

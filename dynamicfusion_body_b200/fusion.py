@@ -59,6 +59,29 @@ class _FusionBase:
         self._sess = None
         self._mode = _capi.MODE_HYBRID
         self._last_views = None
+        self._dev_cache = {}
+
+    # ---- device copies of the host arrays the object owns ------------------------------------------
+    def _dev(self, arr, dtype=torch.float32):
+        """Device copy of a host array held in a reference attribute (`_vertices`, `_normals`, `_neighbor_look_up`), cached by the
+        array's identity.  The device surface extractor leaves its output on the GPU and the numpy attribute is its one download, so
+        the callers either side of the hot paths (update_graph, setupCorrespondences, solve) never upload the mesh again.  The
+        attributes are replaced, never edited in place, by this class (as by the reference); a caller that edits one in place
+        must re-assign it."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(device=self._device, dtype=dtype)
+        key = (id(arr), dtype)
+        hit = self._dev_cache.get(key)
+        if hit is not None and hit[0] is arr:
+            return hit[1]
+        t = engine._to_dev(arr, dtype, self._device)
+        self._remember(arr, t, dtype)
+        return t
+
+    def _remember(self, arr, t, dtype=torch.float32):
+        if len(self._dev_cache) >= 12:
+            self._dev_cache.pop(next(iter(self._dev_cache)))
+        self._dev_cache[(id(arr), dtype)] = (arr, t)       # keeps `arr` alive, so its id cannot be re-used
 
     # ---- device-resident volume exposed under the reference's attribute names -------------------
     @property
@@ -157,6 +180,12 @@ class _FusionBase:
     def _lookup(self, pos, k):
         return self._wf.knn_points(np.asarray(pos, dtype=np.float32).reshape(-1, 3), k).cpu().numpy()
 
+    def _set_lookup(self, nlu_dev):
+        """`_neighbor_look_up` (vertex -> k nearest nodes) from a device int32 table: one download, the device copy is kept."""
+        h = nlu_dev.cpu().numpy().astype(np.int64)
+        self._remember(h, nlu_dev, torch.int32)
+        self._neighbor_look_up = h
+
     def warp(self, pos, dqs=None, locations=None, normal=None, dmax=None, m_lw=None):
         """Fusion.warp (core/fusion.py:502-520) for one point or an (M,3) batch.  `dqs` given explicitly
         must be the current node transforms of `locations` (the reference always passes those)."""
@@ -241,14 +270,19 @@ class _FusionBase:
         if tsdf is not None:
             return engine.marching_cubes(tsdf, step_size) if ext == "device" else ext(_as_np(tsdf), step_size)
         if ext == "device":
-            v, f, n, _ = self._device_surface(step_size)
+            v, f, n, _ = self._device_surface(step_size, keep_on_device=True)
         else:
             v, f, n, _ = ext(_as_np(self._tsdf), step_size)
+        if isinstance(v, torch.Tensor):                               # the mesh stays on the device; the attributes are its download
+            vh, nh = v.cpu().numpy(), n.cpu().numpy()
+            self._remember(vh, v)
+            self._remember(nh, n)
+            v, n, f = vh, nh, f.cpu().numpy()
         self._vertices, self._faces, self._normals = np.asarray(v, dtype=np.float32), f, np.asarray(n, dtype=np.float32)
         if self._verbose:
             print("Marching Cubes result: number of extracted vertices is %d" % (len(self._vertices)))
 
-    def _device_surface(self, step_size, level=None):
+    def _device_surface(self, step_size, level=None, keep_on_device=False):
         """Surface of the resident canonical volume (level None = 0.5 * (min + max) like skimage's default).  A rank that holds an x-slab of a volume sharded over the process group
          extracts its share with three halo planes per boundary and every rank receives the whole mesh, identical to the
         single-GPU one (dist.extract_surface_slab); a lone slab is extracted as is, in whole-grid coordinates."""
@@ -257,7 +291,7 @@ class _FusionBase:
         if ddist.is_dist() and (vol.x0 > 0 or vol.x1 < rx):
             return ddist.allgather_mesh(ddist.extract_surface_slab(vol.tsdf, vol.x0, vol.x1, rx, step_size, level=level))
         if vol.x0 % step_size == 0:
-            return engine.marching_cubes(vol.tsdf, step_size, level, x_origin=vol.x0 // step_size)
+            return engine.marching_cubes(vol.tsdf, step_size, level, x_origin=vol.x0 // step_size, keep_on_device=keep_on_device)
         v, f, n, val = engine.marching_cubes(vol.tsdf, step_size, level)
         v[:, 0] += np.float32(vol.x0)
         return v, f, n, val
@@ -311,7 +345,7 @@ class _FusionBase:
     def _relink_nodes(self):
         """node -> index of its nearest canonical vertex (core/fusion.py:204-209,308-313)."""
         if self._wf.n_nodes and self._vertices is not None and len(self._vertices):
-            grid = engine.PointGrid(self._vertices, device=self._device)
+            grid = engine.PointGrid(self._dev(self._vertices), device=self._device)
             self._node_vertex_idx = grid.knn(self._wf.node_pos.double(), 1).reshape(-1).cpu().numpy().astype(np.int64)
 
 
@@ -392,9 +426,10 @@ class Fusion(_FusionBase):
         else:
             self.marching_cubes()
         self._relink_nodes()
-        vknn = self._wf.knn_points(self._vertices, self._knn)
-        uns = engine.graph_unsupported(self._wf, self._vertices, vknn).cpu().numpy()
-        new_v, new_idx = engine.uniform_sample(self._vertices[uns], self._radius, device=self._device)
+        vd = self._dev(self._vertices)
+        vknn = self._wf.knn_points(vd, self._knn)
+        uns = engine.graph_unsupported(self._wf, vd, vknn)
+        new_v, new_idx = engine.uniform_sample(vd[uns], self._radius, device=self._device)
         if len(new_v):
             new_dq = _gn.dq_blend_points(self._wf, new_v, self._wf.knn_points(new_v, self._knn))
             self._node_vertex_idx = np.concatenate([self._node_vertex_idx, new_idx])
@@ -403,7 +438,7 @@ class Fusion(_FusionBase):
             self._wf.append_nodes(new_v, new_dq.astype(np.float32), np.full(len(new_v), 2 * self._radius, dtype=np.float32))
         if self._verbose:
             print("Inserted %d new deformation nodes. Current number of deformation nodes: %d" % (len(new_v), self._wf.n_nodes))
-        self._neighbor_look_up = self._lookup(self._vertices, self._knn).astype(np.int64)
+        self._set_lookup(self._wf.knn_points(vd, self._knn) if len(new_v) else vknn)
         self._curr_tsdf = None
         self._correspondences = []
         if self._write_warpfield:
@@ -423,8 +458,8 @@ class Fusion(_FusionBase):
         if self._vertices is None or self._normals is None:
             raise ValueError('canonical vertices/normals have not been set')
         lv = self._live_vertices(curr_tsdf, live_vertices)
-        loc = np.asarray(self._neighbor_look_up, dtype=np.int32).reshape(len(self._vertices), -1)
-        wv, wn = engine.warp_points(self._wf, self._lw, self._vertices, self._normals, idx=loc, k=loc.shape[1])
+        loc = self._dev(self._neighbor_look_up, torch.int32).reshape(len(self._vertices), -1)
+        wv, wn = engine.warp_points(self._wf, self._lw, self._dev(self._vertices), self._dev(self._normals), idx=loc, k=loc.shape[1])
         best, cost = self._closest_points(lv, wv, wn)
         self._correspondences = lv[best.long()].cpu().numpy()
         self._corr_cost = cost.cpu().numpy()
@@ -480,7 +515,9 @@ class Fusion(_FusionBase):
         corr = np.asarray(self._correspondences, dtype=np.float64)
         if len(corr) != len(self._vertices):
             raise ValueError("Please first call setupCorrespondences to compute point to point correspondences between canonical and live frame vertices!")
-        return _gn.Problem(self._wf, self._vertices, self._normals, corr, np.asarray(self._neighbor_look_up), self._node_vertex_idx)
+        nlu = self._neighbor_look_up
+        nlu = self._dev(nlu, torch.int32) if isinstance(nlu, np.ndarray) else np.asarray(nlu)
+        return _gn.Problem(self._wf, self._dev(self._vertices), self._dev(self._normals), corr, nlu, self._node_vertex_idx)
 
     def computef(self, x, tdw, trw, rw):
         """core/fusion.py:459-491: residual vector (V + 3*k*N,), float64."""

@@ -108,3 +108,40 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["metric"] == "warped_tsdf_voxels_per_sec" and d["unit"] == "voxels/s"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_balanced_slab_partition():
+    """dist.balanced_slab_partition: contiguous slabs on 16-plane boundaries, every rank gets one, the largest estimated cost is never
+    above the equal split's and reaches the optimum on a profile with an obvious answer."""
+    from dynamicfusion_body_b200 import dist as d
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(8, 64))
+        c = rng.random(n) * rng.choice([1.0, 10.0], n)
+        for world in (1, 2, 3, 8):
+            if world > n:
+                continue
+            p = d.balanced_slab_partition(c, world, 16, 16 * n)
+            assert p[0][0] == 0 and p[-1][1] == 16 * n and all(p[i][1] == p[i + 1][0] for i in range(world - 1))
+            assert all(b > a and a % 16 == 0 for a, b in p)
+            cost = max(c[a // 16:b // 16].sum() for a, b in p)
+            eq = [(16 * ((n * r) // world), 16 * ((n * (r + 1)) // world)) for r in range(world)]
+            assert cost <= max(c[a // 16:b // 16].sum() for a, b in eq) + 1e-9
+    c = np.array([1, 1, 1, 1, 8, 8, 1, 1], dtype=float)
+    assert d.balanced_slab_partition(c, 3, 16, 128) == [(0, 64), (64, 80), (80, 128)] or \
+        max(c[a // 16:b // 16].sum() for a, b in d.balanced_slab_partition(c, 3, 16, 128)) == 10.0
+    with pytest.raises(ValueError):
+        d.balanced_slab_partition(np.ones(2), 3)
+
+
+def test_flat_normal_equation_views():
+    """gn.Problem hands [H | g | cost] out as views of one buffer; dist.flat_normal_equations recovers it (one collective, in place)."""
+    import torch
+    from dynamicfusion_body_b200 import dist as d
+    flat = torch.arange(3 * 64 + 16 + 2, dtype=torch.float64)
+    H, g, c = flat[:192].view(3, 8, 8), flat[192:208], flat[208:]
+    f = d.flat_normal_equations(H, g, c)
+    assert f is not None and f.data_ptr() == flat.data_ptr() and f.numel() == flat.numel()
+    assert d.flat_normal_equations(H.clone(), g, c) is None
+    H2, g2, c2 = d.allreduce_normal_equations(H, g, c)          # no process group: identity
+    assert H2 is H and torch.equal(f, torch.arange(210, dtype=torch.float64))
