@@ -151,7 +151,7 @@ class RankState:
         self.dq_stage = [torch.zeros((sc.n_nodes, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
         self.counters_host = [torch.zeros(8, dtype=torch.int32).pin_memory() for _ in range(2)]
         self.slot_done = [torch.cuda.Event(), torch.cuda.Event()]
-        self.steps, self.ios_res, self.ios_e2e = [], [], []
+        self.steps, self.ios_res, self.ios_e2e, self.ios_nobcast, self.ios_local = [], [], [], [], []
         for slot in range(2):
             views = engine.make_views(self.packets[slot], sc.K, sc.Kinv, sc.extrinsics)
             st = engine.FrameStep(self.vol, self.wf, sc.lw, views, sc.tdist)
@@ -161,6 +161,9 @@ class RankState:
             # end to end: transforms and depth come from pinned host memory, the counters go back to pinned host memory
             self.ios_e2e.append(st.io(comm=comm, comm_prefetch=comm_pre, root=0, dq_src=self.dq_stage[slot], prefetch_dst=self.packets[slot ^ 1],
                                       prefetch_src=frames["depth_host"], counters_host=self.counters_host[slot]))
+            # limiter analysis (N > 1): the same step without the in-step transform broadcast / without any communication
+            self.ios_nobcast.append(st.io(comm=None, comm_prefetch=comm_pre, root=0, prefetch_dst=self.packets[slot ^ 1], prefetch_src=frames["depth_dev"]))
+            self.ios_local.append(st.io())
 
     def reset(self):
         self.vol.tsdf.fill_(self.sc.tdist)
@@ -184,6 +187,17 @@ class RankState:
                 self.wf.node_dq.copy_(self.frames["dq_dev"][i % len(self.frames["dq_dev"])], non_blocking=True)
             self.steps[slot].run(self.ios_res[slot])
 
+    def step_with(self, ios, all_ranks_own_transforms=True):
+        """step function over another set of I/O descriptors (limiter analysis): every rank copies the frame's transforms itself"""
+        import torch
+
+        def f(i):
+            slot = i & 1
+            with torch.cuda.stream(self.stream):
+                self.wf.node_dq.copy_(self.frames["dq_dev"][i % len(self.frames["dq_dev"])], non_blocking=True)
+                self.steps[slot].run(ios[slot])
+        return f
+
     def step_e2e(self, i):
         import torch
         slot = i & 1
@@ -196,7 +210,7 @@ class RankState:
             self.slot_done[slot].record()
         return stats
 
-    def timed(self, step_fn, steps, warmup, src, barrier):
+    def timed(self, step_fn, steps, warmup, src, barrier, per_rank=False):
         import torch
         from dynamicfusion_body_b200 import dist as ddist
         self.prime(src)
@@ -209,6 +223,8 @@ class RankState:
             step_fn(i)
         e1.record(self.stream)
         barrier()
+        if per_rank:
+            return e0.elapsed_time(e1)
         return ddist.max_over_ranks(e0.elapsed_time(e1), self.dev)
 
 
@@ -298,6 +314,20 @@ def run_ours(args):
             torch.cuda.synchronize()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    limiter = None
+    if world > 1:
+        # where the N-GPU step goes: (a) every rank's own compute (no communication at all; each rank uploads the transforms itself),
+        # (b) the step with the sensor prefetch but without the in-step transform broadcast, (c) the real step
+        ms_local = st.timed(st.step_with(st.ios_local), args.steps, args.warmup, depth_dev, barrier, per_rank=True) / args.steps
+        allms = [None] * world
+        dist.all_gather_object(allms, float(ms_local))
+        ms_nob = st.timed(st.step_with(st.ios_nobcast), args.steps, args.warmup, depth_dev, barrier) / args.steps
+        step_now = ms_total / args.steps
+        limiter = {"step_ms": step_now, "rank_compute_ms": allms, "max_rank_compute_ms": max(allms), "mean_rank_compute_ms": float(np.mean(allms)),
+                   "step_without_transform_broadcast_ms": ms_nob, "transform_broadcast_on_critical_path_ms": step_now - ms_nob,
+                   "prefetch_branch_and_rank_skew_ms": ms_nob - max(allms),
+                   "note": "rank_compute = one CUDA-graph launch per step of [node records, counters memset, region bounds, brick classify, "
+                           "update, exact] on the rank's slab, no communication; an N-th of the one-GPU step would be the ideal"}
     for e in st.slot_done:
         e.record(st.stream)
     ms_e2e = st.timed(st.step_e2e, args.steps, max(3, args.warmup // 2), depth_host, barrier)
@@ -394,6 +424,8 @@ def run_ours(args):
         out["equal_slabs"] = equal_info
     if parity is not None:
         out["parity_check"] = parity
+    if limiter is not None:
+        out["limiter"] = limiter
     def leg(name, fn):
         """the extra legs must never cost the headline line"""
         try:
@@ -685,11 +717,12 @@ def bench_gn(args, dev, rank, world, comm=None):
     x = torch.from_numpy(pd.x0).to(dev)
     allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c, comm=comm)) if world > 1 else None
     prob.pattern()
-    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce)         # warm-up
+    bcast = (lambda t: comm.broadcast(t)) if (world > 1 and comm is not None) else None
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce, broadcast=bcast)         # warm-up
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     e[0].record()
-    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce)
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce, broadcast=bcast)
     e[1].record()
     torch.cuda.synchronize()
     total_ms = ddist.max_over_ranks(e[0].elapsed_time(e[1]), dev)
@@ -788,11 +821,12 @@ def bench_gn_depth_frame(args, dev, rank, world, comm=None):
     allreduce = (lambda H, g, c: ddist.allreduce_normal_equations(H, g, c, comm=comm)) if world > 1 else None
     x = torch.from_numpy(x0).to(dev)
     prob.pattern()
-    prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce)
+    bcast = (lambda t: comm.broadcast(t)) if (world > 1 and comm is not None) else None
+    prob.gauss_newton(x, sc.lw, 0.05, max_iter=2, huber=True, allreduce=allreduce, broadcast=bcast)
     torch.cuda.synchronize()
     e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     e[0].record()
-    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce)
+    res = prob.gauss_newton(x, sc.lw, 0.05, max_iter=args.gn_iters, huber=True, ftol=0.0, allreduce=allreduce, broadcast=bcast)
     e[1].record()
     torch.cuda.synchronize()
     total_ms = ddist.max_over_ranks(e[0].elapsed_time(e[1]), dev)
@@ -803,6 +837,31 @@ def bench_gn_depth_frame(args, dev, rank, world, comm=None):
                                    "correspondences against the live frame's pixels via Fusion.setupCorrespondences, %d nodes k=4, 15 iterations" % sc.n_nodes}}
 
 
+def raw_reference_rate(sc):
+    """The UNMODIFIED reference's own loop (Fusion.updateTSDF, core/fusion.py:153-198: KD-tree query + warp + trilinear sample per
+    voxel) on a 16^3 brick of the same node graph, one core -- only where /root/reference exists (the authoring container; the GPU
+    box does not have it: there the figure probed for BASELINE.md section 2 on this container's host is quoted)."""
+    try:
+        from oracle import refload
+        if not refload.available():
+            raise RuntimeError("absent")
+        R = 16
+        rng = np.random.default_rng(0)
+        nodes = sc.nodes_as_reference_tuples()
+        centre = sc.node_pos.mean(0) - R / 2                           # a brick in the middle of the body
+        nodes = [(n[0], (n[1] - centre).astype(np.float32), n[2], n[3]) for n in nodes]
+        f = refload.make_fusion(nodes, np.zeros((R, R, R)), np.zeros((R, R, R)), sc.tdist, sc.k, np.array([1, 0, 0, 0, 0, 0, 0, 0], np.float32))
+        curr = rng.normal(size=(R, R, R))
+        t0 = time.perf_counter()
+        with refload.quiet():
+            f.updateTSDF(curr)
+        dt = time.perf_counter() - t0
+        return {"voxels_per_s_per_core": R ** 3 / dt, "how": "unmodified reference Fusion.updateTSDF on a 16^3 brick, %d nodes, k=%d, %.1f s, measured in this run" % (len(nodes), sc.k, dt)}
+    except Exception:
+        return {"voxels_per_s_per_core": 4651.0, "how": "unmodified reference Fusion.updateTSDF (N=1000, k=4), probed for BASELINE.md section 2 in the authoring "
+                                                       "container (numpy 2.3.5, scipy 1.18.1, one Xeon core); the reference does not travel to the GPU box"}
+
+
 def cpu_baseline(sc, res, budget_s=12.0):
     from oracle import driver
     sd = driver.scene_dict(sc)
@@ -810,7 +869,8 @@ def cpu_baseline(sc, res, budget_s=12.0):
     n_sample = int(min(4_000_000, max(100_000, vps * budget_s)))
     vps, n, dt = driver.time_projective(sd, res, n_sample, seed=1)
     return {"value": vps, "unit": "voxels/s", "cores": 1, "kind": "port",
-            "sample": "%d random voxels of the same %dx%dx%d workload, numpy oracle (oracle/tsdf.py) incl. KD-tree kNN, %.1f s" % (n, res[0], res[1], res[2], dt)}
+            "sample": "%d random voxels of the same %dx%dx%d workload, numpy oracle (oracle/tsdf.py) incl. KD-tree kNN, %.1f s" % (n, res[0], res[1], res[2], dt),
+            "raw_reference": raw_reference_rate(sc)}
 
 
 def run_reference(args):
@@ -838,9 +898,10 @@ def run_reference(args):
     value = nvox / wall
     out = {"impl": "reference", "metric": "warped_tsdf_voxels_per_sec", "value": value, "unit": "voxels/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "%d^3 voxels, warped projective TSDF update (a3), k=%d DQB, %d nodes, %d view(s) 640x480; each step = a "
-                                  "bounded sample of %d voxels" % (res, args.k, sc.n_nodes, args.views, per_step)},
+           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "%d^3 voxels total, warped projective TSDF update (a3), k=%d DQB, %d nodes, %d view(s) 640x480; each step = a "
+                                  "bounded sample of %d voxels, per-voxel KD-tree kNN included (the GPU arm's `value_amortised` accounts "
+                                  "for its kNN table)" % (res, args.k, sc.n_nodes, args.views, per_step)},
            "cpu_baseline": {"value": value, "unit": "voxels/s", "cores": cores, "kind": "port",
                             "sample": "%d random voxels per step over %d worker processes (numpy oracle incl. KD-tree kNN)" % (per_step, cores)},
            "e2e": {"value": value, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

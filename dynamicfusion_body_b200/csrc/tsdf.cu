@@ -1281,8 +1281,13 @@ int run_projective(ProjParams& P, int mode, cudaStream_t s, const dfb_volume* vo
         else if (P.k <= 4) { if (one) KERNEL<4, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<4, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
         else { if (one) KERNEL<8, false, true><<<grid, 128, 0, s>>>(__VA_ARGS__); else KERNEL<8, false, false><<<grid, 128, 0, s>>>(__VA_ARGS__); } \
     } while (0)
-                static int use_smem = -1;
-                if (use_smem < 0) { const char* e = getenv("DFB_UPDATE_SMEM"); use_smem = e ? atoi(e) : 1; }
+                // Shared-memory node table (brick_update_smem_kernel) or node gathers through L1 (brick_update_kernel).  Measured
+                // (profiles/r2_ab_update.md): one view, k = 4 at 512^3 -- 0.397 ms with the table, 0.377 ms without (the quad pre-test
+                // leaves a quarter of the MIXED voxels to gather nodes at all, and eight 128-thread CTAs per SM balance better than one
+                // CTA of 1024); eight views, k = 8 at 256^3 -- 0.61 ms with the table, 0.69 ms without.  DFB_UPDATE_SMEM=0/1 forces one.
+                static int smem_env = -2;
+                if (smem_env == -2) { const char* e = getenv("DFB_UPDATE_SMEM"); smem_env = e ? atoi(e) : -1; }
+                const int use_smem = smem_env >= 0 ? smem_env : (P.n_views > 1 || P.k > 4);
                 static int use_quads = -1;
                 if (use_quads < 0) { const char* e = getenv("DFB_QUADS"); use_quads = e ? atoi(e) : 1; }
                 const float* qrec = use_quads ? rrec : nullptr;

@@ -4,7 +4,9 @@ The TSDF update shards with no halo and no data-path collective: GPU g owns the 
 [x0_g, x1_g) of the C-ordered volume (index = x*ry*rz + y*rz + z), every rank keeps a replica of the (tiny) node
 table, and per frame rank 0 broadcasts the sensor data + node transforms (~1.3 MB).  The Gauss-Newton solve has one
 real exchange: each rank assembles J^T W J / J^T W f over its range of data residuals into the SAME block pattern and
-the blocks are summed with one all-reduce before every rank runs the identical node-space solve.
+the blocks are summed with one all-reduce before every rank runs the same node-space solve (replicated; its atomically
+accumulated inner products agree to rounding only, so the iterate is broadcast from rank 0 after every solve --
+gn.Problem.gauss_newton(broadcast=...) -- and all ranks warp with bit-identical transforms).
 """
 import numpy as np
 import torch

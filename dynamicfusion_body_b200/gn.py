@@ -187,9 +187,11 @@ class Problem:
         return x_new, delta, self._ws[:8]
 
     def gauss_newton(self, x0, lw, rw, max_iter=15, huber=True, f_scale=1.0, lam0=1e-3, lam_min=1e-5, pcg_iters=400,
-                     pcg_tol=1e-4, ftol=1e-9, verbose=False, allreduce=None):
+                     pcg_tol=1e-4, ftol=1e-9, verbose=False, allreduce=None, broadcast=None):
         """Damped Gauss-Newton (Levenberg-Marquardt accept/reject).  `allreduce(H, g, cost)` is called after every
-        assembly when the residuals are sharded over ranks (dist.py).  The linear systems are solved inexactly (PCG stops at a
+        assembly when the residuals are sharded over ranks (dist.py); `broadcast(x)` (rank 0 -> all, in place) after every solve: the
+        PCG's inner products are accumulated with atomics, so the replicated solves agree only to rounding -- broadcasting the
+        iterate keeps every rank's transforms (and with them the sharded TSDF updates) bit-identical.  The linear systems are solved inexactly (PCG stops at a
         relative residual of `pcg_tol`): at 1 k nodes / 300 k residuals 1e-3 reaches the cost of a 1e-9 solve to 2e-6 relative
         in 2.0 instead of 3.2 ms per iteration (the damping shrinks as the iteration converges and the late, ill-conditioned
         systems need 350-400 PCG iterations to 1e-9 for no gain in cost); scripts/gn_forcing.py, DESIGN section 4."""
@@ -211,6 +213,8 @@ class Problem:
         it = 0
         for it in range(1, max_iter + 1):
             x_new, delta, info = self.solve_step(H, g, x, lam, pcg_iters, pcg_tol)
+            if broadcast is not None:
+                broadcast(x_new)
             H2, g2, c2 = assemble(x_new)
             cost_new = float(c2[0].item())
             ok = np.isfinite(cost_new) and cost_new < cost

@@ -10,10 +10,11 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 sc = synth.make_scene(res=R, k=k, n_nodes=N, seed=0, background=True)
 wf = engine.DeviceWarpField(k); wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
-vol = engine.DeviceVolume((R, R, R), fill=sc.tdist)
+x0, x1 = (int(v) for v in os.environ.get("SLAB", "0,%d" % R).split(","))     # SLAB=192,256: one rank's x-slab of the strong-scaling run
+vol = engine.DeviceVolume((R, R, R), x0, x1, fill=sc.tdist)
 depths = torch.from_numpy(sc.depths).cuda()
 views = engine.make_views(depths, sc.K, sc.Kinv, sc.extrinsics)
-wf.knn_table(vol.res, 0, R)
+wf.knn_table(vol.res, x0, x1)
 torch.cuda.synchronize()
 for i in range(reps):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
