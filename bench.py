@@ -274,22 +274,36 @@ def run_ours(args):
     if world > 1:
         # the step time of a sharded volume is the maximum over ranks: measure the equal slabs, then move the slab boundaries
         # (multiples of 16 planes) so that the estimated cost -- brick classes of a frame -- is the same on every rank
+        UNIT = 4                                                       # slab boundaries on brick layers (4 planes)
         ms_eq = st.timed(st.step_resident, args.steps, args.warmup, depth_dev, barrier)
-        prof = engine.slab_cost_profile(st.vol, 16)
-        gathered = [None] * world
-        dist.all_gather_object(gathered, prof.tolist())
-        unit_cost = np.concatenate([np.asarray(g) for g in gathered])
-        equal_info = {"ms_per_step": ms_eq / args.steps, "value": nvox_total * args.steps / (ms_eq * 1e-3), "slabs": parts_equal,
-                      "estimated_cost_per_rank": [float(np.sum(g)) for g in gathered]}
+        equal_info = {"ms_per_step": ms_eq / args.steps, "value": nvox_total * args.steps / (ms_eq * 1e-3), "slabs": parts_equal}
         if not args.equal_slabs:
-            parts_bal = ddist.balanced_slab_partition(unit_cost, world, 16, res)
-            if parts_bal != parts_equal:
+            parts = parts_equal
+            for rnd in range(2):
+                # cost of every 4-plane layer from the brick classes of a frame, rescaled per rank by what the rank's step really
+                # takes on its own (no communication) minus the per-step floor -- the second round corrects the first one's model
+                prof = engine.slab_cost_profile(st.vol, UNIT)
+                t_local = st.timed(st.step_with(st.ios_local), max(10, args.steps // 2), 3, depth_dev, barrier, per_rank=True) / max(10, args.steps // 2)
+                floor_ms = 0.03
+                scale = max(t_local - floor_ms, 0.2 * t_local) / max(float(prof.sum()), 1e-9)
+                gathered = [None] * world
+                dist.all_gather_object(gathered, (prof * scale).tolist())
+                unit_cost = np.concatenate([np.asarray(g) for g in gathered])[:res // UNIT]
+                new_parts = ddist.balanced_slab_partition(unit_cost, world, UNIT, res)
+                if rnd == 0:
+                    equal_info["rank_compute_ms"] = [float(np.sum(g)) + floor_ms for g in gathered]
+                if new_parts == parts:
+                    break
+                parts = new_parts
                 del st
                 torch.cuda.empty_cache()
-                st = RankState(args, sc, grid, parts_bal[rank][0], parts_bal[rank][1], dev, rank, comm, comm_pre, frames)
-                partition = {"kind": "balanced", "slabs": parts_bal,
-                             "how": "x-slab boundaries (multiples of 16 planes) minimising the largest estimated slab cost; cost per "
-                                    "16-plane layer from the brick classes of a frame (0.6 / 1.6 / 10.7 ns per brick / CLAMP brick / MIXED brick)"}
+                st = RankState(args, sc, grid, parts[rank][0], parts[rank][1], dev, rank, comm, comm_pre, frames)
+                st.timed(st.step_resident, 3, 2, depth_dev, barrier)   # a few frames so that the brick classes exist
+            if parts != parts_equal:
+                partition = {"kind": "balanced", "slabs": parts,
+                             "how": "x-slab boundaries on brick layers (multiples of 4 planes) minimising the largest slab cost; cost per layer = "
+                                    "brick classes of a frame (0.6 / 1.6 / 10.7 per brick / CLAMP brick / MIXED brick) scaled by the measured "
+                                    "compute time of the rank that owned the layer, two rounds"}
         st.reset()
     x0, x1 = st.x0, st.x1
     nvox_rank = st.nvox
@@ -616,12 +630,14 @@ def bench_configs(args, dev):
     sdf = synth.mesh_sdf_volume((R, R, R), wv, sc.normals)             # untruncated, as test.py:105-110 loads it
     sdf_s = time.time() - t0
     live_raw = torch.from_numpy(sdf).to(dev)
-    live_trunc = torch.from_numpy(np.clip(sdf, -sc.tdist, sc.tdist)).to(dev)
+    # a live volume as FusionDM / fuseFrame leave it: the band around the surface, +tdist (the initial value) everywhere else --
+    # such volumes never hold -tdist (voxels behind the band are simply not updated, core/fusion_dm.py:203)
+    live_trunc = torch.from_numpy(np.where(sdf < -sc.tdist, np.float32(sc.tdist), np.minimum(sdf, np.float32(sc.tdist))).astype(np.float32)).to(dev)
     for name, live, td, what in (("c2_a1_256_reference_usage", live_raw, float(sdf.max()),
                                   "Fusion.updateTSDF, untruncated live SDF with trunc_distance = volume.max() (test.py:110): every voxel lies inside the "
                                   "band and takes the reference-exact float64 tier"),
                                  ("c2_a1_256_truncated", live_trunc, sc.tdist,
-                                  "Fusion.updateTSDF, live TSDF truncated at +-tdist (what FusionDM / fuseFrame volumes hold)")):
+                                  "Fusion.updateTSDF, live TSDF as FusionDM / fuseFrame volumes hold it (band around the surface, +tdist elsewhere)")):
         vs = [engine.DeviceVolume((R, R, R), device=dev, fill=td) for _ in range(n_rot)]
         it["i"] = 0
 

@@ -350,10 +350,19 @@ DFB_HD uint32_t quad_view_test(const ProjParams& P, const QuadView& Q, const flo
     // |X'/Z' - X/Z| <= (dX + |X/Z| dZ) / Z'   for |X' - X| <= dX, |Z' - Z| <= dZ
     const float ea = (Q.d[0] + am * Q.d[2]) * rl + 4e-6f * am + 1e-6f, eb = (Q.d[1] + bm * Q.d[2]) * rl + 4e-6f * bm + 1e-6f;
     const float al = fminf(a0, a3) - ea, ah = fmaxf(a0, a3) + ea, bl = fminf(b0, b3) - eb, bh = fmaxf(b0, b3) + eb;
-    float ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-    float uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
-    float vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
-    float vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+    // plain pinhole (no skew, K^-1 row 2 = (0,0,1): the usual camera) keeps two multiplies per axis; the general form is the interval
+    // product of the brick classifier
+    const bool plain = P.kf[1] == 0.f && P.kf[3] == 0.f && P.kf[0] > 0.f && P.kf[4] > 0.f && P.kin[0] == 0.f && P.kin[1] == 0.f;
+    float ul, uh, vl, vh;
+    if (plain) {
+        ul = P.kf[0] * al + P.kf[2]; uh = P.kf[0] * ah + P.kf[2];
+        vl = P.kf[4] * bl + P.kf[5]; vh = P.kf[4] * bh + P.kf[5];
+    } else {
+        ul = fminf(P.kf[0] * al, P.kf[0] * ah) + fminf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        uh = fmaxf(P.kf[0] * al, P.kf[0] * ah) + fmaxf(P.kf[1] * bl, P.kf[1] * bh) + P.kf[2];
+        vl = fminf(P.kf[3] * al, P.kf[3] * ah) + fminf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+        vh = fmaxf(P.kf[3] * al, P.kf[3] * ah) + fmaxf(P.kf[4] * bl, P.kf[4] * bh) + P.kf[5];
+    }
     {
         const float su = 4e-6f * (fabsf(ul) + fabsf(uh) + fabsf(P.kf[2])) + 1e-4f, sv = 4e-6f * (fabsf(vl) + fabsf(vh) + fabsf(P.kf[5])) + 1e-4f;
         ul -= su; uh += su; vl -= sv; vh += sv;
@@ -365,18 +374,35 @@ DFB_HD uint32_t quad_view_test(const ProjParams& P, const QuadView& Q, const flo
     if (iu1 - iu0 >= QUAD_MAX_SIDE || iv1 - iv0 >= QUAD_MAX_SIDE) return ALL_OPEN;
     float zmin = 3.0e38f, zmax = -3.0e38f;
     bool bad = false;
-    for (int iv = iv0; iv <= iv1; ++iv)
-        for (int iu = iu0; iu <= iu1; ++iu) {
-            const float z = -depth[(size_t)iv * P.cols + iu];
-            bad |= !(fabsf(z) <= 3.0e38f);
-            zmin = fminf(zmin, z);
-            zmax = fmaxf(zmax, z);
+    {
+        // the rectangle is at most QUAD_MAX_SIDE x QUAD_MAX_SIDE: fixed trip counts, pixels beyond its far edges re-read the edge
+        const float* row = depth + (size_t)iv0 * P.cols + iu0;
+        const int nu = iu1 - iu0, nv = iv1 - iv0;
+#pragma unroll
+        for (int dv = 0; dv < QUAD_MAX_SIDE; ++dv) {
+            if (dv > nv) break;
+#pragma unroll
+            for (int du = 0; du < QUAD_MAX_SIDE; ++du) {
+                if (du > nu) break;
+                const float z = -row[du];
+                bad |= !(fabsf(z) <= 3.0e38f);
+                zmin = fminf(zmin, z);
+                zmax = fmaxf(zmax, z);
+            }
+            row += P.cols;
         }
+    }
     if (bad) return ALL_OPEN;
-    const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
-    const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
-    const float kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
-    const float kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+    float kzl = 1.f, kzh = 1.f;
+    if (!plain) {
+        const float k0l = fminf(P.kin[0] * ul, P.kin[0] * uh), k0h = fmaxf(P.kin[0] * ul, P.kin[0] * uh);
+        const float k1l = fminf(P.kin[1] * vl, P.kin[1] * vh), k1h = fmaxf(P.kin[1] * vl, P.kin[1] * vh);
+        kzl = k0l + k1l + P.kin[2] - 1e-6f * (fabsf(k0l) + fabsf(k1l) + fabsf(P.kin[2]));
+        kzh = k0h + k1h + P.kin[2] + 1e-6f * (fabsf(k0h) + fabsf(k1h) + fabsf(P.kin[2]));
+    } else {
+        kzl = P.kin[2] - 1e-6f * fabsf(P.kin[2]);
+        kzh = P.kin[2] + 1e-6f * fabsf(P.kin[2]);
+    }
     if (!(kzl > 0.f)) return ALL_OPEN;
     *frus = 1;
     if (zmax <= 0.f) return ALL_SKIP;                                                // no measurement on any candidate pixel

@@ -215,8 +215,14 @@ DFB_HDN void voxel_projective_exact(const ProjParams& P, int x, int y, int z, co
         } else {
             for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
         }
+        // -DDFB_EXACT_REC=1: fetch pos / dq from the packed records (3 x 16 B per node) instead of the SoA arrays (11 scalar loads);
+        // measured at 512^3: 0.160 ms against 0.149 ms -- the pass is not load-bound, the wider loads only lengthen the dependency
+        // chains -- so the scalar form stays the default
+#ifndef DFB_EXACT_REC
+#define DFB_EXACT_REC 0
+#endif
         warp_ref<KT>(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, base,
-                     nullptr, nullptr, true, P.node_rec);
+                     nullptr, nullptr, true, DFB_EXACT_REC ? P.node_rec : nullptr);
     }
     double v = (double)*v_io, w = (double)*w_io;
     int m = 0, f = 0;

@@ -37,14 +37,6 @@ __device__ __forceinline__ void st_stream(float* p, float4 v) {
     *reinterpret_cast<float4*>(p) = v;
 #endif
 }
-__device__ __forceinline__ uint4 ld_ids(const uint4* p) {
-#if DFB_STREAM_HINTS
-    return __ldcs(p);
-#else
-    return __ldg(p);
-#endif
-}
-
 template <int KMAX>
 __device__ __forceinline__ void load_ids(const uint16_t* knn, size_t i, int k, uint16_t* ids) {
     if (KMAX == 4) {
@@ -544,85 +536,6 @@ __device__ __forceinline__ void mixed_brick_edge(const ProjParams& P, int bxs, i
             if (P.frustum_out) P.frustum_out[i] = (uint8_t)f;
         }
     }
-}
-
-// Interior bricks: the thread's four z-consecutive voxels move as one float4 of v, one of w and (k = 4 / 8) two / four
-// 16-byte kNN loads, all issued before the arithmetic; the four classifications are independent instruction streams
-// for the scheduler, and the warp reserves its work-list slots with one atomic.
-template <int KMAX, bool EXACTK, bool ONEVIEW, class Rec>
-__device__ __forceinline__ void mixed_brick_full(const ProjParams& P, int bxs, int by, int bz, int dx, int dy, int dz, float sc, int views, int m0,
-                                                 int f0, const Rec rec) {
-    const int xs = bxs * BRICK_X + dx, y = by * BRICK_Y + dy, z0 = bz * BRICK_Z + dz;
-    const size_t i0 = ((size_t)xs * P.ry + y) * P.rz + z0;
-    const float4 v4 = ld_stream(P.tsdf + i0);
-    const float4 w4 = ld_stream(P.weight + i0);
-    uint16_t ids[4][KMAX];
-    if (!P.rigid) {
-        if (EXACTK && KMAX == 4) {
-            const uint4* src = reinterpret_cast<const uint4*>(P.knn + i0 * 4);
-            const uint4 a = ld_ids(src), b = ld_ids(src + 1);
-            const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                ids[q][0] = r[2 * q] & 0xffff; ids[q][1] = r[2 * q] >> 16;
-                ids[q][2] = r[2 * q + 1] & 0xffff; ids[q][3] = r[2 * q + 1] >> 16;
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) load_ids<KMAX>(P.knn, i0 + q, EXACTK ? KMAX : P.k, ids[q]);
-        }
-    }
-    float v[4] = {v4.x, v4.y, v4.z, v4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
-    int cls[4], m[4], f[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        m[q] = 0; f[q] = 0;
-        cls[q] = voxel_projective_classify_rec<KMAX, EXACTK, ONEVIEW>(P, xs + P.x0, y, z0 + q, ids[q], &m[q], &f[q], views, m0, f0, rec);
-    }
-    // work list: one reservation per warp for the four voxels of every lane.  (Measured and dropped: CTA-level
-    // aggregation through shared memory, and prefetch.global.L2 of the next brick's v / w / kNN lines -- neither the
-    // counter nor DRAM latency at the head of a brick is what the kernel waits for.)
-    unsigned bal[4];
-    uint32_t total = 0;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        bal[q] = __ballot_sync(0xffffffffu, cls[q] == CLS_UNCERTAIN);
-        total += __popc(bal[q]);
-    }
-    if (total) {
-        const int lane = threadIdx.x & 31;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(P.counters, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (cls[q] == CLS_UNCERTAIN) {
-                const uint32_t pos = base + __popc(bal[q] & ((1u << lane) - 1u));
-                defer_voxel(pos, (uint32_t)(i0 + q), P.list, P.capacity, P.overflow_bits);
-            }
-            base += __popc(bal[q]);
-        }
-    }
-    bool changed = false;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        if (cls[q] == CLS_UNCERTAIN) { m[q] = 0; f[q] = 0; continue; }
-        if (m[q]) {
-            if (ONEVIEW) {
-                clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
-            } else {
-                for (int vi = 0; vi < P.n_views; ++vi)
-                    if (m[q] & (1 << vi)) clamp_update(v[q], w[q], P.tdist_f, P.wmax_f, sc);
-            }
-            changed = true;
-        }
-    }
-    if (changed) {   // deferred voxels get their old value back; the exact pass runs after this kernel
-        st_stream(P.tsdf + i0, make_float4(v[0], v[1], v[2], v[3]));
-        st_stream(P.weight + i0, make_float4(w[0], w[1], w[2], w[3]));
-    }
-    if (P.mask_out) *reinterpret_cast<uchar4*>(P.mask_out + i0) = make_uchar4(m[0], m[1], m[2], m[3]);
-    if (P.frustum_out) *reinterpret_cast<uchar4*>(P.frustum_out + i0) = make_uchar4(f[0], f[1], f[2], f[3]);
 }
 
 // ---- MIXED bricks of the production pass: quad pre-test + a per-warp queue of open voxels ----------------------------------------

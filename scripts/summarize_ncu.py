@@ -13,14 +13,19 @@ import re
 import subprocess
 import sys
 
-STEP_KERNELS = ["nodes_pack_kernel", "region_bounds_kernel", "brick_classify_kernel", "brick_update_kernel", "proj_exact_kernel"]
+STEP_KERNELS = ["nodes_pack_kernel", "region_bounds_kernel", "brick_classify_kernel", "brick_update_kernel", "brick_update_smem_kernel", "proj_exact_kernel"]
 FULL_KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
              "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
              "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
              "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
              "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
              "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
+             "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+             "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+             "smsp__inst_executed_op_global_red.sum", "smsp__inst_executed_op_global_atom.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_atom.sum",
+             "launch__occupancy_limit_registers", "launch__shared_mem_per_block_dynamic",
+             "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]
 
 
 def short(name):
