@@ -28,7 +28,7 @@ constexpr int BRICK_MAXC = 24;        // cached candidate nodes per brick (more 
 constexpr int REGION_X = 16, REGION_Y = 16, REGION_Z = 32;   // 4 x 4 x 1 bricks
 constexpr int REGION_MAXC = 64;                              // distinct nodes cached per region (more -> region unusable)
 constexpr int REGION_PAIR_WORDS = 65;                        // 64*65/2 = 2080 pair bits
-constexpr int REGION_REC_FLOATS = 16;                        // P_ref (row-major 3x4), D[3], valid
+constexpr int REGION_REC_FLOATS = 32;                        // P_ref (row-major 3x4), D[3], code | view 0's QuadView: M (3x4), d[3], unused
 constexpr int BRICK_PAIR_WORDS = 10;   // bit p = i*(i+1)/2 + j (j <= i) of the 24*25/2 = 300 candidate pairs
 constexpr int BRICK_CLS_MIXED = 0xFF;
 constexpr int REGION_MAX_RECT = 4096;   // depth pixels scanned for a whole region (one warp)

@@ -30,6 +30,7 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {
     return *reinterpret_cast<const float4*>(p);
 #endif
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st_stream(float* p, float4 v) {
 #if DFB_STREAM_HINTS
     __stcs(reinterpret_cast<float4*>(p), v);
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(DFB_REGION_THREADS) region_bounds_kernel(const
     if (threadIdx.x < 32) {
         // warp 0: the record, and -- with (P_ref, D_R) in hand -- one attempt to classify the region as a whole; every
         // brick of a region that is SKIP / CLAMP in its entirety inherits that class without any work of its own
-        float rr[REGION_REC_FLOATS];
+        float rr[16];
         for (int t = 0; t < 12; ++t) rr[t] = Pref[t];
         for (int r = 0; r < 3; ++r) {
             float mx = red[0][r];
@@ -411,7 +412,30 @@ __global__ void __launch_bounds__(DFB_REGION_THREADS) region_bounds_kernel(const
             rc = box_classify_views(P, bx, REGION_MAX_RECT, WarpCtx());
         }
         rr[15] = region_code(valid, rc);
-        if (threadIdx.x < REGION_REC_FLOATS) out[threadIdx.x] = rr[threadIdx.x];
+        if (threadIdx.x < 16) {
+            const int l = threadIdx.x;
+            out[l] = l < 12 ? Pref_s[l] : l == 12 ? rr[12] : l == 13 ? rr[13] : l == 14 ? rr[14] : rr[15];
+        }
+    } else if (threadIdx.x < 64) {
+        // warp 1, meanwhile: the update pass's quad pre-test works with lpos = M [x, 1] +- d of view 0 (one-view frames; dfb_brick.h
+        // quad_view_setup) -- composed once per region here instead of once per brick layer there, one entry per lane
+        const int l = threadIdx.x - 32;
+        const float* T = P.vf[0].T;
+        float val = 0.f;
+        if (l < 12) {
+            const int r = l >> 2, cc = l & 3;
+            val = T[4 * r] * Pref_s[cc] + T[4 * r + 1] * Pref_s[4 + cc] + T[4 * r + 2] * Pref_s[8 + cc] + (cc == 3 ? T[4 * r + 3] : 0.f);
+        } else if (l < 15) {
+            const int r = l - 12;
+            float D[3];
+            for (int a = 0; a < 3; ++a) {
+                float mx = red[0][a];
+                for (int wv = 1; wv < DFB_REGION_THREADS / 32; ++wv) mx = fmaxf(mx, red[wv][a]);
+                D[a] = mx + 2e-3f + 2e-6f * P.coord_mag;
+            }
+            val = fabsf(T[4 * r]) * D[0] + fabsf(T[4 * r + 1]) * D[1] + fabsf(T[4 * r + 2]) * D[2] + 8e-6f * P.coord_mag + 1e-3f;
+        }
+        if (l < 16) out[16 + l] = val;
     }
 }
 
@@ -565,8 +589,12 @@ __device__ __forceinline__ void queue_process(const ProjParams& P, const uint8_t
     const int e = Q.n - count + lane;
     uint32_t i = 0;
     int c = CLS_SKIP, mv = 0, fv = 0;
+    float v = 0.f, w = 0.f;
     if (act) {
         i = Q.vox[e];
+        // requested before the classification (some 300 instructions) so that the update below does not wait for them
+        v = P.tsdf[i];
+        w = P.weight[i];
         const uint32_t xy = Q.xy[e];
         const int xs = (int)(xy >> 16), y = (int)(xy & 0xffffu);
         const int z = (int)(i - ((uint32_t)xs * (uint32_t)P.ry + (uint32_t)y) * (uint32_t)P.rz);
@@ -583,7 +611,6 @@ __device__ __forceinline__ void queue_process(const ProjParams& P, const uint8_t
     if (act) {
         if (c == CLS_UNCERTAIN) { mv = 0; fv = 0; }
         if (mv) {
-            float v = P.tsdf[i], w = P.weight[i];
             if (ONEVIEW) clamp_update(v, w, P.tdist_f, P.wmax_f, sc);
             else
                 for (int vi = 0; vi < P.n_views; ++vi)
@@ -604,11 +631,20 @@ template <bool ONEVIEW>
 __device__ __forceinline__ uint32_t mixed_layer_quads(const ProjParams& P, const float* rr, int xs, int y, int z0, uint32_t i0, float sc, int views, int m0,
                                                       int f0) {
     const int lane = threadIdx.x & 31;
-    // lpos = M [x, 1] +- d per view: lane l < 15 composes entry l of view v, the warp shares them by shuffle
+    // lpos = M [x, 1] +- d per view.  One view: region_bounds_kernel left view 0's (M, d) in the region record (one 128-bit
+    // broadcast load per four entries); several views: lane l < 15 composes entry l of view v, the warp shares them by shuffle
     QuadView qv[ONEVIEW ? 1 : DFB_MAX_VIEWS];
     const int nv = ONEVIEW ? 1 : P.n_views;
-    for (int v = 0; v < nv; ++v) {
-        if (!ONEVIEW && !((views >> v) & 1)) continue;
+    if (ONEVIEW) {
+        const float4* q4 = reinterpret_cast<const float4*>(rr + 16);
+        const float4 a = __ldg(q4), b = __ldg(q4 + 1), c = __ldg(q4 + 2), d = __ldg(q4 + 3);
+        qv[0].M[0] = a.x; qv[0].M[1] = a.y; qv[0].M[2] = a.z; qv[0].M[3] = a.w;
+        qv[0].M[4] = b.x; qv[0].M[5] = b.y; qv[0].M[6] = b.z; qv[0].M[7] = b.w;
+        qv[0].M[8] = c.x; qv[0].M[9] = c.y; qv[0].M[10] = c.z; qv[0].M[11] = c.w;
+        qv[0].d[0] = d.x; qv[0].d[1] = d.y; qv[0].d[2] = d.z;
+    }
+    for (int v = 0; v < (ONEVIEW ? 0 : nv); ++v) {
+        if (!((views >> v) & 1)) continue;
         float val = 0.f;
         {
             const float* T = P.vf[v].T;
@@ -756,6 +792,11 @@ __device__ __forceinline__ void update_body(const ProjParams& P, const float* re
             for (uint32_t s = t * share; s < s1; ++s) stream_brick<ONEVIEW>(P, nb, nby, nbz, cls, stream_list[s], dx, dy, dz, sc, vec);
         }
         const bool any = __any_sync(0xffffffffu, om != 0);
+        if (om) {   // the quad's node ids, values and weights are needed a queue round from now, by some other lane of this warp
+            prefetch_l1(P.knn + (size_t)i0 * P.k);
+            prefetch_l1(P.tsdf + i0);
+            prefetch_l1(P.weight + i0);
+        }
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             if (any) {

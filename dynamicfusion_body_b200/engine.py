@@ -241,7 +241,7 @@ class DeviceWarpField:
             rnodes = torch.zeros((nr, 64), dtype=torch.int16, device=self.device)
             rcount = torch.zeros(nr, dtype=torch.uint8, device=self.device)
             rpairs = torch.zeros((nr, 65), dtype=torch.int32, device=self.device)
-            rrec = torch.zeros((nr, 16), dtype=torch.float32, device=self.device)
+            rrec = torch.zeros((nr, 32), dtype=torch.float32, device=self.device)
             _capi.check(_capi.lib().dfb_region_build(_ptr(knn), self.k, res[0], res[1], res[2], x0, x1, _ptr(rnodes), _ptr(rcount),
                                                      _ptr(rpairs), _stream()))
             t = (nodes, count, pairs, rnodes, rcount, rpairs, rrec)

@@ -70,7 +70,7 @@ typedef struct dfb_warpfield {
     const uint16_t* region_nodes; /* [n_regions][64] */
     const uint8_t* region_count;  /* [n_regions], 255 = more than 64 distinct nodes */
     const uint32_t* region_pairs; /* [n_regions][65] pair bit masks */
-    float* region_rec;            /* [n_regions][16] scratch: reference map + deviation bound, rewritten by every update call */
+    float* region_rec;            /* [n_regions][32] scratch: reference map + deviation bound + view 0's composed map, rewritten by every update call */
 } dfb_warpfield;
 
 typedef struct dfb_views {

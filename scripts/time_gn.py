@@ -12,5 +12,5 @@ H, g, c = prob.normal_equations(x, sc.lw, 0.05, huber=True)
 for rep in range(3):
     a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); c2 = torch.cuda.Event(enable_timing=True)
     a.record(); H, g, c = prob.normal_equations(x, sc.lw, 0.05, huber=True); b.record()
-    xn, d, info = prob.solve_step(H, g, x, 1e-3, 400, 1e-9); c2.record(); torch.cuda.synchronize()
+    xn, d, info = prob.solve_step(H, g, x, 1e-4, 400, 1e-9); c2.record(); torch.cuda.synchronize()
 print("blocks", os.environ.get("DFB_PCG_BLOCKS"), "normal_eq %.3f ms  pcg %.3f ms  iters %d  nnzb %d" % (a.elapsed_time(b), b.elapsed_time(c2), int(info[6].item()), prob.pattern()[2]))
