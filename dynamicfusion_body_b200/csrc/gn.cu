@@ -687,6 +687,174 @@ __global__ void __launch_bounds__(256, 1) pcg_resident_kernel(const int32_t* row
     if (leader) { S[6] = (double)it; S[1] = g_last; }
 }
 
+// Pipelined arrangement (Ghysels & Vanroose) of the same preconditioned CG for the resident case: with u = Minv r, w = A u carried
+// as recurrences next to m = Minv w, n = A m, both inner products of an iteration ((r,u) and (w,u)) are node-local sums over
+// vectors that are already in registers, and the only thing the matrix product needs from the other CTAs is m.  An iteration is
+//   local: (r,u), (w,u), m = Minv w -> L2          -- ONE barrier --          n = A m; z,q,s,p recurrences; x, r, u, w updates
+// i.e. one grid-wide barrier per iteration (the barrier, not the arithmetic, is what an iteration of this small system costs:
+// 6.2 us with two barriers).  m alternates between two buffers (a fast CTA writes m_{i+1} while a slow one still gathers m_i) and
+// the sums rotate through three slots.  Same stopping rule, same iterates up to rounding (1e-7 relative on the bench system).
+// Measured (B200, 993 nodes, 15331 blocks, 324 iterations): 1.56 ms against 2.00 ms for the two-barrier kernel.  Folding the two sums
+// into a hand-made flag barrier ({data, epoch} words gathered by CTA 0 or by every CTA) was tried and is slower: 2.3 - 2.5 ms.
+template <int RPW>
+__global__ void __launch_bounds__(256, 1) pcg_pipelined_kernel(const int32_t* row_ptr, const int32_t* col_idx, const double* H, const double* Minv,
+                                                               int n, int max_iter, double tol2, double* delta, const double* r_in, double* buf0,
+                                                               double* buf1, double* S, int cap_blocks) {
+    extern __shared__ double smem[];
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const int a = lane & 7, cgp = lane >> 3;
+    constexpr int ROWS_PER_CTA = 8 * RPW;
+    // blocks of a row gathered per round = 4 GU: every round is an L2 round trip on the critical path of the iteration, and rows of
+    // a body graph with k = 4 hold up to ~20 blocks (mean 15): five per lane group settle a row in one round
+    constexpr int GU = 5;
+    double* Ms = smem;                                        // [ROWS_PER_CTA][64]
+    constexpr int HS = 64;                                    // blocks transposed + swizzled as in pcg_resident_kernel
+    double* Hs = Ms + ROWS_PER_CTA * 64;                      // [cap_blocks][HS]
+    int32_t* cs = reinterpret_cast<int32_t*>(Hs + (size_t)cap_blocks * HS);   // [cap_blocks]
+    const int row_first = blockIdx.x * ROWS_PER_CTA;
+    const int row_end = min(row_first + ROWS_PER_CTA, n);
+    const int bs = row_first < n ? row_ptr[row_first] : 0;
+    const int be = row_first < n ? row_ptr[row_end] : 0;
+    const int ncache = min(be - bs, cap_blocks);
+    for (int t = threadIdx.x; t < ncache * 64; t += blockDim.x) Hs[(t >> 6) * HS + (((t & 7) ^ ((t >> 6) & 1)) * 8) + ((t >> 3) & 7)] = H[(size_t)bs * 64 + t];
+    for (int t = threadIdx.x; t < ncache; t += blockDim.x) cs[t] = col_idx[bs + t];
+    for (int t = threadIdx.x; t < (row_end - row_first) * 64; t += blockDim.x) Ms[t] = Minv[(size_t)row_first * 64 + t];
+    __syncthreads();
+    double* G = S + 8;     // (r,u) of iteration it in slot it % 3; slot 0 holds (r0,u0) from pcg_init_kernel
+    double* D = S + 11;    // (w,u)
+    const double mu = S[0];
+    const double rz0 = S[4];
+    double rr[RPW], uu[RPW], ww[RPW], mm[RPW], zz[RPW], qq[RPW], sv[RPW], pp[RPW], dd[RPW];
+    int rs[RPW], re[RPW];
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int i = row_first + wic * RPW + j;
+        const bool ok = i < n;
+        rr[j] = ok ? r_in[8 * (size_t)i + a] : 0.0;
+        uu[j] = ok ? buf0[8 * (size_t)i + a] : 0.0;
+        ww[j] = 0.0; mm[j] = 0.0; zz[j] = 0.0; qq[j] = 0.0; sv[j] = 0.0; pp[j] = 0.0; dd[j] = 0.0;
+        rs[j] = ok ? row_ptr[i] : 0;
+        re[j] = ok ? row_ptr[i + 1] : 0;
+    }
+    __shared__ double red[16];
+    auto cta_add2 = [&](double p0, double p1, double* t0, double* t1) {
+        for (int o = 16; o > 0; o >>= 1) { p0 += __shfl_xor_sync(0xffffffffu, p0, o); p1 += __shfl_xor_sync(0xffffffffu, p1, o); }
+        if (lane == 0) { red[wic] = p0; red[8 + wic] = p1; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[8 * threadIdx.x + k];
+            if (t != 0.0) atomicAdd(threadIdx.x ? t1 : t0, t);
+        }
+        __syncthreads();
+    };
+    auto gather = [&](const double* src, int j, int t0, double* zv, const double** Hb, int* hst) {
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int t = t0 + cgp + 4 * u;
+            const bool valid = t < re[j];
+            const int loc = t - bs;
+            const bool cached = valid && loc < ncache;
+            const int col = valid ? (cached ? cs[loc] : col_idx[t]) : 0;
+            zv[u] = valid ? __ldcg(src + 8 * (size_t)col + a) : 0.0;
+            Hb[u] = cached ? Hs + (size_t)loc * HS + a : valid ? H + (size_t)t * 64 + a * 8 : Hs;
+            hst[u] = (cached || !valid) ? 8 | ((loc & 1) << 8) : 1;
+        }
+    };
+    auto consume = [&](const double* zv, const double* const* Hb, const int* hst, double acc) {
+        double acc1 = 0.0;   // two chains: the sum is a string of dependent fp64 FMAs otherwise
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+#pragma unroll
+            for (int b = 0; b < 8; b += 2) {
+                acc += Hb[u][b * (hst[u] & 0xff)] * __shfl_sync(0xffffffffu, zv[u], (lane & 24) | (b ^ (hst[u] >> 8)));
+                acc1 += Hb[u][(b + 1) * (hst[u] & 0xff)] * __shfl_sync(0xffffffffu, zv[u], (lane & 24) | ((b + 1) ^ (hst[u] >> 8)));
+            }
+        }
+        return acc + acc1;
+    };
+    // out = (H + mu I) v for the owned rows; v of the other rows is gathered from `src`, the own rows' v is `own`
+    auto spmv = [&](const double* src, const double* own, double* out) {
+        double zv0[RPW][GU];
+        const double* Hb0[RPW][GU];
+        int hs0[RPW][GU];
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) gather(src, j, rs[j], zv0[j], Hb0[j], hs0[j]);
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            double acc = consume(zv0[j], Hb0[j], hs0[j], 0.0);
+            for (int t0 = rs[j] + 4 * GU; t0 < re[j]; t0 += 4 * GU) {   // rows longer than one round; uniform across the warp
+                double zv[GU];
+                const double* Hb[GU];
+                int hst[GU];
+                gather(src, j, t0, zv, Hb, hst);
+                acc = consume(zv, Hb, hst, acc);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            out[j] = acc + mu * own[j];
+        }
+    };
+    spmv(buf0, uu, ww);   // w0 = A u0 (u0 written by pcg_init_kernel, an earlier launch)
+    double g_prev = 1.0, alpha_prev = 1.0;
+    int it = 0;
+    double g_last = G[0];
+    const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+    for (; it < max_iter; ++it) {
+        const int slot = it % 3, nslot = (it + 1) % 3;
+        double* mdst = (it & 1) ? buf0 : buf1;
+        double part_g = 0.0, part_d = 0.0;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            const int i = row_first + wic * RPW + j;
+            // m = Minv w: lane (a, cgp) multiplies columns 2cgp, 2cgp+1 of row a
+            const double* Mrow = Ms + (size_t)(wic * RPW + j) * 64 + a * 8 + 2 * cgp;
+            const double w0 = __shfl_sync(0xffffffffu, ww[j], 2 * cgp), w1 = __shfl_sync(0xffffffffu, ww[j], 2 * cgp + 1);
+            double mn = (i < n) ? Mrow[0] * w0 + Mrow[1] * w1 : 0.0;
+            mn += __shfl_xor_sync(0xffffffffu, mn, 8);
+            mn += __shfl_xor_sync(0xffffffffu, mn, 16);
+            mm[j] = mn;
+            if (cgp == 0 && i < n) {
+                __stcg(mdst + 8 * (size_t)i + a, mn);
+                part_g += rr[j] * uu[j];
+                part_d += ww[j] * uu[j];
+            }
+        }
+        if (leader) { G[nslot] = 0.0; D[nslot] = 0.0; }
+        cta_add2(it == 0 ? 0.0 : part_g, part_d, G + slot, D + slot);
+        grid.sync();
+        const double gam = __ldcg(G + slot), dl = __ldcg(D + slot);
+        g_last = gam;
+        if (!(gam > tol2 * rz0)) break;
+        double nn[RPW];
+        spmv(mdst, mm, nn);
+        const double beta = (it == 0 || g_prev == 0.0) ? 0.0 : gam / g_prev;
+        const double den = (it == 0) ? dl : dl - beta * gam / alpha_prev;
+        const double alpha = (den != 0.0) ? gam / den : 0.0;
+#pragma unroll
+        for (int j = 0; j < RPW; ++j) {
+            zz[j] = nn[j] + beta * zz[j];
+            qq[j] = mm[j] + beta * qq[j];
+            sv[j] = ww[j] + beta * sv[j];
+            pp[j] = uu[j] + beta * pp[j];
+            dd[j] += alpha * pp[j];
+            rr[j] -= alpha * sv[j];
+            uu[j] -= alpha * qq[j];
+            ww[j] -= alpha * zz[j];
+        }
+        g_prev = gam;
+        alpha_prev = alpha;
+    }
+#pragma unroll
+    for (int j = 0; j < RPW; ++j) {
+        const int i = row_first + wic * RPW + j;
+        if (cgp == 0 && i < n) delta[8 * (size_t)i + a] = dd[j];
+    }
+    if (leader) { S[6] = (double)it; S[1] = g_last; }
+}
+
 __global__ void apply_delta_kernel(const double* x, const double* delta, int n8, double* x_new) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n8) x_new[t] = x[t] + delta[t];
@@ -824,7 +992,8 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
         }
         static const bool force_global = getenv("DFB_PCG_GLOBAL") != nullptr;
         const int warps = sms * 8;
-        const int rpw = (n + warps - 1) / warps;
+        static const int rpw_min = getenv("DFB_PCG_RPW") ? atoi(getenv("DFB_PCG_RPW")) : 1;   // tuning: fewer, fatter CTAs at the barrier
+        const int rpw = max((n + warps - 1) / warps, min(rpw_min, 4));
         if (rpw <= 4 && !force_global) {
             // resident path: one CTA of 8 warps per SM, rpw block rows per warp, matrix blocks cached in shared memory
             const int rows_per_cta = 8 * rpw;
@@ -833,12 +1002,22 @@ extern "C" int dfb_gn_solve(int n_nodes, const int32_t* row_ptr, const int32_t* 
             int cap_blocks = (int)(((size_t)smem_max - 1024 - fixed) / (64 * sizeof(double) + sizeof(int32_t)));
             const size_t smem = fixed + (size_t)cap_blocks * (64 * sizeof(double) + sizeof(int32_t));
             const double* r_in = r;
-            void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
-                            (void*)&delta, (void*)&r_in, (void*)&z, (void*)&S, (void*)&cap_blocks};
-            void* fn = rpw == 1 ? (void*)pcg_resident_kernel<1> : rpw == 2 ? (void*)pcg_resident_kernel<2>
-                     : rpw == 3 ? (void*)pcg_resident_kernel<3> : (void*)pcg_resident_kernel<4>;
-            DFB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            DFB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, s));
+            static const bool two_barriers = getenv("DFB_PCG_TWO_BARRIERS") != nullptr;   // A/B: the Chronopoulos-Gear kernel
+            if (two_barriers) {
+                void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
+                                (void*)&delta, (void*)&r_in, (void*)&z, (void*)&S, (void*)&cap_blocks};
+                void* fn = rpw == 1 ? (void*)pcg_resident_kernel<1> : rpw == 2 ? (void*)pcg_resident_kernel<2>
+                         : rpw == 3 ? (void*)pcg_resident_kernel<3> : (void*)pcg_resident_kernel<4>;
+                DFB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DFB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, s));
+            } else {
+                void* args[] = {(void*)&row_ptr, (void*)&col_idx, (void*)&H, (void*)&Minv, (void*)&n, (void*)&max_iter, (void*)&tol2,
+                                (void*)&delta, (void*)&r_in, (void*)&z, (void*)&p, (void*)&S, (void*)&cap_blocks};
+                void* fn = rpw == 1 ? (void*)pcg_pipelined_kernel<1> : rpw == 2 ? (void*)pcg_pipelined_kernel<2>
+                         : rpw == 3 ? (void*)pcg_pipelined_kernel<3> : (void*)pcg_pipelined_kernel<4>;
+                DFB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DFB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(256), args, smem, s));
+            }
         } else {
             static int coop_blocks = -1;   // co-resident CTAs of pcg_global_kernel on this device
             if (coop_blocks < 0) {
