@@ -292,13 +292,19 @@ DFB_HD int voxel_projective_classify(const ProjParams& P, int x, int y, int z, c
 }
 
 // a1 for one voxel, exact tier.
+template <int KT = 0>   // KT > 0: compile-time neighbour count (== P.k)
 DFB_HDN bool voxel_volume_exact(const VolParams& P, int x, int y, int z, const uint16_t* ids16, float* v_io, float* w_io) {
     const float p[3] = {(float)x, (float)y, (float)z};
     int ids[8];
-    for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
+    if (KT > 0) {
+#pragma unroll
+        for (int i = 0; i < (KT > 0 ? KT : 1); ++i) ids[i] = ids16[i];
+    } else {
+        for (int i = 0; i < P.k; ++i) ids[i] = ids16[i];
+    }
     double pw[3];
     float wi = 0.f;
-    warp_ref(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, pw, nullptr, &wi, true);
+    warp_ref<KT>(p, nullptr, ids, P.k, P.node_pos, P.node_dq, P.node_w, P.lw, P.has_lw != 0, P.lw_is_f32 != 0, pw, nullptr, &wi, true);
     double tl = 0.0;
     const bool valid = interpolate_tsdf_ref(pw, P.curr, P.cx, P.cy, P.cz, &tl);
     double v = (double)*v_io, w = (double)*w_io;

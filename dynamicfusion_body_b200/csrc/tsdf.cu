@@ -993,15 +993,18 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
         }
     }
     if (sweep_bits) {
-        // the voxels that did not fit the list: sweep the bitmap, clearing it for the next call
+        // the voxels that did not fit the list: one thread per voxel over the bitmap (a warp = one word, read by all its lanes,
+        // then cleared for the next call), so that a frame that overflowed by a lot still runs coalesced
         const size_t nwords = (nvox + 31) / 32;
-        for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < nwords; wd += (size_t)gridDim.x * blockDim.x) {
-            uint32_t bits = P.overflow_bits[wd];
+        const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        for (size_t wd = warp0; wd < nwords; wd += nwarps) {
+            const uint32_t bits = P.overflow_bits[wd];
             if (!bits) continue;
-            P.overflow_bits[wd] = 0u;
-            while (bits) {
-                const size_t i = wd * 32 + (size_t)(__ffs(bits) - 1);
-                bits &= bits - 1;
+            __syncwarp();
+            if (lane == 0) P.overflow_bits[wd] = 0u;
+            if ((bits >> lane) & 1u) {
+                const size_t i = wd * 32 + (size_t)lane;
                 uint16_t ids[KMAX];
                 if (!P.rigid) load_ids<KMAX>(P.knn, i, kk, ids);
                 exact_voxel<KMAX, KT>(P, i, nvox, plane, ids, P.tsdf[i], P.weight[i]);
@@ -1016,8 +1019,11 @@ __global__ void __launch_bounds__(128, DFB_EXACT_MINB) proj_exact_kernel(const _
 // ------------------------------------------------------------------------------------------------
 // a1
 // ------------------------------------------------------------------------------------------------
+#ifndef DFB_VOL_FAST_MINB
+#define DFB_VOL_FAST_MINB 6   // latency-bound (ids -> node records -> live corners): 3 -> 0.76 ms at 256^3, 4 -> 0.63, 5 / 6 / 8 -> 0.54
+#endif
 template <int KMAX>
-__global__ void __launch_bounds__(256, 3) vol_fast_kernel(const __grid_constant__ VolParams P) {
+__global__ void __launch_bounds__(256, DFB_VOL_FAST_MINB) vol_fast_kernel(const __grid_constant__ VolParams P) {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int xs = blockIdx.z;
@@ -1048,16 +1054,23 @@ __global__ void __launch_bounds__(256, 3) vol_fast_kernel(const __grid_constant_
     if (P.mask_out) P.mask_out[i] = (cls == CLS_CLAMP) ? 1 : 0;
 }
 
-template <int KMAX>
+template <int KMAX, int KT>
 __device__ __forceinline__ void vol_exact_voxel(const VolParams& P, size_t i, size_t plane) {
-    const int xs = (int)(i / plane);
-    const size_t rem = i - (size_t)xs * plane;
-    const int y = (int)(rem / P.rz);
-    const int z = (int)(rem - (size_t)y * P.rz);
+    int xs, y, z;
+    if (plane * (size_t)(P.x1 - P.x0) <= 0xffffffffull) {   // 32-bit index arithmetic
+        const uint32_t i32 = (uint32_t)i, plane32 = (uint32_t)plane, rz32 = (uint32_t)P.rz;
+        const uint32_t xq = i32 / plane32, rem = i32 - xq * plane32, yq = rem / rz32;
+        xs = (int)xq; y = (int)yq; z = (int)(rem - yq * rz32);
+    } else {
+        xs = (int)(i / plane);
+        const size_t rem = i - (size_t)xs * plane;
+        y = (int)(rem / P.rz);
+        z = (int)(rem - (size_t)y * P.rz);
+    }
     uint16_t ids[KMAX];
     if (P.k > 0) load_ids<KMAX>(P.knn, i, P.k, ids);
     float v = P.tsdf[i], w = P.weight[i];
-    const bool upd = voxel_volume_exact(P, xs + P.x0, y, z, ids, &v, &w);
+    const bool upd = voxel_volume_exact<KT>(P, xs + P.x0, y, z, ids, &v, &w);
     if (upd) {
         P.tsdf[i] = v;
         P.weight[i] = w;
@@ -1065,11 +1078,16 @@ __device__ __forceinline__ void vol_exact_voxel(const VolParams& P, size_t i, si
     if (P.mask_out) P.mask_out[i] = upd ? 1 : 0;
 }
 
-template <int KMAX>
-__global__ void __launch_bounds__(128) vol_exact_kernel(const __grid_constant__ VolParams P, int all_mode) {
+#ifndef DFB_VOL_EXACT_MINB
+#define DFB_VOL_EXACT_MINB 8   // measured, 256^3 with every voxel in the band: 4 -> 2.50 ms, 6 -> 2.19 ms, 8 -> 2.04 ms
+#endif
+template <int KMAX, int KT>
+__global__ void __launch_bounds__(128, DFB_VOL_EXACT_MINB) vol_exact_kernel(const __grid_constant__ VolParams P, int all_mode) {
     const size_t nvox = (size_t)(P.x1 - P.x0) * P.ry * P.rz;
     const uint32_t count = P.counters[0];
     const bool overflow = !all_mode && count > P.capacity;
+    // the voxels that did not fit the list are in the bitmap (swept one thread per voxel, see proj_exact_kernel: the reference's own
+    // a1 call, test.py:110, puts EVERY voxel inside the band); without a bitmap the volume is re-classified
     const bool sweep_bits = overflow && P.overflow_bits != nullptr;
     const bool use_list = !all_mode && (!overflow || sweep_bits);
     const size_t n = use_list ? (size_t)(overflow ? P.capacity : count) : nvox;
@@ -1085,18 +1103,20 @@ __global__ void __launch_bounds__(128) vol_exact_kernel(const __grid_constant__ 
             float wi;
             if (voxel_volume_classify<KMAX>(P, xs + P.x0, (int)(rem / P.rz), (int)(rem % P.rz), ids, &wi) != CLS_UNCERTAIN) continue;
         }
-        vol_exact_voxel<KMAX>(P, i, plane);
+        vol_exact_voxel<KMAX, KT>(P, i, plane);
         ++done;
     }
     if (sweep_bits) {
         const size_t nwords = (nvox + 31) / 32;
-        for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < nwords; wd += (size_t)gridDim.x * blockDim.x) {
-            uint32_t bits = P.overflow_bits[wd];
+        const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+        const int lane = threadIdx.x & 31;
+        for (size_t wd = warp0; wd < nwords; wd += nwarps) {
+            const uint32_t bits = P.overflow_bits[wd];
             if (!bits) continue;
-            P.overflow_bits[wd] = 0u;
-            while (bits) {
-                vol_exact_voxel<KMAX>(P, wd * 32 + (size_t)(__ffs(bits) - 1), plane);
-                bits &= bits - 1;
+            __syncwarp();
+            if (lane == 0) P.overflow_bits[wd] = 0u;
+            if ((bits >> lane) & 1u) {
+                vol_exact_voxel<KMAX, KT>(P, wd * 32 + (size_t)lane, plane);
                 ++done;
             }
         }
@@ -1354,8 +1374,10 @@ extern "C" int dfb_tsdf_update_volume(const dfb_volume* vol, const dfb_warpfield
         if (mode == DFB_MODE_FAST_ONLY) return DFB_OK;
     }
     const int all = mode == DFB_MODE_EXACT ? 1 : 0;
-    if (P.k <= 4) vol_exact_kernel<4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
-    else vol_exact_kernel<8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    if (P.k == 4) vol_exact_kernel<4, 4><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else if (P.k == 8) vol_exact_kernel<8, 8><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else if (P.k <= 4) vol_exact_kernel<4, 0><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
+    else vol_exact_kernel<8, 0><<<exact_blocks(nvox), 128, 0, s>>>(P, all);
     DFB_LAUNCH_CHECK("vol_exact_kernel");
     return DFB_OK;
 }
