@@ -350,7 +350,9 @@ def run_ours(args):
 
     # ---- roofline leg: every kernel of the step timed alone with CUDA events on its stream ----
     kk = 4 if args.k <= 4 else 8
-    prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_update_smem_kernel<%d>" % kk, _capi.MODE_BRICK_UPDATE),
+    # the update pass as tsdf.cu dispatches it: node table in shared memory (TMA) for several views or k > 4, global records otherwise
+    upd_name = ("brick_update_smem_kernel<%d>" % kk) if (sc.depths.shape[0] > 1 or args.k > 4) else ("brick_update_kernel<%d, 1, 1>" % kk)
+    prod = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), (upd_name, _capi.MODE_BRICK_UPDATE),
             ("proj_exact_kernel<%d>" % kk, _capi.MODE_LIST_ONLY)]
     parts = [("region_bounds_kernel+brick_classify_kernel", _capi.MODE_BRICK_CLASSIFY), ("brick_stream_kernel", _capi.MODE_BRICK_STREAM),
              ("brick_mixed_kernel<%d>" % kk, _capi.MODE_BRICK_MIXED)]

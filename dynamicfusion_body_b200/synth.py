@@ -189,7 +189,7 @@ def mesh_sdf_volume(shape, verts, normals, trunc=None, chunk=1 << 20):
     for s in range(0, n, chunk):
         ii = idx[s:s + chunk]
         g = np.stack(np.unravel_index(ii, shape), 1).astype(np.float64)
-        _, nn = tree.query(g)
+        _, nn = tree.query(g, workers=-1)
         out[s:s + chunk] = ((g - verts[nn]) * normals[nn]).sum(1)
     out = out.reshape(shape)
     if trunc is not None:
