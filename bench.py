@@ -477,19 +477,24 @@ def measured_traffic(kernel_name):
     if not os.path.isfile(path):
         return None
     base = kernel_name.split("<")[0]
-    rd = wr = None
-    active = False
+    # the summary may hold several captures of the kernel (the full grid and one rank's slab): the longest launch is the full grid
+    best, cur = None, None
     for line in open(path):
         if line.startswith("## "):
-            active = base in line
-        elif active:
+            cur = {"ms": 0.0} if base in line else None
+            if cur is not None and (best is None or best.get("rd") is None):
+                best = best or cur
+        elif cur is not None:
+            m = re.match(r"- gpu__time_duration\.sum = ([0-9.]+) (\w+)", line)
+            if m:
+                cur["ms"] = float(m.group(1)) * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(m.group(2), 1.0)
             m = re.match(r"- dram__bytes_(read|write)\.sum = ([0-9.]+) (\w+)", line)
             if m:
                 mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
-                if m.group(1) == "read":
-                    rd = float(m.group(2)) * mult
-                else:
-                    wr = float(m.group(2)) * mult
+                cur["rd" if m.group(1) == "read" else "wr"] = float(m.group(2)) * mult
+                if "rd" in cur and "wr" in cur and (best is None or "rd" not in best or cur["ms"] > best["ms"]):
+                    best = cur
+    rd, wr = (best or {}).get("rd"), (best or {}).get("wr")
     return None if rd is None or wr is None else int(rd + wr)
 
 

@@ -717,7 +717,19 @@ __global__ void __launch_bounds__(256, 1) pcg_pipelined_kernel(const int32_t* ro
     const int bs = row_first < n ? row_ptr[row_first] : 0;
     const int be = row_first < n ? row_ptr[row_end] : 0;
     const int ncache = min(be - bs, cap_blocks);
-    for (int t = threadIdx.x; t < ncache * 64; t += blockDim.x) Hs[(t >> 6) * HS + (((t & 7) ^ ((t >> 6) & 1)) * 8) + ((t >> 3) & 7)] = H[(size_t)bs * 64 + t];
+    // One block row per warp and every block of the CTA cached (the usual case: <= 1184 nodes): the product runs without
+    // shuffles.  Lane (a, bq) owns row a and the column pair (2bq, 2bq+1) of EVERY block of its row, reads the two matching
+    // components of the neighbour's vector with one 16-byte load, and the four pair sums meet in two shuffles at the end.  Blocks
+    // are stored as [column parity][bq][a] so that the 32 lanes of a 64-bit access sweep 32 consecutive doubles (2 wavefronts).
+    const bool direct = RPW == 1 && be - bs <= cap_blocks;
+    if (direct) {
+        for (int t = threadIdx.x; t < ncache * 64; t += blockDim.x) {
+            const int ra = (t >> 3) & 7, cb = t & 7;     // H is row-major: element (ra, cb) of block t >> 6
+            Hs[(t >> 6) * HS + (cb & 1) * 32 + (cb >> 1) * 8 + ra] = H[(size_t)bs * 64 + t];
+        }
+    } else {
+        for (int t = threadIdx.x; t < ncache * 64; t += blockDim.x) Hs[(t >> 6) * HS + (((t & 7) ^ ((t >> 6) & 1)) * 8) + ((t >> 3) & 7)] = H[(size_t)bs * 64 + t];
+    }
     for (int t = threadIdx.x; t < ncache; t += blockDim.x) cs[t] = col_idx[bs + t];
     for (int t = threadIdx.x; t < (row_end - row_first) * 64; t += blockDim.x) Ms[t] = Minv[(size_t)row_first * 64 + t];
     __syncthreads();
@@ -777,6 +789,33 @@ __global__ void __launch_bounds__(256, 1) pcg_pipelined_kernel(const int32_t* ro
     };
     // out = (H + mu I) v for the owned rows; v of the other rows is gathered from `src`, the own rows' v is `own`
     auto spmv = [&](const double* src, const double* own, double* out) {
+        if (RPW == 1 && direct) {
+            constexpr int GD = 20;                       // blocks in flight per round
+            const int bq = cgp;
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int t0 = rs[0]; t0 < re[0]; t0 += GD) {
+                double2 zr[GD];
+#pragma unroll
+                for (int u = 0; u < GD; ++u) {
+                    const int t = t0 + u;
+                    zr[u] = t < re[0] ? __ldcg(reinterpret_cast<const double2*>(src + 8 * (size_t)cs[t - bs]) + bq) : make_double2(0.0, 0.0);
+                }
+#pragma unroll
+                for (int u = 0; u < GD; ++u) {
+                    const int t = t0 + u;
+                    if (t < re[0]) {
+                        const double* hb = Hs + (size_t)(t - bs) * HS + bq * 8 + a;
+                        acc0 += hb[0] * zr[u].x;
+                        acc1 += hb[32] * zr[u].y;
+                    }
+                }
+            }
+            double acc = acc0 + acc1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            out[0] = acc + mu * own[0];
+            return;
+        }
         double zv0[RPW][GU];
         const double* Hb0[RPW][GU];
         int hs0[RPW][GU];

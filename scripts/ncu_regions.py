@@ -1,7 +1,8 @@
 """Executed instructions and stall samples of one kernel of an `ncu --set full --import-source on` report, grouped by the source
 function each SASS instruction was inlined from (nvdisasm -gi line info of the SAME build of libdfb_b200.so).
 
-  python scripts/ncu_regions.py <report.ncu-rep> <kernel regex> <mangled-name fragment> [source.cu] > profiles/<name>.md
+  [SKIP=n] [LINES=m] python scripts/ncu_regions.py <report.ncu-rep> <kernel regex> <mangled-name fragment> [source.cu] > profiles/<name>.md
+  (SKIP: launches of that kernel to skip in the report; LINES: rows of the per-line table)
 
 The SASS page of the report and the disassembly of the cubin list the kernel's instructions in the same order, 16 bytes apart;
 rows are joined by offset.  Function extents come from a scan of the sources for top-level definitions."""
@@ -95,7 +96,7 @@ def main():
         return f if not f.endswith((".cu", ".h")) or f not in ext else "%s:%d" % (f, ln)
 
     dis = disasm(fragment, source)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + kregex, "--launch-count", "1"],
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "-k", "regex:" + kregex, "--launch-skip", os.environ.get("SKIP", "0"), "--launch-count", "1"],
                          capture_output=True, text=True).stdout
     lines = raw.split("\n")
     h = [i for i, l in enumerate(lines) if l.startswith('"Address"')][0]
