@@ -636,6 +636,21 @@ def bench_configs(args, dev):
     stt = vols[0].workspace.stats()
     out["c2_a3_256"] = line(ms, extra={"path": "Fusion.fuseFrame (a3: warp + projective update), %d nodes k=4, 1 view" % sc.n_nodes,
                                        "deferred_fraction": stt["deferred"] / nvox, "bricks_mixed_fraction": stt["bricks_mixed"] / stt["bricks"]})
+    # the same frame with the camera along x and y: every other scene looks along z, the long axis of the 4x4x32 bricks
+    axes = {"z": {"ms_per_frame": ms, "bricks_mixed_fraction": stt["bricks_mixed"] / stt["bricks"], "deferred_fraction": stt["deferred"] / nvox}}
+    for ax in ("x", "y"):
+        sa = synth.make_scene(res=R, k=4, n_nodes=1000, seed=0, background=True, view_axis=ax)
+        da = torch.from_numpy(sa.depths).to(dev)
+        va = engine.make_views(da, sa.K, sa.Kinv, sa.extrinsics)
+
+        def a3x():
+            i = it["i"]; it["i"] += 1
+            wf.set_dq(dqs[i % 15])
+            engine.update_projective(vols[i % n_rot], wf, sa.lw, da, sa.K, sa.Kinv, sa.extrinsics, sa.tdist, views=va)
+        msa = _event_ms(a3x, 30, 8)
+        sta = vols[0].workspace.stats()
+        axes[ax] = {"ms_per_frame": msa, "bricks_mixed_fraction": sta["bricks_mixed"] / sta["bricks"], "deferred_fraction": sta["deferred"] / nvox}
+    out["c2_a3_256"]["view_axes"] = axes
     # configs[1] as profiled by the reference (profiles/updateTSDF_*): Fusion.updateTSDF against a live TSDF VOLUME (a1)
     nw = np.full(sc.n_nodes, np.float32(sc.node_w))
     wv = synth.blend_warp(sc.vertices, sc.node_pos, sc.node_dq, nw, sc.vert_knn, lw=None)

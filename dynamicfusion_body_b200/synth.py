@@ -232,10 +232,11 @@ class Scene:
 
 def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=480, cols=640, tdist=None,
                max_disp=0.3, lw_dtype=np.float64, unit_init=False, mesh_path=None,
-               focal=None, cam_dist=1.7, background=False):
+               focal=None, cam_dist=1.7, background=False, view_axis="z"):
     """Seeded benchmark / test scene.  `radius` in units of the 64^3 mesh; either `radius` or
     `n_nodes` (bisection on the radius) may be given.  One view: the global rigid dq `lw` is the camera
-    extrinsic; several views: `lw` is a small rigid motion and cameras sit on a ring (extrinsics)."""
+    extrinsic; several views: `lw` is a small rigid motion and cameras sit on a ring (extrinsics).  `view_axis` (one view): the
+    grid axis the camera looks along -- "z" is the long axis of the update pass's 4x4x32 bricks, "x" / "y" look across them."""
     rng = np.random.default_rng(seed)
     v64, nrm, faces = load_body_mesh(mesh_path)
     scale = (res - 1) / 64.0
@@ -271,7 +272,9 @@ def make_scene(res=64, k=4, radius=None, n_nodes=None, seed=0, n_views=1, rows=4
     Kinv = np.linalg.inv(K)
     dist = cam_dist * res
     if n_views == 1:
-        E = look_at_extrinsic(centre + np.array([0.15 * res, -0.1 * res, -dist]), centre)
+        off = {"z": np.array([0.15 * res, -0.1 * res, -dist]), "x": np.array([-dist, -0.1 * res, 0.15 * res]),
+               "y": np.array([0.15 * res, -dist, -0.1 * res])}[view_axis]
+        E = look_at_extrinsic(centre + off, centre, up=(0.0, 0.0, 1.0) if view_axis == "y" else (0.0, 1.0, 0.0))
         lw = se3_to_dq(E[:, :3], E[:, 3])
         extr = None
     else:

@@ -106,6 +106,46 @@ def test_projective_single_view(small_scene, mode, fresh):
         assert st["deferred"] < 0.5 * R ** 3
 
 
+@pytest.mark.parametrize("axis", ["x", "y"])
+def test_projective_camera_across_the_bricks(axis):
+    """The camera of every other scene looks along z, the long axis of the 4x4x32 bricks: the same bars with the
+    camera along x and y, where a brick spans 32 voxels ACROSS the image -- masks / frustum bits bit-exact against the oracle,
+    values within 1e-5 tdist, hybrid == all-exact bit for bit.  (How the brick shape fares on each axis is a bench number:
+    `view_axes` in the bench line.)"""
+    torch, engine, _ = _engine()
+    import scenes
+    from dynamicfusion_body_b200 import synth
+    from oracle import tsdf as ot
+    R = 64
+    sc = synth.make_scene(res=R, k=4, n_nodes=300, seed=2, rows=96, cols=128, background=True, view_axis=axis)
+    res = (R, R, R)
+    vox, idx, tie = scenes.oracle_knn(res, sc.node_pos, sc.k)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=sc.tdist)
+    nw = np.full(sc.n_nodes, sc.node_w)
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, sc.node_pos, sc.node_dq,
+                                           nw, sc.lw, sc.depths, sc.K, sc.Kinv, sc.tdist)
+    assert 0.02 < om[0].mean() < 0.98
+    wf = _wf(engine, sc)
+    depths = torch.from_numpy(sc.depths).cuda()
+    out = []
+    for mode in (0, 1):
+        vol = engine.DeviceVolume(res, tsdf=t0, weight=w0)
+        mask, frus = engine.update_projective(vol, wf, sc.lw, depths, sc.K, sc.Kinv, None, sc.tdist, mode=mode, want_masks=True)
+        torch.cuda.synchronize()
+        out.append((vol.tsdf.cpu().numpy().ravel(), vol.weight.cpu().numpy().ravel(), mask.cpu().numpy(), frus.cpu().numpy()))
+        if mode == 0:
+            st = vol.workspace.stats()
+            assert st["deferred"] < 0.5 * R ** 3 and st["bricks_mixed"] < st["bricks"], st
+    gv, gw, mask, frus = out[0]
+    ok = ~tie
+    assert np.array_equal(scenes.bits(mask, 0)[ok], om[0][ok])
+    assert np.array_equal(scenes.bits(frus, 0)[ok], ofr[0][ok])
+    assert np.abs(gv - ov)[ok].max() <= TSDF_TOL * sc.tdist
+    assert (np.abs(gw - ow) / np.maximum(1, ow))[ok].max() <= W_RTOL
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
 def test_projective_hybrid_equals_exact_bitwise(small_scene):
     """The fp32 classify tier must never change a result: hybrid == all-exact, bit for bit."""
     torch, engine, _ = _engine()

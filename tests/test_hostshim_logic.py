@@ -171,6 +171,30 @@ def test_brick_culling_is_conservative():
     assert om[0][(cv != 0) & (cv != 255)].all()          # CLAMP bricks contain only updated voxels
 
 
+@pytest.mark.parametrize("axis", ["x", "y"])
+def test_brick_culling_camera_across_the_bricks(axis):
+    """The same conservativeness with the camera along x / y (a 4x4x32 brick then spans 32 voxels across the image): masks and
+    frustum bits equal the oracle's with bricks, regions and the quad pre-test on; SKIP / CLAMP bricks hold what they claim."""
+    s = synth.make_scene(res=64, k=4, n_nodes=300, seed=2, background=True, rows=96, cols=128, view_axis=axis)
+    R = s.res
+    from scipy.spatial import cKDTree
+    vox = ot.voxel_grid((R, R, R))
+    _, idx = cKDTree(s.node_pos.astype(np.float64)).query(vox.astype(np.float64), k=4)
+    t0, w0 = scenes.initial_state(R ** 3, tdist=s.tdist)
+    nw = np.full(s.n_nodes, s.node_w)
+    ov, ow, om, ofr = ot.update_projective(t0.astype(np.float64), w0.astype(np.float64), vox, idx, s.node_pos, s.node_dq, nw, s.lw,
+                                           s.depths, s.K, s.Kinv, s.tdist)
+    wf = hs.HostWarpField(s.node_pos, s.node_dq, np.float32(s.node_w), 4, knn=idx, lw=s.lw)
+    cv = hs.set_bricks(idx, 4, (R, R, R), enable=True, regions=True)
+    tv, tw = t0.copy(), w0.copy()
+    mask, frus, cls, nunc = hs.update_projective(tv, tw, (R, R, R), wf, s.depths, s.K, s.Kinv, s.tdist)
+    hs.set_bricks(enable=False)
+    assert np.array_equal(scenes.bits(mask, 0), om[0]) and np.array_equal(scenes.bits(frus, 0), ofr[0])
+    assert np.abs(tv - ov).max() <= 1e-5 * s.tdist
+    assert (cv != 255).any()                              # (at 64^3 a 32-voxel brick is half the grid: most bricks are MIXED on any axis)
+    assert not (om[0] & (cv == 0)).any() and om[0][(cv != 0) & (cv != 255)].all()
+
+
 @pytest.mark.parametrize("case", ["zero_dq", "w_tiny", "w_small", "q5_lw32"])
 def test_degenerate_blends(case):
     """Blend weights that vanish in the reference: `w * dg_dq` is a float32 product (numpy weak scalar), so weights below the
