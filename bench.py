@@ -729,9 +729,9 @@ def bench_frame_loop(args, dev):
         t0 = time.perf_counter()
         fn()
         torch.cuda.synchronize()
-        stages[name] = stages.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        stages.setdefault(name, []).append(1e3 * (time.perf_counter() - t0))
 
-    n = 3
+    n = 5
     for it in range(n + 1):
         if it == 1:
             stages = {}                                                # the first pass is a warm-up (module loads, allocator growth)
@@ -739,7 +739,7 @@ def bench_frame_loop(args, dev):
         timed("solve_ms", lambda: fus.solve(regularization_weight=0.5, method='cnn', precompute_lw=False, gn_iterations=5))
         timed("fuseFrame_ms", lambda: fus.fuseFrame(depth, extrinsics=sc.extrinsics))
         timed("update_graph_ms", lambda: fus.update_graph())
-    stages = {k: v / n for k, v in stages.items()}
+    stages = {k: float(np.median(v)) for k, v in stages.items()}      # wall-clock stages: the median of 5 passes (one host hiccup is not the loop)
     stages["total_ms"] = float(sum(stages.values()))
     stages["config"] = ("256^3, %d nodes -> %d after update_graph, %d canonical vertices, 5 Gauss-Newton iterations per solve, surface "
                         "extraction (step 3) + node re-sampling + incremental kNN revision inside update_graph" % (sc.n_nodes, fus._wf.n_nodes, len(fus._vertices)))
