@@ -145,3 +145,20 @@ def test_flat_normal_equation_views():
     assert d.flat_normal_equations(H.clone(), g, c) is None
     H2, g2, c2 = d.allreduce_normal_equations(H, g, c)          # no process group: identity
     assert H2 is H and torch.equal(f, torch.arange(210, dtype=torch.float64))
+
+
+def test_scene_view_axis_and_traffic_parser():
+    """synth.make_scene(view_axis=...) puts the single camera on the named grid axis, and bench.measured_traffic reads the dominant
+    kernel's DRAM bytes of the FULL-grid launch out of the committed ncu summary (which also holds one rank's slab launches)."""
+    from dynamicfusion_body_b200 import synth
+    import bench
+    for ax, col in (("z", 2), ("x", 0), ("y", 1)):
+        sc = synth.make_scene(res=32, k=4, n_nodes=60, seed=1, rows=24, cols=32, view_axis=ax)
+        # camera z axis in grid coordinates = third row of the rotation of lw
+        w, x, y, z = (float(v) for v in sc.lw[:4])
+        zc = np.array([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)])
+        assert abs(zc[col]) > 0.95 and (sc.depths != 0).any(), (ax, zc)
+    t = bench.measured_traffic("brick_update_kernel<4, 1, 1>")
+    if t is not None:                                     # the summary is committed with the round's profiles
+        assert 5e8 < t < 1.2e9, t                         # 16 B x the ~56 M voxels of the streamed + mixed bricks, not the slab's 43 MB
+    assert bench.measured_traffic("no_such_kernel") is None
