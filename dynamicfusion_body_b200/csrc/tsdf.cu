@@ -295,7 +295,10 @@ __global__ void __launch_bounds__(256) region_build_kernel(const uint16_t* knn, 
 #define DFB_REGION_THREADS 96   // measured at 512^3: 64 -> 0.153, 96 -> 0.146, 128 -> 0.157 ms (region + brick classification)
 #endif
 static_assert(DFB_REGION_THREADS >= REGION_MAXC && DFB_REGION_THREADS % 32 == 0 && DFB_REGION_THREADS <= 128, "one thread per cached node");
-__global__ void __launch_bounds__(DFB_REGION_THREADS) region_bounds_kernel(const __grid_constant__ ProjParams P, const uint16_t* region_nodes,
+#ifndef DFB_REGION_MINB
+#define DFB_REGION_MINB 16   // CTAs per SM (40 registers): the kernel is a chain of dependent phases; measured at 512^3, region + brick
+#endif                        // classification: unbounded (64 registers, 10 CTAs) 0.153 ms, 12 -> 0.150, 16 -> 0.141, 20 -> 0.144
+__global__ void __launch_bounds__(DFB_REGION_THREADS, DFB_REGION_MINB) region_bounds_kernel(const __grid_constant__ ProjParams P, const uint16_t* region_nodes,
                                                             const uint8_t* region_count, const uint32_t* region_pairs, int nry, int nrz,
                                                             float* region_rec) {
     const float4* node_rec = P.node_rec;
@@ -440,8 +443,13 @@ __global__ void __launch_bounds__(DFB_REGION_THREADS) region_bounds_kernel(const
 }
 
 // 8 lanes per brick, four bricks per warp (lanes split the candidate-node pairs and the depth pixels; dfb_brick.h)
+#ifdef DFB_CLASSIFY_MINB   // measured: 12 / 16 CTAs per SM (40 / 32 registers) do not beat the compiler's own 56 registers
+#define DFB_CLASSIFY_BOUNDS __launch_bounds__(128, DFB_CLASSIFY_MINB)
+#else
+#define DFB_CLASSIFY_BOUNDS __launch_bounds__(128)
+#endif
 template <int CLASSIFY_G>
-__global__ void __launch_bounds__(128) brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
+__global__ void DFB_CLASSIFY_BOUNDS brick_classify_kernel(const __grid_constant__ ProjParams P, const uint16_t* brick_nodes,
                                                              const uint8_t* brick_count, const uint32_t* brick_pairs, const float* region_rec,
                                                              int nbx, int nby, int nbz, uint8_t* cls_out, uint32_t* stream_list,
                                                              uint32_t* mixed_list) {

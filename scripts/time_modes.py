@@ -9,10 +9,11 @@ k = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 V = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 sc = synth.make_scene(res=R, k=k, n_nodes=N, seed=0, background=True, n_views=V)
 wf = engine.DeviceWarpField(k); wf.set_nodes(sc.node_pos, sc.node_dq, np.float32(sc.node_w))
-vol = engine.DeviceVolume((R, R, R), fill=sc.tdist)
+x0, x1 = (int(v) for v in os.environ.get("SLAB", "0,%d" % R).split(","))     # SLAB=112,168: one rank's x-slab of the strong-scaling run
+vol = engine.DeviceVolume((R, R, R), x0, x1, fill=sc.tdist)
 depths = torch.from_numpy(sc.depths).cuda()
 views = engine.make_views(depths, sc.K, sc.Kinv, sc.extrinsics)
-wf.brick_nodes(vol.res, 0, R); torch.cuda.synchronize()
+wf.brick_nodes(vol.res, x0, x1); torch.cuda.synchronize()
 modes = [("classify", 4), ("update", 7), ("exact", 3), ("full", 0)]
 acc = {n: [] for n, _ in modes}
 for i in range(8):
@@ -23,4 +24,4 @@ for i in range(8):
         ev[j + 1].record()
     torch.cuda.synchronize()
     for j, (n, _) in enumerate(modes): acc[n].append(ev[j].elapsed_time(ev[j + 1]))
-print("R=%d N=%d k=%d V=%d G=%s" % (R, sc.n_nodes, k, V, os.environ.get("DFB_CLASSIFY_G", "8")), {n: round(float(np.mean(v[2:])), 4) for n, v in acc.items()}, vol.workspace.stats())
+print("R=%d N=%d k=%d V=%d slab=[%d,%d)" % (R, sc.n_nodes, k, V, x0, x1), {n: round(float(np.mean(v[2:])), 4) for n, v in acc.items()}, vol.workspace.stats())
