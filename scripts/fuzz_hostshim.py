@@ -22,7 +22,7 @@ for seed in range(seed0, seed0 + n_cases):
     sc = copy.copy(synth.make_scene(res=R, k=k, n_nodes=int(rng.integers(max(k + 1, 20), 160)), seed=seed, rows=int(rng.choice([48, 96])),
                                     cols=int(rng.choice([64, 128])), n_views=views, max_disp=max_disp, background=bool(rng.integers(2)),
                                     cam_dist=float(rng.choice([0.9, 1.7, 3.0])), unit_init=bool(rng.random() < 0.15),
-                                    lw_dtype=np.float32 if rng.random() < 0.3 else np.float64))
+                                    lw_dtype=np.float32 if rng.random() < 0.3 else np.float64, view_axis=str(rng.choice(["z", "z", "x", "y"]))))
     if rng.random() < 0.4:                                            # rotating nodes on top of the smooth field
         ax = rng.normal(size=(sc.n_nodes, 3)); ang = np.deg2rad(rng.uniform(0, 6, sc.n_nodes))
         extra = synth.axis_angle_dq(ax, ang, rng.normal(size=(sc.n_nodes, 3)) * max_disp * 0.3).astype(np.float32)
